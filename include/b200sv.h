@@ -1,0 +1,204 @@
+/*
+ * b200sv — C-ABI of the B200-native state-vector backend for qadence.
+ *
+ * The reference (pasqal-io/qadence v1.11.5) is 100 % Python and has no FFI: its hot path calls the
+ * third-party `pyqtorch` package, which executes one `torch.einsum` per gate.  Every entry point
+ * below therefore cites the *reference call site it replaces* (paths relative to /root/reference).
+ * A maintainer binds these with `ctypes`; no torch types cross this boundary:
+ * plain device pointers, sizes, a dtype enum and a `cudaStream_t` passed as `void*`.
+ *
+ * Conventions
+ *   - states are `[batch][2^n]` interleaved complex (re, im), float32 or float64 per component,
+ *     batch-major, basis index bit (n-1-q) <-> qubit q (qubit 0 = most significant bit;
+ *     tests/backends/test_endianness.py:113-138);
+ *   - "bit position" always means the position in the basis index (0 = least significant);
+ *   - parameter tables are `double[n_slots][batch]` on the device;
+ *   - every function returns 0 on success, a positive `cudaError_t`, or a negative B200SV_E_* code;
+ *     nothing throws, nothing allocates device memory (callers pass workspaces), all work is
+ *     enqueued on the given stream and the call returns without synchronising.
+ */
+#ifndef B200SV_H
+#define B200SV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SV_ABI_VERSION 1
+
+enum { B200SV_C64 = 0, B200SV_C128 = 1 };
+
+enum {
+  B200SV_E_ARG = -1,      /* invalid argument */
+  B200SV_E_UNSUPPORTED = -2,
+  B200SV_E_NODEVICE = -3,
+};
+
+/* ---- fused sweep plan records (built by qadence_b200/plan.py, packed little-endian) ---------- */
+
+enum {
+  B200SV_GK_MAT = 0,   /* general complex 2x2 from the constant pool (4 complex128 at cidx)        */
+  B200SV_GK_REAL = 1,  /* real 2x2 from the constant pool (H, ...): 4 doubles packed in 2 complex  */
+  B200SV_GK_RX = 2,    /* exp(-i θ X/2), θ = params[slot][b] or constant at cidx                   */
+  B200SV_GK_RY = 3,
+  B200SV_GK_RZ = 4,
+  B200SV_GK_PHASE = 5, /* diag(1, e^{iθ})                                                           */
+  B200SV_GK_DIAG = 6,  /* diag(d0, d1) from the constant pool (Z, S, T, N, ...)                    */
+  B200SV_GK_X = 7,     /* Pauli X as a register permutation (CNOT / Toffoli with controls)         */
+  B200SV_GK_SWAP = 8,  /* swap of two register bits (SWAP / CSWAP)                                  */
+  B200SV_GK_SCALE = 9  /* ψ <- s ψ, s = params[slot][b] or complex constant at cidx                */
+};
+
+#define B200SV_GF_GRAD 1 /* gate.flags: parametric gate whose gradient is requested (adjoint)      */
+
+typedef struct b200sv_gate {   /* 48 bytes */
+  int32_t kind;       /* B200SV_GK_*                                                               */
+  int32_t a;          /* register index (0..r-1) of the target inside its round; -1: external      */
+  int32_t a2;         /* second register index (SWAP), else -1                                     */
+  int32_t ext_bit;    /* a == -1: global bit position of a diagonal gate's target                  */
+  uint64_t ctrl_ext;  /* all-ones controls outside the round's register bits (global bit mask)     */
+  int32_t ctrl_reg;   /* all-ones controls inside the round's register bits (register-index mask)  */
+  int32_t slot;       /* parameter-table row, or -1 when the parameter is a constant               */
+  int32_t cidx;       /* constant-pool offset in complex128 units, or -1                           */
+  int32_t grad_row;   /* adjoint: row of the gradient table this gate accumulates into, or -1      */
+  int32_t flags;
+  int32_t pad;
+} b200sv_gate;
+
+typedef struct b200sv_round {  /* 32 bytes */
+  int32_t first_gate; /* absolute index into the gate array                                        */
+  int32_t n_gates;
+  uint8_t regpos[4];  /* tile-local bit positions held in registers (ascending)                    */
+  uint8_t thrpos[12]; /* tile-local bit position of thread-index bit i                             */
+  int32_t pad[2];
+} b200sv_round;
+
+typedef struct b200sv_sweep {  /* 96 bytes: one kernel launch = one read + one write of the state  */
+  int32_t m;            /* tile bits: 2^m amplitudes staged in shared memory per CTA               */
+  int32_t r;            /* register bits: 2^r amplitudes per thread per round                      */
+  int32_t first_round;
+  int32_t n_rounds;
+  int32_t first_gate;
+  int32_t n_gates;
+  int32_t n_outer;      /* = n_local - m                                                           */
+  int32_t pad;
+  uint8_t tile_bits[16];  /* global bit position of tile-local bit i (ascending)                   */
+  uint8_t outer_bits[48]; /* global bit positions enumerated by the CTA index (ascending)          */
+} b200sv_sweep;
+
+/* Device-resident plan: the three arrays above plus the constant pool, uploaded once at convert
+ * time (replaces the nn.Module tree built by backends/pyqtorch/convert_ops.py:177-351). */
+typedef struct b200sv_plan {
+  const b200sv_sweep* sweeps;   /* device */
+  const b200sv_round* rounds;   /* device */
+  const b200sv_gate* gates;     /* device */
+  const double* consts;         /* device, complex128 pool as (re, im) pairs */
+  const b200sv_sweep* sweeps_host; /* host copy of `sweeps` (launch geometry) */
+  int32_t n_sweeps;
+  int32_t pad;
+} b200sv_plan;
+
+/* ---- Pauli-sum records (observables, Rydberg / Pauli-like HamEvo generators) ----------------- */
+typedef struct b200sv_pterm {  /* 32 bytes: coef * (-i)^{nY} * (-1)^{popc(i & zmask)} * psi[i ^ xmask] */
+  uint64_t xmask;     /* bit positions carrying X or Y */
+  uint64_t zmask;     /* bit positions carrying Z or Y */
+  int32_t coef_row;   /* row of the coefficient table */
+  int32_t n_y;        /* number of Y factors (phase (-i)^{n_y}) */
+  int32_t pad[2];
+} b200sv_pterm;
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+
+int b200sv_abi_version(void);
+/* number of SMs of the current device, or a negative error code (no device => B200SV_E_NODEVICE:
+ * there is no CPU fallback anywhere in this library). */
+int b200sv_device_sm_count(void);
+
+/* |0...0> for every batch element.  Replaces pyq.QuantumCircuit.init_state
+ * (backends/pyqtorch/backend.py:171). */
+int b200sv_init_zero_state(void* state, int dtype, int n_qubits, int64_t batch, void* stream);
+
+/* Forward execution of sweeps [first, last) of a plan, in place.  Replaces the per-gate einsum loop
+ * `circuit.native.run(state, values)` (backends/pyqtorch/backend.py:176).
+ * `index_hi` is OR-ed into the basis index seen by control / diagonal predicates (rank bits of a
+ * state sharded by its highest-order qubits); 0 on a single GPU. */
+int b200sv_apply_plan(void* state, int dtype, int n_qubits, int64_t batch, const double* params,
+                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* stream);
+
+/* Adjoint (reverse) execution of sweeps [first, last) of a plan on psi AND lambda, accumulating
+ * grads[grad_row][b] += 2 Re<lambda| dU/dθ |psi> for every gate flagged B200SV_GF_GRAD.
+ * Replaces pyqtorch.differentiation.AdjointExpectation.backward
+ * (call site engines/torch/differentiable_expectation.py:153-165). */
+int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n_qubits, int64_t batch,
+                        const double* params, double* grads, const b200sv_plan* plan, int first,
+                        int last, uint64_t index_hi, void* stream);
+
+/* out[b] (+)= Re <psi_b| sum_t coef[row_t][b] P_t |psi_b>.  coef is a device table
+ * `double[n_rows][coef_ld][2]` (complex), coef_ld = batch or 1 (broadcast).
+ * Replaces pyq.Observable.expectation (backends/pyqtorch/backend.py:208,249). */
+int b200sv_pauli_expectation(const void* psi, int dtype, int n_qubits, int64_t batch,
+                             const b200sv_pterm* terms, int n_terms, const double* coef,
+                             int64_t coef_ld, double* out, uint64_t index_hi, void* stream);
+
+/* out = alpha * (sum_t coef_t P_t psi) + beta * acc   (acc may be NULL when beta == 0, may alias out).
+ * With alpha=1, beta=0 this is lambda = O psi (the adjoint's projected state) and the matrix-free
+ * matvec of Krylov HamEvo.  Replaces pyq.Add/Scale/Sequence applied term by term
+ * (backends/pyqtorch/convert_ops.py:223,276-280).  Terms whose xmask has bits >= n_qubits are
+ * rejected (global qubits must be made local first). */
+int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, int n_qubits,
+                       int64_t batch, const b200sv_pterm* terms, int n_terms, const double* coef,
+                       int64_t coef_ld, double alpha_re, double alpha_im, double beta_re,
+                       double beta_im, uint64_t index_hi, void* stream);
+
+/* psi[b][i] *= exp(-i t[b] d_b(i)), d_b(i) = sum_t coef[row_t][b] (-1)^{popc(i & zmask_t)} evaluated
+ * on the fly from the index bits (all terms must have xmask == 0).  The diagonal Rydberg interaction
+ * sum_{i<j} C6/r^6 N_i N_j of analog blocks (analog/hamiltonian_terms.py:16-45) takes this path.
+ * Replaces pyq.HamiltonianEvolution's dense matrix_exp (backends/pyqtorch/convert_ops.py:258-269). */
+int b200sv_diag_evolve(void* psi, int dtype, int n_qubits, int64_t batch, const b200sv_pterm* terms,
+                       int n_terms, const double* coef, int64_t coef_ld, const double* t,
+                       int64_t t_ld, double sign, uint64_t index_hi, void* stream);
+
+/* Batched BLAS-1 on states (Krylov / Lanczos plumbing), all per batch element b:
+ *   dot:   out[b] (complex, 2 doubles) = <x_b|y_b>
+ *   axpy:  y_b += a[b] * x_b         (a complex table [batch][2])
+ *   scal:  x_b *= a[b]
+ *   lincomb: out_b = sum_k c[k][b] * V_k,b   (V: K states stacked [K][batch][2^n]) */
+int b200sv_dot(const void* x, const void* y, int dtype, int n_qubits, int64_t batch, double* out,
+               void* stream);
+int b200sv_axpy(const double* a, const void* x, void* y, int dtype, int n_qubits, int64_t batch,
+                void* stream);
+int b200sv_scal(const double* a, void* x, int dtype, int n_qubits, int64_t batch, void* stream);
+int b200sv_lincomb(const double* c, const void* V, int K, void* out, int dtype, int n_qubits,
+                   int64_t batch, void* stream);
+
+/* Constant dense 2^k x 2^k matrix (complex128, row-major, targets[0] = most significant operand
+ * bit) applied out of place: out = (M ⊗ I) psi.  MatrixBlock / Projector(ket,bra)
+ * (backends/pyqtorch/convert_ops.py:271-272, 287-294).  k <= 10. */
+int b200sv_apply_dense(const void* psi, void* out, int dtype, int n_qubits, int64_t batch,
+                       const double* matrix, const int32_t* target_bits, int k, void* stream);
+
+/* Sampling (replaces pyq.QuantumCircuit.sample, backends/pyqtorch/backend.py:300-302): inverse-CDF
+ * on SUPPLIED uniforms through a fixed-shape sum tree, bit-reproducible on any machine:
+ *   probs[b][i] = re*re + im*im (separately rounded), leaves = sequential sums of `chunk`
+ *   consecutive probabilities, inner nodes = left + right; descend with v = u*root.
+ * `tree` is a workspace of 2*(2^n/chunk) doubles per batch element (chunk = min(2^n, 256));
+ * `probs` 2^n doubles per batch element.  out_idx[b][s] = sampled basis index (int64). */
+int b200sv_sample(const void* psi, int dtype, int n_qubits, int64_t batch, double* probs,
+                  double* tree, const double* uniforms, int64_t n_shots, int64_t* out_idx,
+                  void* stream);
+
+/* out[b][rev_n(i)] = in[b][i]: Endianness.LITTLE views (transpile/invert.py:95-109). */
+int b200sv_bit_reverse(const void* in, void* out, int dtype, int n_qubits, int64_t batch,
+                       void* stream);
+
+/* out[b][P(i)] = in[b][i] where P moves index bit j to position perm[j] (a bijection on n bits);
+ * used to re-index local amplitudes around the all-to-all of a global<->local qubit swap. */
+int b200sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, int64_t batch,
+                        const int32_t* perm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SV_H */

@@ -1,0 +1,669 @@
+// b200sv C-ABI implementation (see include/b200sv.h).  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "b200sv.h"
+#include "sweep.cuh"
+
+using namespace b200sv;
+
+#define CK(expr)                               \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+#define LAUNCH_CK()                            \
+  do {                                         \
+    cudaError_t _e = cudaGetLastError();       \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// sweep launchers
+// ------------------------------------------------------------------------------------------------
+template <typename real, int R, bool ADJ>
+int launch_sweep(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
+                 int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
+  using c2 = typename C2<real>::type;
+  const b200sv_sweep& sw = plan->sweeps_host[s];
+  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_gates);
+  auto kern = sweep_kernel<real, R, ADJ>;
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int nt = 1 << (sw.m - R);
+  const long long grid = ((long long)batch) << sw.n_outer;
+  if (grid <= 0 || grid > 2147483647ll) return B200SV_E_ARG;
+  kern<<<(unsigned)grid, nt, smem, st>>>((c2*)psi, (c2*)lam, params, grads, plan->sweeps, plan->rounds,
+                                         plan->gates, plan->consts, s, n, (long long)batch,
+                                         (unsigned long long)index_hi, dir);
+  LAUNCH_CK();
+  return 0;
+}
+
+template <typename real, bool ADJ>
+int launch_sweep_r(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
+                   int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
+  const b200sv_sweep& sw = plan->sweeps_host[s];
+  if (sw.m < sw.r || sw.m - sw.r > 8 || sw.m > 12 || sw.n_outer != n - sw.m) return B200SV_E_ARG;
+  switch (sw.r) {
+    case 1: return launch_sweep<real, 1, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
+    case 2: return launch_sweep<real, 2, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
+    case 3: return launch_sweep<real, 3, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
+    case 4: return launch_sweep<real, 4, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
+    default: return B200SV_E_ARG;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <typename c2> __global__ void zero_state_kernel(c2* psi, int n, long long batch) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long mask = (1ll << n) - 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    c2 v; v.x = (i & mask) == 0 ? 1 : 0; v.y = 0;
+    psi[i] = v;
+  }
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  __syncthreads();
+  return v;  // valid in thread 0
+}
+
+struct TermS {  // per-CTA resolved term
+  unsigned long long x, z;
+  double cr, ci;
+};
+
+constexpr int MAX_TERMS_SMEM = 1024;
+constexpr int EXP_THREADS = 256;
+constexpr int EXP_PER_THREAD = 8;
+
+__device__ __forceinline__ void resolve_terms(TermS* sh, const b200sv_pterm* terms, int T,
+                                              const double* coef, long long coef_ld, long long b) {
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const b200sv_pterm tm = terms[t];
+    const long long bb = coef_ld == 1 ? 0 : b;
+    double cr = coef[((long long)tm.coef_row * coef_ld + bb) * 2];
+    double ci = coef[((long long)tm.coef_row * coef_ld + bb) * 2 + 1];
+    // multiply by (-i)^{n_y}
+    switch (tm.n_y & 3) {
+      case 1: { const double t0 = cr; cr = ci; ci = -t0; } break;
+      case 2: cr = -cr; ci = -ci; break;
+      case 3: { const double t0 = cr; cr = -ci; ci = t0; } break;
+      default: break;
+    }
+    sh[t].x = tm.xmask; sh[t].z = tm.zmask; sh[t].cr = cr; sh[t].ci = ci;
+  }
+}
+
+// E[b] += Re sum_i conj(psi_i) sum_t c_t (-1)^{popc(i&z_t)} psi[i^x_t]
+template <typename c2>
+__global__ void __launch_bounds__(EXP_THREADS)
+pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b200sv_pterm* __restrict__ terms,
+                    int T, const double* __restrict__ coef, long long coef_ld, double* __restrict__ out,
+                    unsigned long long index_hi, long long blocks_per_state) {
+  __shared__ TermS sh[MAX_TERMS_SMEM];
+  __shared__ double red[32];
+  const long long b = blockIdx.x / blocks_per_state;
+  const long long blk = blockIdx.x % blocks_per_state;
+  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  __syncthreads();
+  const long long N = 1ll << n;
+  const c2* p = psi + (b << n);
+  double acc = 0.0;
+  const long long base = blk * (long long)(EXP_THREADS * EXP_PER_THREAD);
+#pragma unroll 1
+  for (int k = 0; k < EXP_PER_THREAD; ++k) {
+    const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
+    if (i >= N) break;
+    const c2 a = p[i];
+    const unsigned long long gi = (unsigned long long)i | index_hi;
+    double wr = 0.0;             // diagonal weight
+    double sr = 0.0, si = 0.0;   // off-diagonal sum
+    for (int t = 0; t < T; ++t) {
+      const TermS tm = sh[t];
+      const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
+      if (tm.x == 0ull) wr += sg * tm.cr;
+      else {
+        const c2 q = p[i ^ (long long)tm.x];
+        const double cr = sg * tm.cr, ci = sg * tm.ci;
+        sr += cr * (double)q.x - ci * (double)q.y;
+        si += cr * (double)q.y + ci * (double)q.x;
+      }
+    }
+    const double ax = a.x, ay = a.y;
+    acc += wr * (ax * ax + ay * ay) + (ax * sr + ay * si);
+  }
+  acc = block_reduce_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&out[b], acc);
+}
+
+// out = alpha * (sum_t c_t P_t psi) + beta * acc
+template <typename c2>
+__global__ void __launch_bounds__(256)
+pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
+                   const b200sv_pterm* __restrict__ terms, int T, const double* __restrict__ coef,
+                   long long coef_ld, double ar, double ai, double br, double bi,
+                   unsigned long long index_hi, long long blocks_per_state) {
+  __shared__ TermS sh[MAX_TERMS_SMEM];
+  const long long b = blockIdx.x / blocks_per_state;
+  const long long blk = blockIdx.x % blocks_per_state;
+  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  __syncthreads();
+  const long long N = 1ll << n;
+  const c2* p = psi + (b << n);
+  const long long base = blk * (long long)(256 * 4);
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + (long long)k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const unsigned long long gi = (unsigned long long)i | index_hi;
+    const c2 a = p[i];
+    double wr = 0.0, wi = 0.0, sr = 0.0, si = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const TermS tm = sh[t];
+      const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
+      if (tm.x == 0ull) { wr += sg * tm.cr; wi += sg * tm.ci; }
+      else {
+        const c2 q = p[i ^ (long long)tm.x];
+        const double cr = sg * tm.cr, ci = sg * tm.ci;
+        sr += cr * (double)q.x - ci * (double)q.y;
+        si += cr * (double)q.y + ci * (double)q.x;
+      }
+    }
+    sr += wr * (double)a.x - wi * (double)a.y;
+    si += wr * (double)a.y + wi * (double)a.x;
+    double rr = ar * sr - ai * si, ri = ar * si + ai * sr;
+    if (acc != nullptr) {
+      const c2 z = acc[(b << n) + i];
+      rr += br * (double)z.x - bi * (double)z.y;
+      ri += br * (double)z.y + bi * (double)z.x;
+    }
+    c2 o; o.x = rr; o.y = ri;
+    out[(b << n) + i] = o;
+  }
+}
+
+// psi[i] *= exp(-i * sign * t_b * d(i))
+template <typename c2>
+__global__ void __launch_bounds__(256)
+diag_evolve_kernel(c2* psi, int n, long long batch, const b200sv_pterm* __restrict__ terms, int T,
+                   const double* __restrict__ coef, long long coef_ld, const double* __restrict__ tt,
+                   long long t_ld, double sign, unsigned long long index_hi, long long blocks_per_state) {
+  __shared__ TermS sh[MAX_TERMS_SMEM];
+  const long long b = blockIdx.x / blocks_per_state;
+  const long long blk = blockIdx.x % blocks_per_state;
+  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  __syncthreads();
+  const double t = tt[t_ld == 1 ? 0 : b] * sign;
+  const long long N = 1ll << n;
+  c2* p = psi + (b << n);
+  const long long base = blk * (long long)(256 * 4);
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + (long long)k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const unsigned long long gi = (unsigned long long)i | index_hi;
+    double d = 0.0;
+    for (int q = 0; q < T; ++q) {
+      const TermS tm = sh[q];
+      d += (__popcll(gi & tm.z) & 1) ? -tm.cr : tm.cr;
+    }
+    double s, c;
+    sincos(-t * d, &s, &c);
+    const c2 a = p[i];
+    c2 o; o.x = (double)a.x * c - (double)a.y * s; o.y = (double)a.x * s + (double)a.y * c;
+    p[i] = o;
+  }
+}
+
+// ---- batched BLAS-1 --------------------------------------------------------------------------
+template <typename c2>
+__global__ void __launch_bounds__(256)
+dot_kernel(const c2* __restrict__ x, const c2* __restrict__ y, int n, double* out, long long blocks_per_state) {
+  __shared__ double red[32];
+  const long long b = blockIdx.x / blocks_per_state;
+  const long long blk = blockIdx.x % blocks_per_state;
+  const long long N = 1ll << n;
+  double re = 0.0, im = 0.0;
+  const long long base = blk * 2048ll;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < N) {
+      const c2 a = x[(b << n) + i], c = y[(b << n) + i];
+      re += (double)a.x * (double)c.x + (double)a.y * (double)c.y;   // conj(a) * c
+      im += (double)a.x * (double)c.y - (double)a.y * (double)c.x;
+    }
+  }
+  re = block_reduce_sum(re, red);
+  im = block_reduce_sum(im, red);
+  if (threadIdx.x == 0) { atomicAdd(&out[2 * b], re); atomicAdd(&out[2 * b + 1], im); }
+}
+
+template <typename c2>
+__global__ void axpy_kernel(const double* __restrict__ a, const c2* __restrict__ x, c2* y, int n, long long batch) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long b = i >> n;
+    const double ar = a[2 * b], ai = a[2 * b + 1];
+    const c2 xv = x[i]; c2 yv = y[i];
+    yv.x = (double)yv.x + ar * (double)xv.x - ai * (double)xv.y;
+    yv.y = (double)yv.y + ar * (double)xv.y + ai * (double)xv.x;
+    y[i] = yv;
+  }
+}
+
+template <typename c2>
+__global__ void scal_kernel(const double* __restrict__ a, c2* x, int n, long long batch) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long b = i >> n;
+    const double ar = a[2 * b], ai = a[2 * b + 1];
+    const c2 xv = x[i]; c2 o;
+    o.x = ar * (double)xv.x - ai * (double)xv.y;
+    o.y = ar * (double)xv.y + ai * (double)xv.x;
+    x[i] = o;
+  }
+}
+
+template <typename c2>
+__global__ void lincomb_kernel(const double* __restrict__ c, const c2* __restrict__ V, int K, c2* out, int n,
+                               long long batch) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long b = i >> n;
+    double re = 0.0, im = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const double cr = c[((long long)k * batch + b) * 2], ci = c[((long long)k * batch + b) * 2 + 1];
+      const c2 v = V[(long long)k * total + i];
+      re += cr * (double)v.x - ci * (double)v.y;
+      im += cr * (double)v.y + ci * (double)v.x;
+    }
+    c2 o; o.x = re; o.y = im;
+    out[i] = o;
+  }
+}
+
+// ---- dense k-qubit constant matrix, out of place ---------------------------------------------
+struct DenseArgs { int bits[10]; };
+
+template <typename c2>
+__global__ void dense_kernel(const c2* __restrict__ psi, c2* __restrict__ out, int n, long long batch,
+                             const double* __restrict__ mat, DenseArgs da, int k) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int dim = 1 << k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long b = i >> n;
+    const long long idx = i & ((1ll << n) - 1);
+    int row = 0;
+    long long cleared = idx;
+    for (int q = 0; q < k; ++q) {  // operand bit (k-1-q) <-> targets[q]
+      const int bit = da.bits[q];
+      row |= (int)((idx >> bit) & 1) << (k - 1 - q);
+      cleared &= ~(1ll << bit);
+    }
+    double re = 0.0, im = 0.0;
+    for (int col = 0; col < dim; ++col) {
+      long long src = cleared;
+      for (int q = 0; q < k; ++q) src |= (long long)((col >> (k - 1 - q)) & 1) << da.bits[q];
+      const c2 v = psi[(b << n) + src];
+      const double mr = mat[2 * ((long long)row * dim + col)], mi = mat[2 * ((long long)row * dim + col) + 1];
+      re += mr * (double)v.x - mi * (double)v.y;
+      im += mr * (double)v.y + mi * (double)v.x;
+    }
+    c2 o; o.x = re; o.y = im;
+    out[i] = o;
+  }
+}
+
+// ---- sampling ----------------------------------------------------------------------------------
+template <typename c2>
+__global__ void probs_kernel(const c2* __restrict__ psi, double* __restrict__ probs, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const double re = psi[i].x, im = psi[i].y;
+    probs[i] = __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im));  // no FMA contraction: bit-reproducible
+  }
+}
+
+__global__ void leaf_kernel(const double* __restrict__ probs, double* __restrict__ tree, int n, long long batch,
+                            int chunk, long long L) {
+  const long long total = batch * L;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const long long b = j / L, leaf = j % L;
+    const double* p = probs + (b << n) + leaf * chunk;
+    double run = 0.0;
+    for (int k = 0; k < chunk; ++k) run = __dadd_rn(run, p[k]);
+    tree[b * 2 * L + leaf] = run;
+  }
+}
+
+// one CTA per batch element builds the inner levels: level l at offset off_l, off_0 = 0, size L>>l
+__global__ void tree_kernel(double* __restrict__ tree, long long L) {
+  double* t = tree + (long long)blockIdx.x * 2 * L;
+  long long off = 0, sz = L;
+  while (sz > 1) {
+    const long long nxt = off + sz;
+    for (long long i = threadIdx.x; i < sz / 2; i += blockDim.x)
+      t[nxt + i] = __dadd_rn(t[off + 2 * i], t[off + 2 * i + 1]);
+    __syncthreads();
+    off = nxt; sz >>= 1;
+  }
+}
+
+__global__ void descend_kernel(const double* __restrict__ probs, const double* __restrict__ tree,
+                               const double* __restrict__ uniforms, long long* __restrict__ out, int n,
+                               long long batch, long long shots, int chunk, long long L, int levels) {
+  const long long total = batch * shots;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const long long b = j / shots;
+    const double* t = tree + b * 2 * L;
+    // offsets of levels: off_l = sum_{q<l} L>>q = 2L - (L >> (l-1)) for l>=1
+    long long off_root = 2 * L - 2;  // level `levels-1` has size 1 (for L == 1: off 0)
+    if (L == 1) off_root = 0;
+    double v = __dmul_rn(uniforms[j], t[off_root]);
+    long long node = 0;
+    for (int lvl = levels - 2; lvl >= 0; --lvl) {
+      const long long off = lvl == 0 ? 0 : 2 * L - (L >> (lvl - 1));
+      const double left = t[off + 2 * node];
+      if (v < left) node = 2 * node;
+      else { v = __dadd_rn(v, -left); node = 2 * node + 1; }
+    }
+    const double* p = probs + (b << n) + node * chunk;
+    double acc = 0.0;
+    int sel = chunk - 1;
+    for (int k = 0; k < chunk; ++k) {
+      acc = __dadd_rn(acc, p[k]);
+      if (v < acc) { sel = k; break; }
+    }
+    out[j] = node * chunk + sel;
+  }
+}
+
+// ---- index permutations ------------------------------------------------------------------------
+struct PermArgs { int perm[64]; };
+
+template <typename c2>
+__global__ void permute_kernel(const c2* __restrict__ in, c2* __restrict__ out, int n, long long batch, PermArgs pa) {
+  const long long total = batch << n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+    // gather form: out[o] = in[P^{-1}(o)], with source bit j found at output position perm[j]
+    const long long b = o >> n;
+    const long long oi = o & ((1ll << n) - 1);
+    long long src = 0;
+    for (int j = 0; j < n; ++j) src |= ((oi >> pa.perm[j]) & 1ll) << j;
+    out[o] = in[(b << n) + src];
+  }
+}
+
+inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 148ll * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int b200sv_abi_version(void) { return B200SV_ABI_VERSION; }
+
+int b200sv_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200SV_E_NODEVICE; }
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return B200SV_E_NODEVICE;
+  }
+  return sms;
+}
+
+int b200sv_init_zero_state(void* state, int dtype, int n, int64_t batch, void* stream) {
+  if (!state || n < 0 || n > 40 || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) zero_state_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>((double2*)state, n, batch);
+  else if (dtype == B200SV_C64) zero_state_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>((float2*)state, n, batch);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_apply_plan(void* state, int dtype, int n, int64_t batch, const double* params,
+                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* stream) {
+  if (!state || !plan || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = first; s < last; ++s) {
+    int rc;
+    if (dtype == B200SV_C128) rc = launch_sweep_r<double, false>(state, nullptr, params, nullptr, plan, s, n, batch, index_hi, +1, st);
+    else if (dtype == B200SV_C64) rc = launch_sweep_r<float, false>(state, nullptr, params, nullptr, plan, s, n, batch, index_hi, +1, st);
+    else return B200SV_E_ARG;
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n, int64_t batch, const double* params,
+                        double* grads, const b200sv_plan* plan, int first, int last, uint64_t index_hi,
+                        void* stream) {
+  if (!psi || !lam || !plan || !grads || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = last - 1; s >= first; --s) {
+    int rc;
+    if (dtype == B200SV_C128) rc = launch_sweep_r<double, true>(psi, lam, params, grads, plan, s, n, batch, index_hi, -1, st);
+    else if (dtype == B200SV_C64) rc = launch_sweep_r<float, true>(psi, lam, params, grads, plan, s, n, batch, index_hi, -1, st);
+    else return B200SV_E_ARG;
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int check_terms(int n_terms) { return (n_terms < 0 || n_terms > MAX_TERMS_SMEM) ? B200SV_E_UNSUPPORTED : 0; }
+
+int b200sv_pauli_expectation(const void* psi, int dtype, int n, int64_t batch, const b200sv_pterm* terms,
+                             int n_terms, const double* coef, int64_t coef_ld, double* out,
+                             uint64_t index_hi, void* stream) {
+  if (!psi || !out || batch <= 0 || (coef_ld != 1 && coef_ld != batch)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long per = EXP_THREADS * EXP_PER_THREAD;
+  const long long bps = (N + per - 1) / per;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (dtype == B200SV_C128)
+    pauli_expect_kernel<double2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, coef, coef_ld, out, index_hi, bps);
+  else if (dtype == B200SV_C64)
+    pauli_expect_kernel<float2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, coef, coef_ld, out, index_hi, bps);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, int n, int64_t batch,
+                       const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld,
+                       double ar, double ai, double br, double bi, uint64_t index_hi, void* stream) {
+  if (!psi || !out || psi == out || batch <= 0 || (coef_ld != 1 && coef_ld != batch)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + 1023) / 1024;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (br == 0.0 && bi == 0.0) acc = nullptr;
+  if (dtype == B200SV_C128)
+    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+  else if (dtype == B200SV_C64)
+    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_diag_evolve(void* psi, int dtype, int n, int64_t batch, const b200sv_pterm* terms, int n_terms,
+                       const double* coef, int64_t coef_ld, const double* t, int64_t t_ld, double sign,
+                       uint64_t index_hi, void* stream) {
+  if (!psi || !t || batch <= 0 || (coef_ld != 1 && coef_ld != batch) || (t_ld != 1 && t_ld != batch)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + 1023) / 1024;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (dtype == B200SV_C128)
+    diag_evolve_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)psi, n, batch, terms, n_terms, coef, coef_ld, t, t_ld, sign, index_hi, bps);
+  else if (dtype == B200SV_C64)
+    diag_evolve_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)psi, n, batch, terms, n_terms, coef, coef_ld, t, t_ld, sign, index_hi, bps);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_dot(const void* x, const void* y, int dtype, int n, int64_t batch, double* out, void* stream) {
+  if (!x || !y || !out || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(out, 0, sizeof(double) * 2 * batch, st));
+  const long long N = 1ll << n;
+  const long long bps = (N + 2047) / 2048;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (dtype == B200SV_C128) dot_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)x, (const double2*)y, n, out, bps);
+  else if (dtype == B200SV_C64) dot_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)x, (const float2*)y, n, out, bps);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_axpy(const double* a, const void* x, void* y, int dtype, int n, int64_t batch, void* stream) {
+  if (!a || !x || !y || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) axpy_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>(a, (const double2*)x, (double2*)y, n, batch);
+  else if (dtype == B200SV_C64) axpy_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>(a, (const float2*)x, (float2*)y, n, batch);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_scal(const double* a, void* x, int dtype, int n, int64_t batch, void* stream) {
+  if (!a || !x || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) scal_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>(a, (double2*)x, n, batch);
+  else if (dtype == B200SV_C64) scal_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>(a, (float2*)x, n, batch);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_lincomb(const double* c, const void* V, int K, void* out, int dtype, int n, int64_t batch, void* stream) {
+  if (!c || !V || !out || K <= 0 || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) lincomb_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>(c, (const double2*)V, K, (double2*)out, n, batch);
+  else if (dtype == B200SV_C64) lincomb_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>(c, (const float2*)V, K, (float2*)out, n, batch);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_apply_dense(const void* psi, void* out, int dtype, int n, int64_t batch, const double* matrix,
+                       const int32_t* target_bits, int k, void* stream) {
+  if (!psi || !out || psi == out || !matrix || !target_bits || k < 1 || k > 10 || k > n || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  DenseArgs da;
+  for (int q = 0; q < k; ++q) {
+    if (target_bits[q] < 0 || target_bits[q] >= n) return B200SV_E_ARG;
+    da.bits[q] = target_bits[q];
+  }
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) dense_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>((const double2*)psi, (double2*)out, n, batch, matrix, da, k);
+  else if (dtype == B200SV_C64) dense_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>((const float2*)psi, (float2*)out, n, batch, matrix, da, k);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_sample(const void* psi, int dtype, int n, int64_t batch, double* probs, double* tree,
+                  const double* uniforms, int64_t n_shots, int64_t* out_idx, void* stream) {
+  if (!psi || !probs || !tree || !uniforms || !out_idx || batch <= 0 || n_shots <= 0 || n > 34) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const int chunk = (int)(N < 256 ? N : 256);
+  const long long L = N / chunk;
+  int levels = 1;
+  for (long long s = L; s > 1; s >>= 1) ++levels;
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) probs_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>((const double2*)psi, probs, total);
+  else if (dtype == B200SV_C64) probs_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>((const float2*)psi, probs, total);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  leaf_kernel<<<grid_for(batch * L, 128), 128, 0, st>>>(probs, tree, n, batch, chunk, L);
+  LAUNCH_CK();
+  if (batch > 2147483647ll) return B200SV_E_ARG;
+  tree_kernel<<<(unsigned)batch, 256, 0, st>>>(tree, L);
+  LAUNCH_CK();
+  descend_kernel<<<grid_for(batch * n_shots, 128), 128, 0, st>>>(probs, tree, uniforms, (long long*)out_idx, n, batch, n_shots, chunk, L, levels);
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_permute_bits(const void* in, void* out, int dtype, int n, int64_t batch, const int32_t* perm, void* stream) {
+  if (!in || !out || in == out || !perm || n < 0 || n > 40 || batch <= 0) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PermArgs pa;
+  uint64_t seen = 0;
+  for (int j = 0; j < n; ++j) {
+    if (perm[j] < 0 || perm[j] >= n || ((seen >> perm[j]) & 1)) return B200SV_E_ARG;
+    seen |= 1ull << perm[j];
+    pa.perm[j] = perm[j];
+  }
+  const long long total = (long long)batch << n;
+  if (dtype == B200SV_C128) permute_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>((const double2*)in, (double2*)out, n, batch, pa);
+  else if (dtype == B200SV_C64) permute_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>((const float2*)in, (float2*)out, n, batch, pa);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_bit_reverse(const void* in, void* out, int dtype, int n, int64_t batch, void* stream) {
+  int32_t perm[64];
+  for (int j = 0; j < n; ++j) perm[j] = n - 1 - j;
+  return b200sv_permute_bits(in, out, dtype, n, batch, perm, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,579 @@
+"""Execution engine: runs `Program`s on a B200 through the C-ABI (`cabi.py` → `libb200sv.so`).
+
+Host-side counterpart of `pyq.QuantumCircuit.run / sample`, `pyq.Observable.expectation` and
+`pyqtorch.differentiation.AdjointExpectation` as they are called from
+`/root/reference/qadence/backends/pyqtorch/backend.py:158-310` and
+`/root/reference/qadence/engines/torch/differentiable_expectation.py:134-165`.
+PyTorch is used for device memory, streams and autograd plumbing only; all state-vector arithmetic
+happens in the hand-written CUDA kernels.  No CPU fallback: everything here raises without a GPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections import Counter
+from dataclasses import dataclass, field
+from typing import Any, Mapping, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import cabi
+from .plan import SweepPlan, TileConfig, build_plan, pack_pauli_terms
+from .program import Op, OpKind, PauliSum, Program
+
+_DT = {torch.complex64: cabi.C64, torch.complex128: cabi.C128}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dev(device: torch.device | str | None) -> torch.device:
+    cabi.require_device()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise cabi.B200svError(f"b200sv executes on CUDA devices only (got {d}); there is no CPU fallback")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------------
+class DevicePlan:
+    """A `SweepPlan` uploaded to the device + the `b200sv_plan` struct the C-ABI takes."""
+
+    def __init__(self, plan: SweepPlan, device: torch.device):
+        self.plan = plan
+        self.device = device
+        self._host_sweeps = np.ascontiguousarray(plan.sweeps)
+
+        def up(a: np.ndarray) -> Tensor:
+            raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+            if raw.size == 0:
+                raw = np.zeros(16, dtype=np.uint8)
+            return torch.from_numpy(raw.copy()).to(device)
+
+        self._sweeps = up(plan.sweeps)
+        self._rounds = up(plan.rounds)
+        self._gates = up(plan.gates)
+        self._consts = up(plan.consts)
+        self.struct = cabi.PlanStruct(
+            self._sweeps.data_ptr(),
+            self._rounds.data_ptr(),
+            self._gates.data_ptr(),
+            self._consts.data_ptr(),
+            self._host_sweeps.ctypes.data,
+            plan.n_sweeps,
+            0,
+        )
+
+    @property
+    def n_sweeps(self) -> int:
+        return self.plan.n_sweeps
+
+
+def _is_unitary_simple(op: Op) -> bool:
+    if op.kind == OpKind.MAT1:
+        m = np.asarray(op.matrix, dtype=np.complex128)
+        return bool(np.allclose(m.conj().T @ m, np.eye(2), atol=1e-12))
+    return True
+
+
+@dataclass
+class CompiledPauliSum:
+    ps: PauliSum
+    terms_np: np.ndarray
+    consts: np.ndarray  # [T] complex
+    names: list[tuple[str, ...]]
+    diagonal: bool
+    _dev_terms: dict = field(default_factory=dict)
+    _dev_const_coef: dict = field(default_factory=dict)
+
+    @staticmethod
+    def build(ps: PauliSum) -> "CompiledPauliSum":
+        ps = ps.simplified()
+        if len(ps.terms) > 1024:
+            raise NotImplementedError("Pauli sums with more than 1024 distinct terms are not supported yet")
+        terms = pack_pauli_terms([t.paulis for t in ps.terms], ps.n_qubits)
+        return CompiledPauliSum(
+            ps, terms, np.array([t.const for t in ps.terms], dtype=np.complex128), [t.names for t in ps.terms], ps.is_diagonal
+        )
+
+    @property
+    def n_terms(self) -> int:
+        return len(self.ps.terms)
+
+    @property
+    def is_parametric(self) -> bool:
+        return any(len(nm) > 0 for nm in self.names)
+
+    def terms(self, device: torch.device) -> Tensor:
+        if device not in self._dev_terms:
+            raw = self.terms_np.view(np.uint8).reshape(-1)
+            if raw.size == 0:
+                raw = np.zeros(32, dtype=np.uint8)
+            self._dev_terms[device] = torch.from_numpy(raw.copy()).to(device)
+        return self._dev_terms[device]
+
+    def coef(self, values: Mapping[str, Tensor], device: torch.device) -> Tensor:
+        """[T, Bc] complex128 coefficient table (Bc = 1 or batch); differentiable w.r.t. values."""
+        if not self.is_parametric:
+            if device not in self._dev_const_coef:
+                self._dev_const_coef[device] = torch.from_numpy(self.consts.reshape(-1, 1).copy()).to(device)
+            return self._dev_const_coef[device]
+        rows = []
+        bc = 1
+        for c, nms in zip(self.consts, self.names):
+            v: Tensor = torch.full((1,), complex(c), dtype=torch.complex128, device=device)
+            for nm in nms:
+                p = torch.as_tensor(values[nm]).to(device).reshape(-1)
+                v = v * p
+            bc = max(bc, v.numel())
+            rows.append(v)
+        rows = [r.expand(bc) for r in rows]
+        return torch.stack(rows) if rows else torch.zeros(0, 1, dtype=torch.complex128, device=device)
+
+
+@dataclass
+class Segment:
+    gates: list[Op] | None = None  # run of simple gates
+    op: Op | None = None  # one non-fusable op
+    compiled: Any = None  # CompiledPauliSum / CompiledProgram(s) for op.generator / op.subs
+    _plans: dict = field(default_factory=dict)
+
+
+class CompiledProgram:
+    """A Program split into fused-gate segments and non-fusable ops, with its parameter slots."""
+
+    def __init__(self, program: Program):
+        self.program = program
+        self.n_qubits = program.n_qubits
+        self.names: list[str] = program.param_names
+        self.slot_of = {nm: i for i, nm in enumerate(self.names)}
+        self.segments: list[Segment] = []
+        run: list[Op] = []
+        for op in program.ops:
+            if op.kind < OpKind.MATK:
+                run.append(op)
+                continue
+            if run:
+                self.segments.append(Segment(gates=run))
+                run = []
+            seg = Segment(op=op)
+            if op.kind == OpKind.ADD:
+                seg.compiled = [CompiledProgram(s) for s in op.subs]
+            elif op.kind == OpKind.HAMEVO:
+                g = op.generator
+                if isinstance(g, PauliSum):
+                    seg.compiled = CompiledPauliSum.build(g)
+                elif isinstance(g, Program):
+                    seg.compiled = CompiledProgram(g)
+            self.segments.append(seg)
+        if run:
+            self.segments.append(Segment(gates=run))
+        self.invertible = all(
+            all(_is_unitary_simple(o) for o in s.gates) if s.gates is not None else s.op.kind in (OpKind.HAMEVO, OpKind.MATK)
+            for s in self.segments
+        )
+
+    def device_plan(self, seg: Segment, dtype: torch.dtype, adjoint: bool, device: torch.device, cfg: TileConfig | None = None) -> DevicePlan:
+        key = (dtype, adjoint, device, None if cfg is None else (cfg.m, cfg.r, cfg.low))
+        if key not in seg._plans:
+            tc = cfg or TileConfig.default(dtype == torch.complex128, adjoint)
+            seg._plans[key] = DevicePlan(build_plan(seg.gates, self.n_qubits, self.slot_of, tc), device)
+        return seg._plans[key]
+
+    def n_sweeps(self, dtype: torch.dtype = torch.complex128, adjoint: bool = False) -> int:
+        tc = TileConfig.default(dtype == torch.complex128, adjoint)
+        return sum(build_plan(s.gates, self.n_qubits, self.slot_of, tc).n_sweeps for s in self.segments if s.gates is not None)
+
+
+# ---------------------------------------------------------------------------------------------------
+def infer_batch(values: Mapping[str, Any] | None) -> int:
+    """Max leading length of the tensor values (`qadence/backends/utils.py:169-184`)."""
+    b = 1
+    for v in (values or {}).values():
+        if isinstance(v, Tensor) and v.dim() >= 1:
+            b = max(b, v.shape[0])
+    return b
+
+
+def pack_params(names: Sequence[str], values: Mapping[str, Tensor], batch: int, device: torch.device) -> Tensor:
+    """[n_slots, batch] float64 device table of gate parameters, differentiable w.r.t. `values`."""
+    if not names:
+        return torch.zeros(1, batch, dtype=torch.float64, device=device)
+    rows = []
+    for nm in names:
+        if nm not in values:
+            raise KeyError(f"parameter '{nm}' missing from param_values")
+        v = torch.as_tensor(values[nm])
+        if v.dim() > 1 and v.numel() != v.shape[0]:
+            rows.append(torch.zeros(batch, dtype=torch.float64))  # matrix-valued (generator) entry: not a scalar slot
+            continue
+        v = v.reshape(-1)
+        if v.is_complex():
+            v = v.real
+        v = v.to(torch.float64)
+        if v.numel() == 1:
+            v = v.expand(batch)
+        elif v.numel() != batch:
+            raise ValueError(f"parameter '{nm}' has batch {v.numel()}, expected 1 or {batch}")
+        rows.append(v)
+    devs = {r.device for r in rows}
+    if len(devs) == 1 and next(iter(devs)).type == "cpu":
+        return torch.stack(rows).to(device)  # one H2D copy
+    return torch.stack([r.to(device) for r in rows])
+
+
+def zero_state(n: int, batch: int, dtype: torch.dtype, device: torch.device) -> Tensor:
+    st = torch.empty(batch, 2**n, dtype=dtype, device=device)
+    cabi.check(cabi.load().b200sv_init_zero_state(st.data_ptr(), _DT[dtype], n, batch, _stream_ptr(device)), "init_zero_state")
+    return st
+
+
+def prepare_state(n: int, batch: int, state: Tensor | None, dtype: torch.dtype, device: torch.device) -> Tensor:
+    """Fresh, writable `[batch, 2^n]` device state (zero state, or a copy of the user's state)."""
+    if state is None:
+        return zero_state(n, batch, dtype, device)
+    if state.dim() != 2 or state.shape[1] != 2**n:
+        raise ValueError(f"state must have shape (batch, 2**{n}); got {tuple(state.shape)}")
+    st = state.detach().to(device=device, dtype=dtype)
+    if st.shape[0] == 1 and batch > 1:
+        st = st.expand(batch, -1)
+    elif st.shape[0] != batch:
+        raise ValueError(f"state batch {st.shape[0]} incompatible with parameter batch {batch}")
+    return st.clone(memory_format=torch.contiguous_format)
+
+
+# ---------------------------------------------------------------------------------------------------
+def pauli_apply(cps: CompiledPauliSum, coef: Tensor, psi: Tensor, out: Tensor | None = None, acc: Tensor | None = None,
+                alpha: complex = 1.0, beta: complex = 0.0, index_hi: int = 0) -> Tensor:
+    """out = alpha·(Σ_t coef_t P_t ψ) + beta·acc."""
+    n = cps.ps.n_qubits
+    B = psi.shape[0]
+    dev = psi.device
+    out = torch.empty_like(psi) if out is None else out
+    cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+    rc = cabi.load().b200sv_pauli_apply(
+        psi.data_ptr(), out.data_ptr(), 0 if acc is None else acc.data_ptr(), _DT[psi.dtype], n, B,
+        cps.terms(dev).data_ptr(), cps.n_terms, cf.data_ptr(), coef.shape[1],
+        float(np.real(alpha)), float(np.imag(alpha)), float(np.real(beta)), float(np.imag(beta)), index_hi, _stream_ptr(dev),
+    )
+    cabi.check(rc, "pauli_apply")
+    return out
+
+
+def pauli_expectation(cps: CompiledPauliSum, coef: Tensor, psi: Tensor, index_hi: int = 0) -> Tensor:
+    """[B] float64: Re⟨ψ|Σ_t coef_t P_t|ψ⟩."""
+    n = cps.ps.n_qubits
+    B = psi.shape[0]
+    dev = psi.device
+    out = torch.zeros(B, dtype=torch.float64, device=dev)
+    cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+    rc = cabi.load().b200sv_pauli_expectation(
+        psi.data_ptr(), _DT[psi.dtype], n, B, cps.terms(dev).data_ptr(), cps.n_terms, cf.data_ptr(), coef.shape[1],
+        out.data_ptr(), index_hi, _stream_ptr(dev),
+    )
+    cabi.check(rc, "pauli_expectation")
+    return out
+
+
+def dot(x: Tensor, y: Tensor) -> Tensor:
+    """[B] complex128 ⟨x_b|y_b⟩."""
+    B = x.shape[0]
+    n = int(x.shape[1]).bit_length() - 1
+    out = torch.empty(B, 2, dtype=torch.float64, device=x.device)
+    cabi.check(cabi.load().b200sv_dot(x.data_ptr(), y.data_ptr(), _DT[x.dtype], n, B, out.data_ptr(), _stream_ptr(x.device)), "dot")
+    return torch.view_as_complex(out)
+
+
+def axpy(a: Tensor, x: Tensor, y: Tensor) -> None:
+    """y_b += a[b]·x_b (a: [B] complex128 on device)."""
+    B = x.shape[0]
+    n = int(x.shape[1]).bit_length() - 1
+    ar = torch.view_as_real(a.to(torch.complex128).contiguous())
+    cabi.check(cabi.load().b200sv_axpy(ar.data_ptr(), x.data_ptr(), y.data_ptr(), _DT[x.dtype], n, B, _stream_ptr(x.device)), "axpy")
+
+
+def scal(a: Tensor, x: Tensor) -> None:
+    B = x.shape[0]
+    n = int(x.shape[1]).bit_length() - 1
+    ar = torch.view_as_real(a.to(torch.complex128).contiguous())
+    cabi.check(cabi.load().b200sv_scal(ar.data_ptr(), x.data_ptr(), _DT[x.dtype], n, B, _stream_ptr(x.device)), "scal")
+
+
+def lincomb(c: Tensor, V: Tensor, out: Tensor) -> None:
+    """out_b = Σ_k c[k,b]·V[k,b,:]  (c: [K,B] complex128; V: [K,B,2^n])."""
+    K, B = c.shape
+    n = int(V.shape[2]).bit_length() - 1
+    cr = torch.view_as_real(c.to(torch.complex128).contiguous())
+    cabi.check(cabi.load().b200sv_lincomb(cr.data_ptr(), V.data_ptr(), K, out.data_ptr(), _DT[V.dtype], n, B, _stream_ptr(V.device)), "lincomb")
+
+
+def apply_dense(psi: Tensor, matrix: np.ndarray | Tensor, target_bits: Sequence[int]) -> Tensor:
+    n = int(psi.shape[1]).bit_length() - 1
+    m = torch.as_tensor(matrix).to(torch.complex128).contiguous().to(psi.device)
+    mr = torch.view_as_real(m)
+    tb = np.asarray(list(target_bits), dtype=np.int32)
+    out = torch.empty_like(psi)
+    rc = cabi.load().b200sv_apply_dense(psi.data_ptr(), out.data_ptr(), _DT[psi.dtype], n, psi.shape[0], mr.data_ptr(), tb.ctypes.data, len(tb), _stream_ptr(psi.device))
+    cabi.check(rc, "apply_dense")
+    return out
+
+
+def bit_reverse(psi: Tensor) -> Tensor:
+    n = int(psi.shape[1]).bit_length() - 1
+    out = torch.empty_like(psi)
+    cabi.check(cabi.load().b200sv_bit_reverse(psi.data_ptr(), out.data_ptr(), _DT[psi.dtype], n, psi.shape[0], _stream_ptr(psi.device)), "bit_reverse")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def _run_segments(cp: CompiledProgram, state: Tensor, ptable: Tensor, values: Mapping[str, Tensor], index_hi: int = 0) -> Tensor:
+    from . import hamevo
+
+    lib = cabi.load()
+    dev = state.device
+    B = state.shape[0]
+    for seg in cp.segments:
+        if seg.gates is not None:
+            dp = cp.device_plan(seg, state.dtype, False, dev)
+            rc = lib.b200sv_apply_plan(state.data_ptr(), _DT[state.dtype], cp.n_qubits, B, ptable.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, index_hi, _stream_ptr(dev))
+            cabi.check(rc, "apply_plan")
+            continue
+        op = seg.op
+        if op.kind == OpKind.MATK:
+            bits = [cp.n_qubits - 1 - q for q in op.targets]
+            state = apply_dense(state, op.matrix, bits)
+        elif op.kind == OpKind.ADD:
+            acc = torch.zeros_like(state)
+            for sub in seg.compiled:
+                tmp = state.clone()
+                sub_table = pack_params(sub.names, values, B, dev)
+                tmp = _run_segments(sub, tmp, sub_table, values, index_hi)
+                acc += tmp
+            state = acc
+        elif op.kind == OpKind.HAMEVO:
+            state = hamevo.evolve(op, seg.compiled, state, values, cp.n_qubits, dagger=False)
+        else:
+            raise NotImplementedError(op.kind)
+    return state
+
+
+def run(cp: CompiledProgram, values: Mapping[str, Tensor] | None = None, state: Tensor | None = None,
+        dtype: torch.dtype = torch.complex128, device: torch.device | str | None = None) -> Tensor:
+    """ψ_out `[B, 2^n]` = U(values)·ψ_in — `Backend.run` (backends/pyqtorch/backend.py:158-179)."""
+    dev = _dev(device)
+    values = values or {}
+    B = infer_batch(values)
+    if state is not None:
+        B = max(B, state.shape[0])
+    with torch.no_grad():
+        st = prepare_state(cp.n_qubits, B, state, dtype, dev)
+        ptable = pack_params(cp.names, values, B, dev)
+        return _run_segments(cp, st, ptable, values)
+
+
+class CompiledObservable:
+    """A Pauli-sum observable (fast path) or a generic linear program (Re⟨ψ|prog ψ⟩)."""
+
+    def __init__(self, obs: PauliSum | Program):
+        self.obs = obs
+        self.pauli = CompiledPauliSum.build(obs) if isinstance(obs, PauliSum) else None
+        self.program = CompiledProgram(obs) if isinstance(obs, Program) else None
+        self.n_qubits = obs.n_qubits
+
+    @property
+    def names(self) -> list[str]:
+        return self.pauli.ps.param_names if self.pauli is not None else self.program.names
+
+    def apply(self, psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
+        """λ = O ψ (new tensor)."""
+        if self.pauli is not None:
+            return pauli_apply(self.pauli, self.pauli.coef(values, psi.device), psi)
+        tmp = psi.clone()
+        tab = pack_params(self.program.names, values, psi.shape[0], psi.device)
+        return _run_segments(self.program, tmp, tab, values)
+
+    def expectation(self, psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
+        if self.pauli is not None:
+            return pauli_expectation(self.pauli, self.pauli.coef(values, psi.device), psi)
+        return dot(psi, self.apply(psi, values)).real
+
+
+# ---------------------------------------------------------------------------------------------------
+class _AdjointExpectation(torch.autograd.Function):
+    """E[b,o] = Re⟨ψ_b|O_o|ψ_b⟩ with the adjoint-method backward pass in fused sweeps.
+
+    One backward pass serves every observable: λ = Σ_o ḡ[b,o]·O_o ψ (linearity), where the reference
+    runs one `AdjointExpectation.apply` per observable (differentiable_expectation.py:153-165).
+    """
+
+    @staticmethod
+    def forward(ctx, cp: CompiledProgram, cobs: list[CompiledObservable], values: dict, state: Tensor | None,
+                dtype: torch.dtype, device: torch.device, batch: int, ptable: Tensor) -> Tensor:
+        st = prepare_state(cp.n_qubits, batch, state, dtype, device)
+        psi = _run_segments(cp, st, ptable, values)
+        cols = [o.expectation(psi, values) for o in cobs]
+        ctx.cp, ctx.cobs, ctx.values, ctx.batch = cp, cobs, {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}, batch
+        ctx.psi = psi
+        ctx.save_for_backward(ptable)
+        return torch.stack(cols, dim=1)
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        from . import hamevo
+
+        (ptable,) = ctx.saved_tensors
+        cp: CompiledProgram = ctx.cp
+        psi: Tensor = ctx.psi
+        values = ctx.values
+        dev = psi.device
+        B = ctx.batch
+        lib = cabi.load()
+        if not cp.invertible:
+            raise NotImplementedError(
+                "adjoint differentiation needs an invertible circuit (unitary gates, Scale, HamEvo); "
+                "use diff_mode='gpsr' for circuits with projectors / AddBlocks"
+            )
+        # λ = Σ_o ḡ[:,o] · O_o ψ
+        lam = None
+        go = grad_out.to(torch.float64)
+        for o, cob in enumerate(ctx.cobs):
+            w = go[:, o].to(torch.complex128)
+            if cob.pauli is not None:
+                coef = cob.pauli.coef(values, dev)
+                coef = coef.expand(coef.shape[0], B) * w[None, :]
+                if lam is None:
+                    lam = pauli_apply(cob.pauli, coef, psi)
+                else:
+                    new = torch.empty_like(lam)
+                    pauli_apply(cob.pauli, coef, psi, out=new, acc=lam, alpha=1.0, beta=1.0)
+                    lam = new
+            else:
+                t = cob.apply(psi, values)
+                scal(w, t)
+                lam = t if lam is None else lam + t
+        grads = torch.zeros(ptable.shape, dtype=torch.float64, device=dev)
+        psi = psi.clone()  # keep ctx.psi intact for double calls of backward(retain_graph=True)
+        for seg in reversed(cp.segments):
+            if seg.gates is not None:
+                dp = cp.device_plan(seg, psi.dtype, True, dev)
+                rc = lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[psi.dtype], cp.n_qubits, B, ptable.data_ptr(),
+                                             grads.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, 0, _stream_ptr(dev))
+                cabi.check(rc, "adjoint_plan")
+                continue
+            op = seg.op
+            if op.kind == OpKind.HAMEVO:
+                if isinstance(op.param, str):
+                    g_psi = hamevo.generator_apply(op, seg.compiled, psi, values, cp.n_qubits)
+                    grads[cp.slot_of[op.param]] += 2.0 * dot(lam, g_psi).imag
+                psi = hamevo.evolve(op, seg.compiled, psi, values, cp.n_qubits, dagger=True)
+                lam = hamevo.evolve(op, seg.compiled, lam, values, cp.n_qubits, dagger=True)
+            elif op.kind == OpKind.MATK:
+                bits = [cp.n_qubits - 1 - q for q in op.targets]
+                md = np.asarray(op.matrix, dtype=np.complex128).conj().T
+                psi = apply_dense(psi, md, bits)
+                lam = apply_dense(lam, md, bits)
+            else:
+                raise NotImplementedError(op.kind)
+        return None, None, None, None, None, None, None, grads
+
+
+def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], values: Mapping[str, Tensor] | None = None,
+                state: Tensor | None = None, dtype: torch.dtype = torch.complex128,
+                device: torch.device | str | None = None) -> Tensor:
+    """`[B, n_obs]` real expectation values, differentiable (adjoint method) w.r.t. every tensor in `values`
+    that feeds a gate parameter or an observable coefficient."""
+    dev = _dev(device)
+    values = dict(values or {})
+    B = infer_batch(values)
+    if state is not None:
+        B = max(B, state.shape[0])
+    cobs = list(observables)
+    ptable = pack_params(cp.names, values, B, dev)
+    real_dt = torch.float64 if dtype == torch.complex128 else torch.float32
+    if not (torch.is_grad_enabled() and ptable.requires_grad):
+        with torch.no_grad():
+            st = prepare_state(cp.n_qubits, B, state, dtype, dev)
+            psi = _run_segments(cp, st, ptable, values)
+            out = torch.stack([o.expectation(psi, values) for o in cobs], dim=1)
+            obs_grad = torch.is_grad_enabled() and any(
+                isinstance(values.get(nm), Tensor) and values[nm].requires_grad for o in cobs for nm in o.names
+            )
+        if not obs_grad:
+            return out.to(real_dt)
+        return (out + _observable_param_term(cobs, psi, values)).to(real_dt)
+    out = _AdjointExpectation.apply(cp, cobs, values, state, dtype, dev, B, ptable)
+    if any(isinstance(values.get(nm), Tensor) and values[nm].requires_grad for o in cobs for nm in o.names):
+        # recompute ψ is avoided: the Function keeps it; add the (value-free) observable-parameter path
+        psi = run(cp, values, state, dtype, dev)
+        out = out + _observable_param_term(cobs, psi, values)
+    return out.to(real_dt)
+
+
+def _observable_param_term(cobs: Sequence[CompiledObservable], psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
+    """Zero-valued tensor carrying dE/d(observable coefficient) = ⟨ψ|P_t|ψ⟩ through autograd."""
+    dev = psi.device
+    cols = []
+    for cob in cobs:
+        if cob.pauli is None or not cob.pauli.is_parametric:
+            cols.append(torch.zeros(psi.shape[0], dtype=torch.float64, device=dev))
+            continue
+        cps = cob.pauli
+        coef = cps.coef(values, dev)  # differentiable [T, Bc]
+        with torch.no_grad():
+            per_term = []
+            for t in range(cps.n_terms):
+                one = torch.zeros(cps.n_terms, 1, dtype=torch.complex128, device=dev)
+                one[t, 0] = 1.0
+                per_term.append(pauli_expectation(cps, one, psi))
+            e = torch.stack(per_term)  # [T, B]
+        lin = (coef.real * e).sum(0)
+        cols.append(lin - lin.detach())
+    return torch.stack(cols, dim=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+def sample_indices(psi: Tensor, uniforms: Tensor) -> Tensor:
+    """int64 `[B, n_shots]` basis indices by inverse-CDF on the supplied uniforms (sum-tree descent)."""
+    B, N = psi.shape
+    n = int(N).bit_length() - 1
+    dev = psi.device
+    u = uniforms.to(device=dev, dtype=torch.float64).contiguous()
+    if u.shape[0] != B:
+        raise ValueError("uniforms must have shape [batch, n_shots]")
+    shots = u.shape[1]
+    chunk = min(N, 256)
+    L = N // chunk
+    probs = torch.empty(B, N, dtype=torch.float64, device=dev)
+    tree = torch.zeros(B, 2 * L, dtype=torch.float64, device=dev)
+    out = torch.empty(B, shots, dtype=torch.int64, device=dev)
+    rc = cabi.load().b200sv_sample(psi.data_ptr(), _DT[psi.dtype], n, B, probs.data_ptr(), tree.data_ptr(), u.data_ptr(), shots, out.data_ptr(), _stream_ptr(dev))
+    cabi.check(rc, "sample")
+    return out
+
+
+def counts_from_indices(idx: Tensor, n: int, little_endian: bool = False) -> list[Counter]:
+    out = []
+    for row in idx.cpu().numpy():
+        vals, cnts = np.unique(row, return_counts=True)
+        c = Counter()
+        for v, k in zip(vals, cnts):
+            s = format(int(v), f"0{n}b")
+            c[s[::-1] if little_endian else s] = int(k)
+        out.append(c)
+    return out
+
+
+def sample(cp: CompiledProgram, values: Mapping[str, Tensor] | None = None, n_shots: int = 1, state: Tensor | None = None,
+           dtype: torch.dtype = torch.complex128, device: torch.device | str | None = None,
+           uniforms: Tensor | None = None, little_endian: bool = False) -> list[Counter]:
+    """`list[Counter]` of big-endian bitstrings — `Backend.sample` (backends/pyqtorch/backend.py:283-310)."""
+    psi = run(cp, values, state, dtype, device)
+    if uniforms is None:
+        uniforms = torch.rand(psi.shape[0], n_shots, dtype=torch.float64, device=psi.device)
+    idx = sample_indices(psi, uniforms)
+    return counts_from_indices(idx, cp.n_qubits, little_endian)

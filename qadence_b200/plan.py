@@ -1,0 +1,314 @@
+"""Fusion planner: a run of simple gates → fused sweeps → register rounds (host side, convert time).
+
+Where the reference converts a block tree into one pyqtorch module per gate
+(`/root/reference/qadence/backends/pyqtorch/convert_ops.py:273-345`, `pyq.Merge` only for chains on
+a single qubit, `:277-278`), this planner groups gates so that each group costs ONE read + ONE write
+of the state (a "sweep", `include/b200sv.h: b200sv_sweep`):
+
+* a sweep stages tiles of 2^m amplitudes in shared memory; a non-diagonal gate fits if its target
+  bit is one of the m tile bits (controls and diagonal gates fit anywhere: they are predicates /
+  phases evaluated from the basis index);
+* inside a sweep, gates are packed into rounds of r register bits;
+* gates are pulled forward past deferred gates only when they commute with all of them
+  (disjoint supports, or both acting diagonally — control or diagonal target — on every shared bit).
+
+Pure Python/numpy; no CUDA needed (unit-tested on CPU against the oracle).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+
+from .program import Op, OpKind
+
+# ---- binary layouts (must match include/b200sv.h) ---------------------------------------------
+GATE_DT = np.dtype(
+    [
+        ("kind", "<i4"), ("a", "<i4"), ("a2", "<i4"), ("ext_bit", "<i4"), ("ctrl_ext", "<u8"),
+        ("ctrl_reg", "<i4"), ("slot", "<i4"), ("cidx", "<i4"), ("grad_row", "<i4"), ("flags", "<i4"), ("pad", "<i4"),
+    ]
+)
+ROUND_DT = np.dtype(
+    [("first_gate", "<i4"), ("n_gates", "<i4"), ("regpos", "u1", (4,)), ("thrpos", "u1", (12,)), ("pad", "<i4", (2,))]
+)
+SWEEP_DT = np.dtype(
+    [
+        ("m", "<i4"), ("r", "<i4"), ("first_round", "<i4"), ("n_rounds", "<i4"), ("first_gate", "<i4"),
+        ("n_gates", "<i4"), ("n_outer", "<i4"), ("pad", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
+    ]
+)
+PTERM_DT = np.dtype([("xmask", "<u8"), ("zmask", "<u8"), ("coef_row", "<i4"), ("n_y", "<i4"), ("pad", "<i4", (2,))])
+assert GATE_DT.itemsize == 48 and ROUND_DT.itemsize == 32 and SWEEP_DT.itemsize == 96 and PTERM_DT.itemsize == 32
+
+GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
+GF_GRAD = 1
+
+MAX_GATES_PER_SWEEP = 96
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+
+
+@dataclass
+class TileConfig:
+    """Tile geometry for one (dtype, mode): m tile bits, r register bits, `low` forced low bits."""
+
+    m: int
+    r: int
+    low: int
+    fold: int  # bank-swizzle fold width: 3 for 16-byte amplitudes, 4 for 8-byte
+
+    @staticmethod
+    def default(dtype_is_c128: bool, adjoint: bool) -> "TileConfig":
+        if dtype_is_c128:
+            return TileConfig(m=11, r=3, low=4, fold=3) if not adjoint else TileConfig(m=10, r=3, low=4, fold=3)
+        return TileConfig(m=12, r=4, low=5, fold=4) if not adjoint else TileConfig(m=11, r=3, low=5, fold=4)
+
+
+@dataclass
+class _G:
+    """A simple gate in bit-position space."""
+
+    kind: int
+    hard: tuple[int, ...]  # bit positions that must be register bits (non-diagonal targets)
+    soft: int  # bit position of a diagonal target, or -1
+    ctrl: tuple[int, ...]
+    slot: int
+    cidx: int
+    grad: bool
+    src: int  # index in the op list (diagnostics)
+
+    @property
+    def bits_any(self) -> set[int]:
+        s = set(self.hard) | set(self.ctrl)
+        if self.soft >= 0:
+            s.add(self.soft)
+        return s
+
+
+class ConstPool:
+    def __init__(self) -> None:
+        self.data: list[complex] = []
+        self._index: dict[tuple, int] = {}
+
+    def add(self, vals: Sequence[complex]) -> int:
+        key = tuple(complex(v) for v in vals)
+        if key not in self._index:
+            self._index[key] = len(self.data)
+            self.data.extend(key)
+        return self._index[key]
+
+    def array(self) -> np.ndarray:
+        a = np.zeros((max(1, len(self.data)), 2), dtype=np.float64)
+        for i, v in enumerate(self.data):
+            a[i, 0], a[i, 1] = v.real, v.imag
+        return a
+
+
+def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, r: int = 2) -> list[_G]:
+    out: list[_G] = []
+    for i, op in enumerate(ops):
+        bit = lambda q: n - 1 - q  # noqa: E731
+        ctrl = tuple(sorted(bit(q) for q in op.controls))
+        slot, cidx, grad = -1, -1, False
+        if op.kind in (OpKind.RX, OpKind.RY, OpKind.RZ, OpKind.PHASE, OpKind.SCALE):
+            if isinstance(op.param, str):
+                slot, grad = slot_of[op.param], True
+            else:
+                cidx = pool.add([complex(op.param)])
+        if op.kind == OpKind.MAT1:
+            m = np.asarray(op.matrix, dtype=np.complex128).reshape(2, 2)
+            t = bit(op.targets[0])
+            if m[0, 1] == 0 and m[1, 0] == 0:
+                out.append(_G(GK_DIAG, (), t, ctrl, -1, pool.add([m[0, 0], m[1, 1]]), False, i))
+            elif np.array_equal(m, _X):
+                out.append(_G(GK_X, (t,), -1, ctrl, -1, -1, False, i))
+            elif np.all(m.imag == 0):
+                out.append(_G(GK_REAL, (t,), -1, ctrl, -1, pool.add([complex(m[0, 0].real, m[0, 1].real), complex(m[1, 0].real, m[1, 1].real)]), False, i))
+            else:
+                out.append(_G(GK_MAT, (t,), -1, ctrl, -1, pool.add(list(m.ravel())), False, i))
+        elif op.kind in (OpKind.RX, OpKind.RY):
+            out.append(_G(GK_RX if op.kind == OpKind.RX else GK_RY, (bit(op.targets[0]),), -1, ctrl, slot, cidx, grad, i))
+        elif op.kind in (OpKind.RZ, OpKind.PHASE):
+            out.append(_G(GK_RZ if op.kind == OpKind.RZ else GK_PHASE, (), bit(op.targets[0]), ctrl, slot, cidx, grad, i))
+        elif op.kind == OpKind.SWAP:
+            ta, tb = (bit(q) for q in op.targets)
+            if r >= 2:
+                out.append(_G(GK_SWAP, tuple(sorted((ta, tb))), -1, ctrl, -1, -1, False, i))
+            else:  # a single register bit cannot hold both targets: SWAP = 3 CNOTs (block_to_tensor.py:207-223)
+                for c, t in ((ta, tb), (tb, ta), (ta, tb)):
+                    out.append(_G(GK_X, (t,), -1, tuple(sorted((*ctrl, c))), -1, -1, False, i))
+        elif op.kind == OpKind.SCALE:
+            out.append(_G(GK_SCALE, (), -1, (), slot, cidx, grad, i))
+        else:
+            raise ValueError(f"op kind {op.kind} is not a simple gate")
+    return out
+
+
+def _pack(gates: list[_G], capacity: int, forced: set[int], max_gates: int) -> list[tuple[list[_G], set[int]]]:
+    """Greedy commutation-aware packing of `gates` (ordered) into groups whose hard bits ∪ forced fit capacity."""
+    groups: list[tuple[list[_G], set[int]]] = []
+    pending = list(gates)
+    while pending:
+        bits = set(forced)
+        taken: list[_G] = []
+        deferred: list[_G] = []
+        def_any: set[int] = set()  # every bit touched by a deferred gate
+        def_hard: set[int] = set()  # bits a deferred gate acts on non-diagonally
+        for g in pending:
+            hard = set(g.hard)
+            commutes = not (g.bits_any & def_hard) and not (hard & def_any)
+            fits = len(bits | hard) <= capacity and len(taken) < max_gates
+            if commutes and fits:
+                taken.append(g)
+                bits |= hard
+            else:
+                deferred.append(g)
+                def_any |= g.bits_any
+                def_hard |= hard
+        if not taken:  # cannot happen: the first pending gate always commutes with the empty set
+            raise RuntimeError("planner stalled (gate needs more register bits than the tile offers)")
+        groups.append((taken, bits))
+        pending = deferred
+    return groups
+
+
+def _thread_positions(m: int, regpos: list[int], fold: int) -> list[int]:
+    avail = [p for p in range(m) if p not in regpos]
+    chosen: list[int] = []
+    used_res: set[int] = set()
+    for _ in range(min(fold, len(avail))):
+        pick = next((p for p in avail if p % fold not in used_res), None)
+        if pick is None:
+            pick = avail[0]
+        chosen.append(pick)
+        used_res.add(pick % fold)
+        avail.remove(pick)
+    return chosen + avail
+
+
+@dataclass
+class SweepPlan:
+    """Packed, device-uploadable plan for one run of simple gates."""
+
+    n_qubits: int
+    cfg: TileConfig
+    sweeps: np.ndarray
+    rounds: np.ndarray
+    gates: np.ndarray
+    consts: np.ndarray  # [n_const, 2] float64
+    n_source_gates: int
+    # diagnostics: for each sweep, list of rounds, each a list of source-op indices (execution order)
+    order: list[list[list[int]]] = field(default_factory=list)
+
+    @property
+    def n_sweeps(self) -> int:
+        return int(self.sweeps.shape[0])
+
+    def execution_order(self) -> list[int]:
+        return [i for sw in self.order for rd in sw for i in rd]
+
+
+def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig) -> SweepPlan:
+    pool = ConstPool()
+    m = min(cfg.m, n)
+    r = max(1, min(cfg.r, m)) if n > 0 else 1
+    if m - r > 8:
+        m = r + 8
+    lowered = _lower(ops, n, slot_of, pool, r)
+    forced = set(range(min(cfg.low, m)))
+    sweep_groups = _pack(lowered, m, forced, MAX_GATES_PER_SWEEP)
+
+    sweeps = np.zeros(len(sweep_groups), dtype=SWEEP_DT)
+    rounds_l: list[np.ndarray] = []
+    gates_l: list[np.ndarray] = []
+    order: list[list[list[int]]] = []
+    n_gates_total = 0
+    n_rounds_total = 0
+    for si, (sgates, bits) in enumerate(sweep_groups):
+        # complete the tile with the lowest unused bit positions
+        tile = sorted(bits)
+        for p in range(n):
+            if len(tile) >= m:
+                break
+            if p not in bits:
+                tile.append(p)
+        tile = sorted(tile)
+        assert len(tile) == m, (tile, m)
+        local = {p: i for i, p in enumerate(tile)}
+        outer = [p for p in range(n) if p not in local]
+        sw = sweeps[si]
+        sw["m"], sw["r"], sw["n_outer"] = m, r, n - m
+        sw["first_round"], sw["first_gate"] = n_rounds_total, n_gates_total
+        sw["tile_bits"][:m] = tile
+        sw["outer_bits"][: len(outer)] = outer
+        round_groups = _pack(sgates, r, set(), MAX_GATES_PER_SWEEP)
+        sw_order: list[list[int]] = []
+        for rgates, rbits in round_groups:
+            regs = sorted(local[p] for p in rbits)
+            for p in range(m):  # pad register set to exactly r positions (prefer high tile bits: keeps low bits on threads)
+                if len(regs) >= r:
+                    break
+                cand = m - 1 - p
+                if cand not in regs:
+                    regs.append(cand)
+            regs = sorted(regs)
+            reg_index = {tile[lp]: a for a, lp in enumerate(regs)}  # global bit -> register index
+            rd = np.zeros(1, dtype=ROUND_DT)
+            rd["first_gate"], rd["n_gates"] = n_gates_total, len(rgates)
+            rd["regpos"][0, :r] = regs
+            thr = _thread_positions(m, regs, cfg.fold)
+            rd["thrpos"][0, : len(thr)] = thr
+            rounds_l.append(rd)
+            ga = np.zeros(len(rgates), dtype=GATE_DT)
+            for gi, g in enumerate(rgates):
+                rec = ga[gi]
+                rec["kind"], rec["slot"], rec["cidx"] = g.kind, g.slot, g.cidx
+                rec["a"], rec["a2"], rec["ext_bit"] = -1, -1, 0
+                rec["grad_row"] = g.slot if g.grad else -1
+                rec["flags"] = GF_GRAD if g.grad else 0
+                if g.kind == GK_SWAP:
+                    rec["a"], rec["a2"] = reg_index[g.hard[0]], reg_index[g.hard[1]]
+                elif g.hard:
+                    rec["a"] = reg_index[g.hard[0]]
+                elif g.soft >= 0:
+                    if g.soft in reg_index:
+                        rec["a"] = reg_index[g.soft]
+                    else:
+                        rec["ext_bit"] = g.soft
+                cext, creg = 0, 0
+                for cb in g.ctrl:
+                    if cb in reg_index:
+                        creg |= 1 << reg_index[cb]
+                    else:
+                        cext |= 1 << cb
+                rec["ctrl_ext"], rec["ctrl_reg"] = cext, creg
+            gates_l.append(ga)
+            sw_order.append([g.src for g in rgates])
+            n_gates_total += len(rgates)
+            n_rounds_total += 1
+        sw["n_rounds"] = len(round_groups)
+        sw["n_gates"] = n_gates_total - int(sw["first_gate"])
+        order.append(sw_order)
+    rounds = np.concatenate(rounds_l) if rounds_l else np.zeros(0, dtype=ROUND_DT)
+    gates = np.concatenate(gates_l) if gates_l else np.zeros(0, dtype=GATE_DT)
+    return SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), order)
+
+
+# ---- Pauli sums -----------------------------------------------------------------------------------
+def pack_pauli_terms(paulis_per_term: Sequence[Sequence[tuple[int, str]]], n: int) -> np.ndarray:
+    """Pack Pauli strings (qubit, 'X'|'Y'|'Z') into b200sv_pterm records; coef_row = term index."""
+    arr = np.zeros(len(paulis_per_term), dtype=PTERM_DT)
+    for t, ps in enumerate(paulis_per_term):
+        x = z = ny = 0
+        for q, p in ps:
+            bit = 1 << (n - 1 - q)
+            if p in ("X", "Y"):
+                x |= bit
+            if p in ("Z", "Y"):
+                z |= bit
+            if p == "Y":
+                ny += 1
+        arr[t]["xmask"], arr[t]["zmask"], arr[t]["coef_row"], arr[t]["n_y"] = x, z, t, ny
+    return arr

@@ -1,0 +1,99 @@
+"""Planner (host logic) vs the oracle, on CPU: the packed sweep plan, interpreted record by record,
+must reproduce the op-by-op einsum result for random circuits of every simple gate kind."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import statevec as oracle
+from qadence_b200.plan import TileConfig, build_plan
+from qadence_b200.program import CONST_MATS, OpKind, ProgramBuilder, hea_program
+from tests.plan_emulator import emulate
+
+
+def random_program(n: int, n_gates: int, rng: np.random.Generator, n_params: int = 6):
+    b = ProgramBuilder(n)
+    names = [f"p{i}" for i in range(n_params)]
+    fixed = [k for k in CONST_MATS if k not in ("Zero",)]
+    for _ in range(n_gates):
+        kind = rng.integers(0, 8)
+        qs = list(rng.permutation(n))
+        t = int(qs[0])
+        n_ctrl = int(rng.integers(0, min(3, n))) if n > 1 else 0
+        ctrl = [int(q) for q in qs[1 : 1 + n_ctrl]]
+        param = names[int(rng.integers(n_params))] if rng.random() < 0.7 else float(rng.normal())
+        if kind == 0:
+            b.gate(fixed[int(rng.integers(len(fixed)))], t, ctrl)
+        elif kind == 1:
+            b.rot(OpKind.RX, t, param, ctrl)
+        elif kind == 2:
+            b.rot(OpKind.RY, t, param, ctrl)
+        elif kind == 3:
+            b.rot(OpKind.RZ, t, param, ctrl)
+        elif kind == 4:
+            b.rot(OpKind.PHASE, t, param, ctrl)
+        elif kind == 5 and n >= 2:
+            b.SWAP(int(qs[0]), int(qs[1]), [int(q) for q in qs[2 : 2 + min(n_ctrl, n - 2)]])
+        elif kind == 6:
+            m = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+            b._add(__import__("qadence_b200").Op(OpKind.MAT1, (t,), tuple(ctrl), matrix=m, label="rand"))
+        else:
+            b.scale(param if rng.random() < 0.5 else complex(rng.normal(), rng.normal()))
+    return b.build(), names
+
+
+CONFIGS = [
+    TileConfig(m=11, r=3, low=4, fold=3),
+    TileConfig(m=5, r=2, low=2, fold=3),
+    TileConfig(m=6, r=4, low=3, fold=4),
+    TileConfig(m=4, r=1, low=1, fold=3),
+]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7])
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"m{c.m}r{c.r}")
+def test_plan_matches_oracle(n: int, cfg: TileConfig) -> None:
+    rng = np.random.default_rng(100 * n + cfg.m)
+    prog, names = random_program(n, 40, rng)
+    B = 3
+    values = {nm: torch.tensor(rng.normal(size=B)) for nm in names}
+    psi0 = torch.tensor(rng.normal(size=(B, 2**n)) + 1j * rng.normal(size=(B, 2**n)))
+    want = oracle.run(prog, values, psi0).numpy()
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, cfg)
+    params = np.stack([values[nm].numpy() for nm in prog.param_names]) if prog.param_names else np.zeros((1, B))
+    got = emulate(plan, psi0.numpy(), params)
+    assert sorted(set(plan.execution_order())) == list(range(len(prog.ops)))
+    np.testing.assert_allclose(got, want, atol=1e-10 * max(1.0, np.abs(want).max()))
+
+
+def test_hea_fuses_into_few_sweeps() -> None:
+    n, depth = 20, 8
+    prog = hea_program(n, depth)
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, TileConfig.default(True, False))
+    assert len(prog.ops) == 632
+    assert plan.n_sweeps <= 40, plan.n_sweeps  # vs 632 state round trips gate by gate
+    for sw in plan.sweeps:
+        assert set(range(4)) <= set(int(x) for x in sw["tile_bits"][: sw["m"]])  # coalesced low bits
+
+
+def test_dagger_plan_inverts() -> None:
+    rng = np.random.default_rng(7)
+    n = 6
+    b = ProgramBuilder(n)
+    for q in range(n):
+        b.RX(q, "a").RY(q, 0.3).RZ(q, "b").H(q)
+    for q in range(n - 1):
+        b.CNOT(q, q + 1).CPHASE(q, q + 1, "c")
+    b.SWAP(0, 5).scale(1.5)
+    prog = b.build()
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, TileConfig(m=5, r=3, low=2, fold=3))
+    params = rng.normal(size=(3, 2))
+    psi0 = rng.normal(size=(2, 2**n)) + 1j * rng.normal(size=(2, 2**n))
+    fwd = emulate(plan, psi0, params)
+    back = emulate(plan, fwd, params, dagger=True)
+    np.testing.assert_allclose(back, psi0 * 1.5**2, atol=1e-12)  # Scale is not unitary: s·conj(s)

@@ -53,7 +53,19 @@ enum {
 
 #define B200SV_GF_GRAD 1 /* gate.flags: parametric gate whose gradient is requested (adjoint)      */
 
-typedef struct b200sv_gate {   /* 48 bytes */
+/* execution class of a resolved entry (chosen by the planner; a chain of 1-qubit gates on one
+ * target is multiplied into a single 2x2 per CTA and executed as the class of the product) */
+enum {
+  B200SV_XK_MAT = 0,  /* general complex 2x2                      */
+  B200SV_XK_REAL = 1, /* real 2x2 (RY, H, chains of those)        */
+  B200SV_XK_RX = 2,   /* [[c, -i s], [-i s, c]] (RX chains)       */
+  B200SV_XK_DIAG = 3, /* diagonal (RZ, PHASE, Z, S, T, N, chains) */
+  B200SV_XK_X = 4,
+  B200SV_XK_SWAP = 5,
+  B200SV_XK_SCALE = 6
+};
+
+typedef struct b200sv_gate {   /* 56 bytes */
   int32_t kind;       /* B200SV_GK_*                                                               */
   int32_t a;          /* register index (0..r-1) of the target inside its round; -1: external      */
   int32_t a2;         /* second register index (SWAP), else -1                                     */
@@ -64,15 +76,36 @@ typedef struct b200sv_gate {   /* 48 bytes */
   int32_t cidx;       /* constant-pool offset in complex128 units, or -1                           */
   int32_t grad_row;   /* adjoint: row of the gradient table this gate accumulates into, or -1      */
   int32_t flags;
-  int32_t pad;
+  int32_t chain;      /* >= 1: leader of `chain` consecutive records merged into one 2x2; 0: follower */
+  int32_t xidx;       /* index of the resolved entry inside its sweep (followers repeat the leader's) */
+  int32_t xkind;      /* B200SV_XK_* of the resolved entry (leader)                                */
 } b200sv_gate;
 
-typedef struct b200sv_round {  /* 32 bytes */
+#define B200SV_GF_MSLOT 2 /* gate.flags: chain executed in the round's unrolled matrix phase      */
+#define B200SV_XK_PERM 7  /* X / CNOT / SWAP folded into the round's index permutation (not executed) */
+#define B200SV_RF_PERM 1  /* round.flags: the permutation phase is not the identity                  */
+
+/* A round = three phases over the 2^r amplitudes each thread holds in registers:
+ *   M: one merged 2x2 per register bit (mslot[a], unrolled, no dispatch);
+ *   G: generic resolved entries [first_exec, first_exec + n_exec) (controlled gates, external
+ *      diagonals, scales ...), interpreted in order;
+ *   P: uncontrolled X, singly-controlled X (CNOT) and SWAP gates on tile bits, composed into one
+ *      GF(2)-affine map of the tile index  pi(i) = XOR_{bits of i} pcol[bit] ^ pconst ^ XOR_k pext[k].vec
+ *      (k over external control bits that are 1 for this CTA) and applied for free by storing the
+ *      registers at pi(index) instead of index.  Backward execution loads from pi(index). */
+typedef struct b200sv_round {  /* 96 bytes */
   int32_t first_gate; /* absolute index into the gate array                                        */
   int32_t n_gates;
   uint8_t regpos[4];  /* tile-local bit positions held in registers (ascending)                    */
   uint8_t thrpos[12]; /* tile-local bit position of thread-index bit i                             */
-  int32_t pad[2];
+  int32_t first_exec; /* G-phase resolved entries of this round, relative to the sweep             */
+  int32_t n_exec;
+  int32_t mslot[4];   /* M-phase: resolved-entry index (relative to the sweep) for register bit a, or -1 */
+  uint16_t pcol[12];  /* P-phase: image of tile-local bit i                                        */
+  uint16_t pconst;
+  uint16_t n_pext;
+  struct { uint8_t bit; uint8_t pad; uint16_t vec; } pext[4]; /* external control bit (global position) -> xor vector */
+  int32_t flags;      /* B200SV_RF_*                                                               */
 } b200sv_round;
 
 typedef struct b200sv_sweep {  /* 96 bytes: one kernel launch = one read + one write of the state  */
@@ -83,7 +116,7 @@ typedef struct b200sv_sweep {  /* 96 bytes: one kernel launch = one read + one w
   int32_t first_gate;
   int32_t n_gates;
   int32_t n_outer;      /* = n_local - m                                                           */
-  int32_t pad;
+  int32_t n_exec;       /* resolved entries (chains) in this sweep                                  */
   uint8_t tile_bits[16];  /* global bit position of tile-local bit i (ascending)                   */
   uint8_t outer_bits[48]; /* global bit positions enumerated by the CTA index (ascending)          */
 } b200sv_sweep;

@@ -30,7 +30,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
                  int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
-  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_gates);
+  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec);
   auto kern = sweep_kernel<real, R, ADJ>;
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
@@ -38,6 +38,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
     configured = smem;
   }
   const int nt = 1 << (sw.m - R);
+  if (nt > SweepCfg<real, R, ADJ>::MAXT) return B200SV_E_ARG;
   const long long grid = ((long long)batch) << sw.n_outer;
   if (grid <= 0 || grid > 2147483647ll) return B200SV_E_ARG;
   kern<<<(unsigned)grid, nt, smem, st>>>((c2*)psi, (c2*)lam, params, grads, plan->sweeps, plan->rounds,

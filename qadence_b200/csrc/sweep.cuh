@@ -3,14 +3,22 @@
 // One launch = one "sweep": every CTA stages a tile of 2^m amplitudes of one batch element in
 // shared memory (coalesced, vectorised 16-byte global accesses), then runs several "rounds".  In a
 // round each thread pulls 2^r amplitudes into registers (the r "register bits" of that round),
-// applies every gate of the round entirely in registers (sincos for parametric rotations is
-// evaluated in-kernel, once per CTA), and writes them back to the XOR-swizzled tile.  After the
-// last round the tile is written back: 2·S bytes of HBM traffic for all gates of the sweep
-// instead of 2·S per gate (the reference's einsum-per-gate loop,
+// applies every gate of the round entirely in registers, and writes them back to the XOR-swizzled
+// tile.  After the last round the tile is written back: 2·S bytes of HBM traffic for all gates of
+// the sweep instead of 2·S per gate (the reference's einsum-per-gate loop,
 // /root/reference/qadence/backends/pyqtorch/backend.py:176).
 //
-// The adjoint variant (ADJ) walks the same records backwards on ψ and λ simultaneously and reduces
-// the per-parameter gradient inner products 2·Re<λ|∂U|ψ> in the same pass (4·S bytes).
+// Per-CTA prologue ("resolve"): parametric gates evaluate sincos in-kernel from the parameter
+// table of THIS batch element, and chains of 1-qubit gates on the same target are multiplied into a
+// single 2x2 (what `pyq.Merge` does for single-qubit chains, convert_ops.py:277-278, but per CTA and
+// for any chain the planner finds).
+//
+// The adjoint variant (ADJ) walks the same records backwards on ψ and λ simultaneously.  For every
+// chain it reduces the four moments  m_P = Im<λ|P|ψ>, P ∈ {I, X, Y, Z}  of the POST-chain states on
+// the control-active subspace, un-applies the merged 2x2 from both states, and the epilogue turns
+// the moments into the gradient of every parametric gate of the chain:
+//   g_i = 2 Re<λ_i| ∂G_i G_i† |ψ_i> = c_I m_I + (W_i c W_i†)·m,  W_i = G_k ··· G_{i+1},
+// with ∂G G† = −(i/2)(c_I I + c·σ): RX c=x̂, RY c=ŷ, RZ c=ẑ, PHASE c_I=−1, c=ẑ.   (4·S bytes.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,14 +38,18 @@ template <typename T> __device__ __forceinline__ T cmul(T a, T b) {
   return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// execution kinds after per-CTA resolution of parameters
-enum { EX_MAT = 0, EX_REAL, EX_RX, EX_DIAG, EX_X, EX_SWAP, EX_SCALE, EX_NOP };
-enum { GR_NONE = 0, GR_RX, GR_RY, GR_RZ, GR_PHASE, GR_SCALE };
+// flat opcodes of resolved gates: base + register index
+enum {
+  OP_NOP = 0, OP_SCALE = 1, OP_DIAGEXT = 2,
+  OP_SWAP = 4,   // + pair index (a<b): 01,02,12,03,13,23 -> 0..5
+  OP_MAT = 16, OP_REAL = 24, OP_RX = 32, OP_DIAG = 40, OP_X = 48
+};
+enum { GR_NONE = 0, GR_CHAIN = 1, GR_SCALE = 2 };
 
-template <typename real> struct ExecGate {
+template <typename real> struct __align__(16) ExecGate {
   real m[8];
   unsigned long long ctrl_ext;
-  int ex, a, a2, ext_bit, ctrl_reg, gr;
+  int op, ext_bit, cr, gr;
 };
 
 template <typename real> __device__ __forceinline__ int swz(int e);
@@ -49,74 +61,143 @@ template <> __device__ __forceinline__ int swz<float>(int e) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-CTA resolution of one gate record into an ExecGate (matrix entries for THIS batch element)
+// 2x2 complex helpers in double (prologue / epilogue only)
+// ------------------------------------------------------------------------------------------------
+struct M22 { double v[8]; };  // m00 m01 m10 m11 as (re, im)
+
+__device__ __forceinline__ M22 m22_mul(const M22& a, const M22& b) {  // a * b
+  M22 r;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double re = 0, im = 0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double ar = a.v[2 * (2 * i + k)], ai = a.v[2 * (2 * i + k) + 1];
+        const double br = b.v[2 * (2 * k + j)], bi = b.v[2 * (2 * k + j) + 1];
+        re += ar * br - ai * bi; im += ar * bi + ai * br;
+      }
+      r.v[2 * (2 * i + j)] = re; r.v[2 * (2 * i + j) + 1] = im;
+    }
+  return r;
+}
+__device__ __forceinline__ M22 m22_dag(const M22& a) {
+  M22 r;
+  r.v[0] = a.v[0]; r.v[1] = -a.v[1]; r.v[2] = a.v[4]; r.v[3] = -a.v[5];
+  r.v[4] = a.v[2]; r.v[5] = -a.v[3]; r.v[6] = a.v[6]; r.v[7] = -a.v[7];
+  return r;
+}
+__device__ __forceinline__ M22 m22_eye() { M22 r = {{1, 0, 0, 0, 0, 0, 1, 0}}; return r; }
+
+__device__ __forceinline__ double gate_theta(const b200sv_gate& g, const double* __restrict__ params,
+                                             const double* __restrict__ consts, long long batch, long long b,
+                                             double* im) {
+  if (g.slot >= 0) { *im = 0.0; return params[(long long)g.slot * batch + b]; }
+  *im = consts[2 * g.cidx + 1];
+  return consts[2 * g.cidx];
+}
+
+// forward 2x2 of an elementary 1-qubit record
+__device__ M22 elem_matrix(const b200sv_gate& g, const double* __restrict__ params,
+                           const double* __restrict__ consts, long long batch, long long b) {
+  M22 r = m22_eye();
+  double th_im;
+  switch (g.kind) {
+    case B200SV_GK_MAT: { const double* c = consts + 2 * g.cidx; for (int i = 0; i < 8; ++i) r.v[i] = c[i]; } break;
+    case B200SV_GK_REAL: { const double* c = consts + 2 * g.cidx; r.v[0] = c[0]; r.v[2] = c[1]; r.v[4] = c[2]; r.v[6] = c[3]; } break;
+    case B200SV_GK_RX: { double s, c; sincos(0.5 * gate_theta(g, params, consts, batch, b, &th_im), &s, &c);
+      r.v[0] = c; r.v[6] = c; r.v[2] = 0; r.v[3] = -s; r.v[4] = 0; r.v[5] = -s; } break;
+    case B200SV_GK_RY: { double s, c; sincos(0.5 * gate_theta(g, params, consts, batch, b, &th_im), &s, &c);
+      r.v[0] = c; r.v[2] = -s; r.v[4] = s; r.v[6] = c; } break;
+    case B200SV_GK_RZ: { double s, c; sincos(0.5 * gate_theta(g, params, consts, batch, b, &th_im), &s, &c);
+      r.v[0] = c; r.v[1] = -s; r.v[6] = c; r.v[7] = s; } break;
+    case B200SV_GK_PHASE: { double s, c; sincos(gate_theta(g, params, consts, batch, b, &th_im), &s, &c);
+      r.v[6] = c; r.v[7] = s; } break;
+    case B200SV_GK_DIAG: { const double* c = consts + 2 * g.cidx; r.v[0] = c[0]; r.v[1] = c[1]; r.v[6] = c[2]; r.v[7] = c[3]; } break;
+    case B200SV_GK_X: r.v[0] = 0; r.v[6] = 0; r.v[2] = 1; r.v[4] = 1; break;
+    default: break;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-CTA resolution of one exec entry (chain leader record + followers) into an ExecGate
 // ------------------------------------------------------------------------------------------------
 template <typename real>
-__device__ void resolve_gate(const b200sv_gate& g, ExecGate<real>& e, const double* __restrict__ params,
-                             const double* __restrict__ consts, long long batch, long long b, int dir,
-                             bool want_grad) {
+__device__ void resolve_gate(const b200sv_gate* __restrict__ recs, ExecGate<real>& e,
+                             const double* __restrict__ params, const double* __restrict__ consts,
+                             long long batch, long long b, int dir, bool adj) {
+  const b200sv_gate& g = recs[0];
   e.ctrl_ext = g.ctrl_ext;
-  e.a = g.a; e.a2 = g.a2; e.ext_bit = g.ext_bit; e.ctrl_reg = g.ctrl_reg;
+  e.ext_bit = g.ext_bit; e.cr = g.ctrl_reg;
   e.gr = GR_NONE;
-  double theta = 0.0, theta_im = 0.0;
-  if (g.kind >= B200SV_GK_RX && g.kind <= B200SV_GK_PHASE || g.kind == B200SV_GK_SCALE) {
-    if (g.slot >= 0) theta = params[(long long)g.slot * batch + b];
-    else { theta = consts[2 * g.cidx]; theta_im = consts[2 * g.cidx + 1]; }
+  const int xk = g.xkind;
+  if (xk == B200SV_XK_X) { e.op = OP_X + g.a; return; }
+  if (xk == B200SV_XK_SWAP) {
+    int a = g.a, c = g.a2; if (a > c) { const int t = a; a = c; c = t; }
+    e.op = OP_SWAP + (c * (c - 1)) / 2 + a; return;
   }
-  const bool grad = want_grad && (g.flags & B200SV_GF_GRAD) && g.grad_row >= 0;
-  switch (g.kind) {
-    case B200SV_GK_MAT: {
-      const double* c = consts + 2 * g.cidx;
-      if (dir > 0) { for (int i = 0; i < 8; ++i) e.m[i] = (real)c[i]; }
-      else {  // conjugate transpose
-        e.m[0] = (real)c[0]; e.m[1] = (real)-c[1]; e.m[2] = (real)c[4]; e.m[3] = (real)-c[5];
-        e.m[4] = (real)c[2]; e.m[5] = (real)-c[3]; e.m[6] = (real)c[6]; e.m[7] = (real)-c[7];
-      }
-      e.ex = EX_MAT; break;
+  if (xk == B200SV_XK_SCALE) {
+    double ti; const double tr = gate_theta(g, params, consts, batch, b, &ti);
+    if (dir > 0) { e.m[0] = (real)tr; e.m[1] = (real)ti; }
+    else {  // psi <- psi / s (inverse), lambda <- conj(s) lambda (adjoint)
+      const double d = tr * tr + ti * ti;
+      e.m[0] = (real)(tr / d); e.m[1] = (real)(-ti / d); e.m[2] = (real)tr; e.m[3] = (real)-ti;
     }
-    case B200SV_GK_REAL: {
-      const double* c = consts + 2 * g.cidx;  // m00 m01 m10 m11
-      e.m[0] = (real)c[0]; e.m[3] = (real)c[3];
-      e.m[1] = (real)(dir > 0 ? c[1] : c[2]); e.m[2] = (real)(dir > 0 ? c[2] : c[1]);
-      e.ex = EX_REAL; break;
+    e.op = OP_SCALE;
+    if (adj && (g.flags & B200SV_GF_GRAD)) e.gr = GR_SCALE;
+    return;
+  }
+  // 1-qubit chain: product of `chain` elementary matrices, first record applied first
+  M22 prod = elem_matrix(g, params, consts, batch, b);
+  bool any_grad = (g.flags & B200SV_GF_GRAD) != 0;
+  for (int i = 1; i < g.chain; ++i) {
+    prod = m22_mul(elem_matrix(recs[i], params, consts, batch, b), prod);
+    any_grad |= (recs[i].flags & B200SV_GF_GRAD) != 0;
+  }
+  if (dir < 0) prod = m22_dag(prod);
+  if (adj && any_grad) e.gr = GR_CHAIN;
+  if (g.flags & B200SV_GF_MSLOT) {  // unrolled matrix phase: always a general 2x2
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e.m[i] = (real)prod.v[i];
+    e.op = OP_MAT + g.a;
+    return;
+  }
+  switch (xk) {
+    case B200SV_XK_RX: e.m[0] = (real)prod.v[0]; e.m[1] = (real)-prod.v[3]; e.op = OP_RX + g.a; break;  // [[c,-is],[-is,c]]
+    case B200SV_XK_REAL: e.m[0] = (real)prod.v[0]; e.m[1] = (real)prod.v[2]; e.m[2] = (real)prod.v[4]; e.m[3] = (real)prod.v[6];
+      e.op = OP_REAL + g.a; break;
+    case B200SV_XK_DIAG: e.m[0] = (real)prod.v[0]; e.m[1] = (real)prod.v[1]; e.m[2] = (real)prod.v[6]; e.m[3] = (real)prod.v[7];
+      e.op = g.a >= 0 ? OP_DIAG + g.a : OP_DIAGEXT; break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e.m[i] = (real)prod.v[i];
+      e.op = OP_MAT + g.a; break;
+  }
+}
+
+// epilogue: turn the four moments of a chain into per-gate gradients
+__device__ void chain_gradients(const b200sv_gate* __restrict__ recs, const double* mom,
+                                const double* __restrict__ params, const double* __restrict__ consts,
+                                double* __restrict__ grads, long long batch, long long b) {
+  const int k = recs[0].chain;
+  M22 W = m22_eye();
+  for (int i = k - 1; i >= 0; --i) {
+    const b200sv_gate& g = recs[i];
+    if ((g.flags & B200SV_GF_GRAD) && g.grad_row >= 0) {
+      // P = c·σ in {X, Y, Z};  A = W P W†  (traceless Hermitian) = [[az, ax - i ay],[ax + i ay, -az]]
+      M22 P = {{0, 0, 0, 0, 0, 0, 0, 0}};
+      double cI = 0.0;
+      if (g.kind == B200SV_GK_RX) { P.v[2] = 1; P.v[4] = 1; }
+      else if (g.kind == B200SV_GK_RY) { P.v[3] = -1; P.v[5] = 1; }
+      else { P.v[0] = 1; P.v[6] = -1; if (g.kind == B200SV_GK_PHASE) cI = -1.0; }
+      const M22 A = m22_mul(m22_mul(W, P), m22_dag(W));
+      const double az = A.v[0], ax = A.v[4], ay = A.v[5];
+      const double gsum = cI * mom[0] + ax * mom[1] + ay * mom[2] + az * mom[3];
+      atomicAdd(&grads[(long long)g.grad_row * batch + b], gsum);
     }
-    case B200SV_GK_RX: {
-      double s, c; sincos(0.5 * theta, &s, &c); if (dir < 0) s = -s;
-      e.m[0] = (real)c; e.m[1] = (real)s; e.ex = EX_RX; if (grad) e.gr = GR_RX; break;
-    }
-    case B200SV_GK_RY: {
-      double s, c; sincos(0.5 * theta, &s, &c); if (dir < 0) s = -s;
-      e.m[0] = (real)c; e.m[1] = (real)-s; e.m[2] = (real)s; e.m[3] = (real)c;
-      e.ex = EX_REAL; if (grad) e.gr = GR_RY; break;
-    }
-    case B200SV_GK_RZ: {
-      double s, c; sincos(0.5 * theta, &s, &c); if (dir < 0) s = -s;
-      e.m[0] = (real)c; e.m[1] = (real)-s; e.m[2] = (real)c; e.m[3] = (real)s;
-      e.ex = EX_DIAG; if (grad) e.gr = GR_RZ; break;
-    }
-    case B200SV_GK_PHASE: {
-      double s, c; sincos(theta, &s, &c); if (dir < 0) s = -s;
-      e.m[0] = (real)1; e.m[1] = (real)0; e.m[2] = (real)c; e.m[3] = (real)s;
-      e.ex = EX_DIAG; if (grad) e.gr = GR_PHASE; break;
-    }
-    case B200SV_GK_DIAG: {
-      const double* c = consts + 2 * g.cidx;
-      const double sg = dir > 0 ? 1.0 : -1.0;
-      e.m[0] = (real)c[0]; e.m[1] = (real)(sg * c[1]); e.m[2] = (real)c[2]; e.m[3] = (real)(sg * c[3]);
-      e.ex = EX_DIAG; break;
-    }
-    case B200SV_GK_X: e.ex = EX_X; break;
-    case B200SV_GK_SWAP: e.ex = EX_SWAP; break;
-    case B200SV_GK_SCALE: {
-      if (dir > 0) { e.m[0] = (real)theta; e.m[1] = (real)theta_im; }
-      else {  // psi <- psi / s (inverse), lambda <- conj(s) lambda (adjoint)
-        const double d = theta * theta + theta_im * theta_im;
-        e.m[0] = (real)(theta / d); e.m[1] = (real)(-theta_im / d);
-        e.m[2] = (real)theta; e.m[3] = (real)-theta_im;
-      }
-      e.ex = EX_SCALE; if (grad) e.gr = GR_SCALE; break;
-    }
-    default: e.ex = EX_NOP; break;
+    if (i > 0) W = m22_mul(W, elem_matrix(g, params, consts, batch, b));
   }
 }
 
@@ -127,62 +208,64 @@ template <typename real, int R> struct Regs {
   using c2 = typename C2<real>::type;
   static constexpr int NV = 1 << R;
 
-  template <int A> static __device__ __forceinline__ void mat(c2 (&v)[NV], const real* m, int cr) {
+  template <int A, bool CK> static __device__ __forceinline__ void mat_(c2 (&v)[NV], const real* m, int cr) {
+    const real m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5], m6 = m[6], m7 = m[7];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
-      if ((j & cr) != cr) continue;
+      if (CK && (j & cr) != cr) continue;
       const c2 x = v[j], y = v[j | (1 << A)];
-      v[j] = mk<c2>(m[0] * x.x - m[1] * x.y + m[2] * y.x - m[3] * y.y,
-                    m[0] * x.y + m[1] * x.x + m[2] * y.y + m[3] * y.x);
-      v[j | (1 << A)] = mk<c2>(m[4] * x.x - m[5] * x.y + m[6] * y.x - m[7] * y.y,
-                               m[4] * x.y + m[5] * x.x + m[6] * y.y + m[7] * y.x);
+      v[j] = mk<c2>(m0 * x.x - m1 * x.y + m2 * y.x - m3 * y.y, m0 * x.y + m1 * x.x + m2 * y.y + m3 * y.x);
+      v[j | (1 << A)] = mk<c2>(m4 * x.x - m5 * x.y + m6 * y.x - m7 * y.y, m4 * x.y + m5 * x.x + m6 * y.y + m7 * y.x);
     }
   }
-  template <int A> static __device__ __forceinline__ void realm(c2 (&v)[NV], const real* m, int cr) {
+  template <int A, bool CK> static __device__ __forceinline__ void real_(c2 (&v)[NV], const real* m, int cr) {
+    const real m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
-      if ((j & cr) != cr) continue;
+      if (CK && (j & cr) != cr) continue;
       const c2 x = v[j], y = v[j | (1 << A)];
-      v[j] = mk<c2>(m[0] * x.x + m[1] * y.x, m[0] * x.y + m[1] * y.y);
-      v[j | (1 << A)] = mk<c2>(m[2] * x.x + m[3] * y.x, m[2] * x.y + m[3] * y.y);
+      v[j] = mk<c2>(m0 * x.x + m1 * y.x, m0 * x.y + m1 * y.y);
+      v[j | (1 << A)] = mk<c2>(m2 * x.x + m3 * y.x, m2 * x.y + m3 * y.y);
     }
   }
-  template <int A> static __device__ __forceinline__ void rx(c2 (&v)[NV], real c, real s, int cr) {
+  template <int A, bool CK> static __device__ __forceinline__ void rx_(c2 (&v)[NV], const real* m, int cr) {
+    const real c = m[0], s = m[1];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
-      if ((j & cr) != cr) continue;
+      if (CK && (j & cr) != cr) continue;
       const c2 x = v[j], y = v[j | (1 << A)];
-      // [[c, -i s], [-i s, c]]
-      v[j] = mk<c2>(c * x.x + s * y.y, c * x.y - s * y.x);
+      v[j] = mk<c2>(c * x.x + s * y.y, c * x.y - s * y.x);  // [[c, -i s], [-i s, c]]
       v[j | (1 << A)] = mk<c2>(c * y.x + s * x.y, c * y.y - s * x.x);
     }
   }
-  template <int A> static __device__ __forceinline__ void xperm(c2 (&v)[NV], int cr) {
+  template <int A, bool CK> static __device__ __forceinline__ void diag_(c2 (&v)[NV], const real* m, int cr) {
+    const c2 d0 = mk<c2>(m[0], m[1]), d1 = mk<c2>(m[2], m[3]);
+    const bool one0 = (d0.x == (real)1 && d0.y == (real)0);  // PHASE / CZ / CPHASE: |0> branch untouched
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (CK && (j & cr) != cr) continue;
+      if (j & (1 << A)) v[j] = cmul(v[j], d1);
+      else if (!one0) v[j] = cmul(v[j], d0);
+    }
+  }
+  template <int A, bool CK> static __device__ __forceinline__ void x_(c2 (&v)[NV], const real*, int cr) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
-      if ((j & cr) != cr) continue;
+      if (CK && (j & cr) != cr) continue;
       const c2 x = v[j]; v[j] = v[j | (1 << A)]; v[j | (1 << A)] = x;
     }
   }
-  template <int A, int B> static __device__ __forceinline__ void swapab(c2 (&v)[NV], int cr) {
+  template <int A, int B> static __device__ __forceinline__ void swap_(c2 (&v)[NV], int cr) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if ((j & (1 << A)) || !(j & (1 << B))) continue;  // j: bit A = 0, bit B = 1
       if ((j & cr) != cr) continue;
       const int k = (j | (1 << A)) & ~(1 << B);
       const c2 x = v[j]; v[j] = v[k]; v[k] = x;
-    }
-  }
-  static __device__ __forceinline__ void diag_in(c2 (&v)[NV], const real* m, int a, int cr) {
-    const c2 d0 = mk<c2>(m[0], m[1]), d1 = mk<c2>(m[2], m[3]);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      if ((j & cr) != cr) continue;
-      v[j] = cmul(v[j], ((j >> a) & 1) ? d1 : d0);
     }
   }
   static __device__ __forceinline__ void scale_all(c2 (&v)[NV], c2 d, int cr) {
@@ -193,64 +276,43 @@ template <typename real, int R> struct Regs {
     }
   }
 
-#define B200SV_DISPATCH_A(a_, STMT)                                   \
-  switch (a_) {                                                       \
-    case 0: { constexpr int A = 0; STMT; } break;                     \
-    case 1: if constexpr (R > 1) { constexpr int A = 1; STMT; } break; \
-    case 2: if constexpr (R > 2) { constexpr int A = 2; STMT; } break; \
-    case 3: if constexpr (R > 3) { constexpr int A = 3; STMT; } break; \
-    case 4: if constexpr (R > 4) { constexpr int A = 4; STMT; } break; \
-    default: break;                                                   \
-  }
-
-  static __device__ __forceinline__ void swap_dispatch(c2 (&v)[NV], int a, int b, int cr) {
-    if (a > b) { const int t = a; a = b; b = t; }
-    // a < b
-    switch (a * 8 + b) {
-      case 0 * 8 + 1: if constexpr (R > 1) swapab<0, 1>(v, cr); break;
-      case 0 * 8 + 2: if constexpr (R > 2) swapab<0, 2>(v, cr); break;
-      case 1 * 8 + 2: if constexpr (R > 2) swapab<1, 2>(v, cr); break;
-      case 0 * 8 + 3: if constexpr (R > 3) swapab<0, 3>(v, cr); break;
-      case 1 * 8 + 3: if constexpr (R > 3) swapab<1, 3>(v, cr); break;
-      case 2 * 8 + 3: if constexpr (R > 3) swapab<2, 3>(v, cr); break;
-      case 0 * 8 + 4: if constexpr (R > 4) swapab<0, 4>(v, cr); break;
-      case 1 * 8 + 4: if constexpr (R > 4) swapab<1, 4>(v, cr); break;
-      case 2 * 8 + 4: if constexpr (R > 4) swapab<2, 4>(v, cr); break;
-      case 3 * 8 + 4: if constexpr (R > 4) swapab<3, 4>(v, cr); break;
-      default: break;
-    }
-  }
+#define B200SV_CASES(BASE, FN)                                                                      \
+  case BASE + 0: if (cr) FN<0, true>(v, e.m, cr); else FN<0, false>(v, e.m, 0); break;              \
+  case BASE + 1: if constexpr (R > 1) { if (cr) FN<1, true>(v, e.m, cr); else FN<1, false>(v, e.m, 0); } break; \
+  case BASE + 2: if constexpr (R > 2) { if (cr) FN<2, true>(v, e.m, cr); else FN<2, false>(v, e.m, 0); } break; \
+  case BASE + 3: if constexpr (R > 3) { if (cr) FN<3, true>(v, e.m, cr); else FN<3, false>(v, e.m, 0); } break; \
+  case BASE + 4: if constexpr (R > 4) { if (cr) FN<4, true>(v, e.m, cr); else FN<4, false>(v, e.m, 0); } break;
 
   // apply one resolved gate to a register file (thread already known to satisfy ctrl_ext)
   static __device__ __forceinline__ void apply(c2 (&v)[NV], const ExecGate<real>& e,
                                                unsigned long long gthr, bool is_lambda) {
-    const int cr = e.ctrl_reg;
-    switch (e.ex) {
-      case EX_MAT: B200SV_DISPATCH_A(e.a, mat<A>(v, e.m, cr)); break;
-      case EX_REAL: B200SV_DISPATCH_A(e.a, realm<A>(v, e.m, cr)); break;
-      case EX_RX: B200SV_DISPATCH_A(e.a, rx<A>(v, e.m[0], e.m[1], cr)); break;
-      case EX_X: B200SV_DISPATCH_A(e.a, xperm<A>(v, cr)); break;
-      case EX_SWAP: swap_dispatch(v, e.a, e.a2, cr); break;
-      case EX_DIAG:
-        if (e.a >= 0) diag_in(v, e.m, e.a, cr);
-        else {
-          const int bit = (int)((gthr >> e.ext_bit) & 1ull);
-          const c2 d = bit ? mk<c2>(e.m[2], e.m[3]) : mk<c2>(e.m[0], e.m[1]);
-          if (!(d.x == (real)1 && d.y == (real)0)) scale_all(v, d, cr);
-        }
-        break;
-      case EX_SCALE:
-        scale_all(v, is_lambda ? mk<c2>(e.m[2], e.m[3]) : mk<c2>(e.m[0], e.m[1]), 0);
-        break;
+    const int cr = e.cr;
+    switch (e.op) {
+      B200SV_CASES(OP_MAT, mat_)
+      B200SV_CASES(OP_REAL, real_)
+      B200SV_CASES(OP_RX, rx_)
+      B200SV_CASES(OP_DIAG, diag_)
+      B200SV_CASES(OP_X, x_)
+      case OP_SWAP + 0: if constexpr (R > 1) swap_<0, 1>(v, cr); break;
+      case OP_SWAP + 1: if constexpr (R > 2) swap_<0, 2>(v, cr); break;
+      case OP_SWAP + 2: if constexpr (R > 2) swap_<1, 2>(v, cr); break;
+      case OP_SWAP + 3: if constexpr (R > 3) swap_<0, 3>(v, cr); break;
+      case OP_SWAP + 4: if constexpr (R > 3) swap_<1, 3>(v, cr); break;
+      case OP_SWAP + 5: if constexpr (R > 3) swap_<2, 3>(v, cr); break;
+      case OP_DIAGEXT: {
+        const int bit = (int)((gthr >> e.ext_bit) & 1ull);
+        const c2 d = bit ? mk<c2>(e.m[2], e.m[3]) : mk<c2>(e.m[0], e.m[1]);
+        if (!(d.x == (real)1 && d.y == (real)0)) scale_all(v, d, cr);
+      } break;
+      case OP_SCALE: scale_all(v, is_lambda ? mk<c2>(e.m[2], e.m[3]) : mk<c2>(e.m[0], e.m[1]), 0); break;
       default: break;
     }
   }
 
-  // ---- adjoint gradient partials, evaluated on the POST-gate ψ, λ ----
-  //  RX/RY/RZ: g = Im<λ|P|ψ> on the control-active subspace; PHASE: g = -2 Im(conj(λ1) ψ1).
+  // ---- adjoint: four moments Im<λ|P|ψ>, P = I, X, Y, Z, on the control-active subspace ----------
   template <int A>
-  static __device__ __forceinline__ double grad_pair(const c2 (&p)[NV], const c2 (&l)[NV], int gr, int cr) {
-    double acc = 0.0;
+  static __device__ __forceinline__ void moments_(const c2 (&p)[NV], const c2 (&l)[NV], int cr, double (&mo)[4]) {
+    double s00 = 0, s11 = 0, x_im = 0, y_re = 0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
@@ -258,23 +320,34 @@ template <typename real, int R> struct Regs {
       const int k = j | (1 << A);
       const double p0x = p[j].x, p0y = p[j].y, p1x = p[k].x, p1y = p[k].y;
       const double l0x = l[j].x, l0y = l[j].y, l1x = l[k].x, l1y = l[k].y;
-      if (gr == GR_RX) acc += (l0x * p1y - l0y * p1x) + (l1x * p0y - l1y * p0x);
-      else if (gr == GR_RY) acc += -(l0x * p1x + l0y * p1y) + (l1x * p0x + l1y * p0y);
-      else if (gr == GR_RZ) acc += (l0x * p0y - l0y * p0x) - (l1x * p1y - l1y * p1x);
-      else if (gr == GR_PHASE) acc += -2.0 * (l1x * p1y - l1y * p1x);
+      s00 += l0x * p0y - l0y * p0x;                                  // Im conj(l0) p0
+      s11 += l1x * p1y - l1y * p1x;                                  // Im conj(l1) p1
+      x_im += (l0x * p1y - l0y * p1x) + (l1x * p0y - l1y * p0x);     // Im<λ|X|ψ>
+      y_re += (l1x * p0x + l1y * p0y) - (l0x * p1x + l0y * p1y);     // Im<λ|Y|ψ>
     }
-    return acc;
+    mo[0] = s00 + s11; mo[1] = x_im; mo[2] = y_re; mo[3] = s00 - s11;
   }
-  static __device__ __forceinline__ double grad_ext(const c2 (&p)[NV], const c2 (&l)[NV], int gr, int cr, int bit) {
-    double acc = 0.0;
+  static __device__ __forceinline__ void moments(const c2 (&p)[NV], const c2 (&l)[NV], const ExecGate<real>& e,
+                                                 unsigned long long gthr, double (&mo)[4]) {
+    const int cr = e.cr;
+    mo[0] = mo[1] = mo[2] = mo[3] = 0.0;
+    if (e.op == OP_DIAGEXT) {
+      double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      if ((j & cr) != cr) continue;
-      acc += (double)l[j].x * (double)p[j].y - (double)l[j].y * (double)p[j].x;  // Im(conj(l) p)
+      for (int j = 0; j < NV; ++j) {
+        if ((j & cr) != cr) continue;
+        s += (double)l[j].x * (double)p[j].y - (double)l[j].y * (double)p[j].x;
+      }
+      mo[0] = s; mo[3] = ((gthr >> e.ext_bit) & 1ull) ? -s : s;
+      return;
     }
-    if (gr == GR_RZ) return bit ? -acc : acc;
-    if (gr == GR_PHASE) return bit ? -2.0 * acc : 0.0;
-    return 0.0;
+    switch (e.op & 7) {
+      case 0: moments_<0>(p, l, cr, mo); break;
+      case 1: if constexpr (R > 1) moments_<1>(p, l, cr, mo); break;
+      case 2: if constexpr (R > 2) moments_<2>(p, l, cr, mo); break;
+      case 3: if constexpr (R > 3) moments_<3>(p, l, cr, mo); break;
+      default: break;
+    }
   }
   static __device__ __forceinline__ double grad_scale(const c2 (&p)[NV], const c2 (&l)[NV]) {
     double acc = 0.0;  // 2 Re <λ|ψ_before>
@@ -282,20 +355,21 @@ template <typename real, int R> struct Regs {
     for (int j = 0; j < NV; ++j) acc += (double)l[j].x * (double)p[j].x + (double)l[j].y * (double)p[j].y;
     return 2.0 * acc;
   }
-  static __device__ __forceinline__ double gradient(const c2 (&p)[NV], const c2 (&l)[NV],
-                                                    const ExecGate<real>& e, unsigned long long gthr) {
-    double g = 0.0;
-    if (e.a >= 0) { B200SV_DISPATCH_A(e.a, g = grad_pair<A>(p, l, e.gr, e.ctrl_reg)); }
-    else g = grad_ext(p, l, e.gr, e.ctrl_reg, (int)((gthr >> e.ext_bit) & 1ull));
-    return g;
-  }
 };
+
+__device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (int)((w >> (8 * i)) & 0xffull); }
 
 // ------------------------------------------------------------------------------------------------
 // the sweep kernel
 // ------------------------------------------------------------------------------------------------
+// launch geometry per instantiation: (max threads per CTA, min CTAs per SM)
+template <typename real, int R, bool ADJ> struct SweepCfg {
+  static constexpr int MAXT = (ADJ && sizeof(real) == 8) ? 128 : 256;
+  static constexpr int MINB = (ADJ && sizeof(real) == 8) ? 3 : ((sizeof(real) == 8 && R >= 3) || ADJ ? 2 : 3);
+};
+
 template <typename real, int R, bool ADJ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SweepCfg<real, R, ADJ>::MAXT, SweepCfg<real, R, ADJ>::MINB)
 sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::type* __restrict__ lam_g,
              const double* __restrict__ params, double* __restrict__ grads,
              const b200sv_sweep* __restrict__ sweeps, const b200sv_round* __restrict__ rounds,
@@ -312,13 +386,14 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   const int nt = blockDim.x;  // == 2^(m-R)
   const int tid = threadIdx.x;
   const int n_gates = sw.n_gates;
+  const int n_exec = sw.n_exec;
 
   c2* tile_psi = reinterpret_cast<c2*>(smem_raw);
   c2* tile_lam = tile_psi + (ADJ ? tile : 0);
   unsigned long long* t_lo = reinterpret_cast<unsigned long long*>(tile_lam + tile);
   unsigned long long* t_hi = t_lo + 64;
   ExecGate<real>* eg = reinterpret_cast<ExecGate<real>*>(t_hi + 64);
-  double* gsum = reinterpret_cast<double*>(eg + n_gates);
+  double* gsum = reinterpret_cast<double*>(eg + n_exec);  // ADJ: 4 doubles per exec entry
 
   const long long tiles_per_state = 1ll << sw.n_outer;
   const long long b = blockIdx.x / tiles_per_state;
@@ -336,9 +411,10 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     t_lo[v] = lo; t_hi[v] = hi;
   }
   for (int g = tid; g < n_gates; g += nt) {
-    resolve_gate<real>(gates[sw.first_gate + g], eg[g], params, consts, batch, b, dir, ADJ);
-    if (ADJ) gsum[g] = 0.0;
+    const b200sv_gate* rec = gates + sw.first_gate + g;
+    if (rec->chain >= 1) resolve_gate<real>(rec, eg[rec->xidx], params, consts, batch, b, dir, ADJ);
   }
+  if (ADJ) for (int g = tid; g < 4 * n_exec; g += nt) gsum[g] = 0.0;
   __syncthreads();
 
   // ---- stage the tile: coalesced global -> swizzled shared ----
@@ -366,65 +442,157 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
 
   // ---- rounds ----
   const int nthr_bits = m - R;
+  const unsigned long long cta_index = cta_base | index_hi;
   for (int rr = 0; rr < sw.n_rounds; ++rr) {
     const int ridx = dir > 0 ? sw.first_round + rr : sw.first_round + sw.n_rounds - 1 - rr;
-    const b200sv_round rd = rounds[ridx];
+    const uint4* rq = reinterpret_cast<const uint4*>(rounds + ridx);
+    const uint4 rw0 = rq[0];  // first_gate n_gates regpos thrpos[0:4]
+    const uint4 rw1 = rq[1];  // thrpos[4:12] first_exec n_exec
+    const uint4 rw2 = rq[2];  // mslot[0:4]
+    const unsigned long long regw = rw0.z;
+    const unsigned long long thrw = (unsigned long long)rw0.w | ((unsigned long long)rw1.x << 32);  // m - r <= 8
+    const int first_exec = (int)rw1.z, n_ex = (int)rw1.w;
+    const int ms[4] = {(int)rw2.x, (int)rw2.y, (int)rw2.z, (int)rw2.w};
+    const b200sv_round& rdr = rounds[ridx];
+    const bool has_perm = (rdr.flags & B200SV_RF_PERM) != 0;
+
     int tbase = 0;
-    for (int i = 0; i < nthr_bits; ++i) tbase |= ((tid >> i) & 1) << rd.thrpos[i];
-    int idx[NV];
+    for (int i = 0; i < nthr_bits; ++i) tbase |= ((tid >> i) & 1) << byte_of(thrw, i);
+    int rb[R];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int a = 0; a < R; ++a) rb[a] = 1 << byte_of(regw, a);
+    // permuted addressing: pi(tbase | off_j) = pbase ^ XOR_a pcol[regpos[a]]
+    int pbase = tbase, pb[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) pb[a] = rb[a];
+    if (has_perm) {
+      pbase = rdr.pconst;
+      for (int i = 0; i < nthr_bits; ++i)
+        if ((tid >> i) & 1) pbase ^= rdr.pcol[byte_of(thrw, i)];
+      for (int k = 0; k < (int)rdr.n_pext; ++k)
+        if ((cta_index >> rdr.pext[k].bit) & 1ull) pbase ^= rdr.pext[k].vec;
+#pragma unroll
+      for (int a = 0; a < R; ++a) pb[a] = rdr.pcol[byte_of(regw, a)];
+    }
+    auto sidx = [&](int j) {  // swizzled tile index of register j before the permutation phase
       int o = tbase;
 #pragma unroll
       for (int a = 0; a < R; ++a)
-        if ((j >> a) & 1) o |= 1 << rd.regpos[a];
-      idx[j] = swz<real>(o);
-    }
+        if ((j >> a) & 1) o |= rb[a];
+      return swz<real>(o);
+    };
+    auto pidx = [&](int j) {  // ... after it
+      int o = pbase;
+#pragma unroll
+      for (int a = 0; a < R; ++a)
+        if ((j >> a) & 1) o ^= pb[a];
+      return swz<real>(o);
+    };
     const unsigned long long gthr = cta_base | t_lo[tbase & 63] | t_hi[tbase >> 6] | index_hi;
 
     c2 p[NV];
     c2 l[ADJ ? NV : 1];
+    if (dir > 0) {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) p[j] = tile_psi[idx[j]];
-    if constexpr (ADJ) {
+      for (int j = 0; j < NV; ++j) p[j] = tile_psi[sidx(j)];
+    } else {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) l[j] = tile_lam[idx[j]];
-    }
-
-    for (int gi = 0; gi < rd.n_gates; ++gi) {
-      const int g = (dir > 0 ? rd.first_gate + gi : rd.first_gate + rd.n_gates - 1 - gi) - sw.first_gate;
-      const ExecGate<real>& e = eg[g];
-      const bool active = (gthr & e.ctrl_ext) == e.ctrl_ext;
+      for (int j = 0; j < NV; ++j) p[j] = tile_psi[pidx(j)];
       if constexpr (ADJ) {
-        if (e.gr != GR_NONE) {  // uniform across the CTA
-          double part = 0.0;
-          if (e.gr == GR_SCALE) {
-            if (active) RG::apply(p, e, gthr, false);  // ψ_before = ψ / s
-            part = RG::grad_scale(p, l);
-            RG::apply(l, e, gthr, true);
-          } else if (active) {
-            part = RG::gradient(p, l, e, gthr);
-          }
-          if (nt >= 32) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if ((tid & 31) == 0) atomicAdd(&gsum[g], part);
-          } else {
-            atomicAdd(&gsum[g], part);
-          }
-          if (e.gr == GR_SCALE) continue;
-        }
-        if (active) { RG::apply(p, e, gthr, false); RG::apply(l, e, gthr, true); }
-      } else {
-        if (active) RG::apply(p, e, gthr, false);
+        for (int j = 0; j < NV; ++j) l[j] = tile_lam[pidx(j)];
       }
     }
+    if (has_perm) __syncthreads();  // every register file is loaded before anyone stores at permuted addresses
 
+    if (dir > 0) {
+      // ---- M phase: one merged 2x2 per register bit, straight-line ----
 #pragma unroll
-    for (int j = 0; j < NV; ++j) tile_psi[idx[j]] = p[j];
-    if constexpr (ADJ) {
+      for (int a = 0; a < R; ++a) {
+        if (ms[a] >= 0) {
+          const real* mm = eg[ms[a]].m;
+          if (a == 0) RG::template mat_<0, false>(p, mm, 0);
+          if constexpr (R > 1) { if (a == 1) RG::template mat_<1, false>(p, mm, 0); }
+          if constexpr (R > 2) { if (a == 2) RG::template mat_<2, false>(p, mm, 0); }
+          if constexpr (R > 3) { if (a == 3) RG::template mat_<3, false>(p, mm, 0); }
+        }
+      }
+      // ---- G phase ----
+      for (int gi = 0; gi < n_ex; ++gi) {
+        const ExecGate<real>& e = eg[first_exec + gi];
+        if ((gthr & e.ctrl_ext) == e.ctrl_ext) RG::apply(p, e, gthr, false);
+      }
 #pragma unroll
-      for (int j = 0; j < NV; ++j) tile_lam[idx[j]] = l[j];
+      for (int j = 0; j < NV; ++j) tile_psi[pidx(j)] = p[j];
+    } else {
+      auto reduce_moments = [&](double (&mo)[4], int nmo, int x) {
+        if (nt >= 32) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nmo) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mo[q] += __shfl_xor_sync(0xffffffffu, mo[q], o);
+            }
+          }
+          if ((tid & 31) == 0)
+            for (int q = 0; q < nmo; ++q) atomicAdd(&gsum[4 * x + q], mo[q]);
+        } else {
+          for (int q = 0; q < nmo; ++q) atomicAdd(&gsum[4 * x + q], mo[q]);
+        }
+      };
+      // ---- G phase, reversed ----
+      for (int gi = n_ex - 1; gi >= 0; --gi) {
+        const int x = first_exec + gi;
+        const ExecGate<real>& e = eg[x];
+        const bool active = (gthr & e.ctrl_ext) == e.ctrl_ext;
+        if constexpr (ADJ) {
+          if (e.gr != GR_NONE) {  // uniform across the CTA
+            double mo[4] = {0.0, 0.0, 0.0, 0.0};
+            int nmo = 4;
+            if (e.gr == GR_SCALE) {
+              RG::apply(p, e, gthr, false);  // ψ_before = ψ / s
+              mo[0] = RG::grad_scale(p, l);
+              RG::apply(l, e, gthr, true);
+              nmo = 1;
+            } else if (active) {
+              RG::moments(p, l, e, gthr, mo);
+            }
+            reduce_moments(mo, nmo, x);
+            if (e.gr == GR_SCALE) continue;
+          }
+          if (active) { RG::apply(p, e, gthr, false); RG::apply(l, e, gthr, true); }
+        } else {
+          if (active) RG::apply(p, e, gthr, false);
+        }
+      }
+      // ---- M phase, reversed: moments of the post-chain states, then un-apply the merged 2x2 ----
+#pragma unroll
+      for (int a = R - 1; a >= 0; --a) {
+        if (ms[a] >= 0) {
+          const ExecGate<real>& e = eg[ms[a]];
+          if constexpr (ADJ) {
+            if (e.gr == GR_CHAIN) {
+              double mo[4] = {0.0, 0.0, 0.0, 0.0};
+              if (a == 0) RG::template moments_<0>(p, l, 0, mo);
+              if constexpr (R > 1) { if (a == 1) RG::template moments_<1>(p, l, 0, mo); }
+              if constexpr (R > 2) { if (a == 2) RG::template moments_<2>(p, l, 0, mo); }
+              if constexpr (R > 3) { if (a == 3) RG::template moments_<3>(p, l, 0, mo); }
+              reduce_moments(mo, 4, ms[a]);
+            }
+          }
+          const real* mm = e.m;
+          if (a == 0) { RG::template mat_<0, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<0, false>(l, mm, 0); }
+          if constexpr (R > 1) { if (a == 1) { RG::template mat_<1, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<1, false>(l, mm, 0); } }
+          if constexpr (R > 2) { if (a == 2) { RG::template mat_<2, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<2, false>(l, mm, 0); } }
+          if constexpr (R > 3) { if (a == 3) { RG::template mat_<3, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<3, false>(l, mm, 0); } }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) tile_psi[sidx(j)] = p[j];
+      if constexpr (ADJ) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) tile_lam[sidx(j)] = l[j];
+      }
     }
     __syncthreads();
   }
@@ -443,21 +611,24 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
         lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])] = tile_lam[swz<real>(e)];
       }
       for (int g = tid; g < n_gates; g += nt) {
-        const b200sv_gate& gr = gates[sw.first_gate + g];
-        if ((gr.flags & B200SV_GF_GRAD) && gr.grad_row >= 0)
-          atomicAdd(&grads[(long long)gr.grad_row * batch + b], gsum[g]);
+        const b200sv_gate* rec = gates + sw.first_gate + g;
+        if (rec->chain < 1) continue;
+        const ExecGate<real>& e = eg[rec->xidx];
+        if (e.gr == GR_CHAIN) chain_gradients(rec, gsum + 4 * rec->xidx, params, consts, grads, batch, b);
+        else if (e.gr == GR_SCALE && rec->grad_row >= 0)
+          atomicAdd(&grads[(long long)rec->grad_row * batch + b], gsum[4 * rec->xidx]);
       }
     }
   }
 }
 
 template <typename real, bool ADJ>
-inline size_t sweep_smem_bytes(int m, int n_gates) {
+inline size_t sweep_smem_bytes(int m, int n_exec) {
   size_t tile = (size_t)1 << m;
   size_t s = tile * 2 * sizeof(real) * (ADJ ? 2 : 1);
   s += 128 * sizeof(unsigned long long);
-  s += (size_t)n_gates * sizeof(ExecGate<real>);
-  s += (size_t)n_gates * sizeof(double);
+  s += (size_t)n_exec * sizeof(ExecGate<real>);
+  s += (size_t)n_exec * 4 * sizeof(double);
   return s;
 }
 

@@ -28,23 +28,36 @@ from .program import Op, OpKind
 GATE_DT = np.dtype(
     [
         ("kind", "<i4"), ("a", "<i4"), ("a2", "<i4"), ("ext_bit", "<i4"), ("ctrl_ext", "<u8"),
-        ("ctrl_reg", "<i4"), ("slot", "<i4"), ("cidx", "<i4"), ("grad_row", "<i4"), ("flags", "<i4"), ("pad", "<i4"),
+        ("ctrl_reg", "<i4"), ("slot", "<i4"), ("cidx", "<i4"), ("grad_row", "<i4"), ("flags", "<i4"),
+        ("chain", "<i4"), ("xidx", "<i4"), ("xkind", "<i4"),
     ]
 )
+PEXT_DT = np.dtype([("bit", "u1"), ("pad", "u1"), ("vec", "<u2")])
 ROUND_DT = np.dtype(
-    [("first_gate", "<i4"), ("n_gates", "<i4"), ("regpos", "u1", (4,)), ("thrpos", "u1", (12,)), ("pad", "<i4", (2,))]
+    [
+        ("first_gate", "<i4"), ("n_gates", "<i4"), ("regpos", "u1", (4,)), ("thrpos", "u1", (12,)), ("first_exec", "<i4"),
+        ("n_exec", "<i4"), ("mslot", "<i4", (4,)), ("pcol", "<u2", (12,)), ("pconst", "<u2"), ("n_pext", "<u2"),
+        ("pext", PEXT_DT, (4,)), ("flags", "<i4"),
+    ]
 )
 SWEEP_DT = np.dtype(
     [
         ("m", "<i4"), ("r", "<i4"), ("first_round", "<i4"), ("n_rounds", "<i4"), ("first_gate", "<i4"),
-        ("n_gates", "<i4"), ("n_outer", "<i4"), ("pad", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
+        ("n_gates", "<i4"), ("n_outer", "<i4"), ("n_exec", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
     ]
 )
 PTERM_DT = np.dtype([("xmask", "<u8"), ("zmask", "<u8"), ("coef_row", "<i4"), ("n_y", "<i4"), ("pad", "<i4", (2,))])
-assert GATE_DT.itemsize == 48 and ROUND_DT.itemsize == 32 and SWEEP_DT.itemsize == 96 and PTERM_DT.itemsize == 32
+assert GATE_DT.itemsize == 56 and ROUND_DT.itemsize == 96 and SWEEP_DT.itemsize == 96 and PTERM_DT.itemsize == 32
 
 GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
 GF_GRAD = 1
+GF_MSLOT = 2
+RF_PERM = 1
+XK_PERM = 7
+MAX_PEXT = 4
+XK_MAT, XK_REAL, XK_RX, XK_DIAG, XK_X, XK_SWAP, XK_SCALE = range(7)
+_XK_SINGLE = {GK_MAT: XK_MAT, GK_REAL: XK_REAL, GK_RX: XK_RX, GK_RY: XK_REAL, GK_RZ: XK_DIAG, GK_PHASE: XK_DIAG,
+              GK_DIAG: XK_DIAG, GK_X: XK_X, GK_SWAP: XK_SWAP, GK_SCALE: XK_SCALE}
 
 MAX_GATES_PER_SWEEP = 96
 _X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
@@ -61,6 +74,12 @@ class TileConfig:
 
     @staticmethod
     def default(dtype_is_c128: bool, adjoint: bool) -> "TileConfig":
+        import os
+
+        key = f"B200SV_TILE_{'ADJ' if adjoint else 'FWD'}_{'C128' if dtype_is_c128 else 'C64'}"
+        if key in os.environ:  # tuning override: "m,r,low"
+            m, r, low = (int(x) for x in os.environ[key].split(","))
+            return TileConfig(m=m, r=r, low=low, fold=3 if dtype_is_c128 else 4)
         if dtype_is_c128:
             return TileConfig(m=11, r=3, low=4, fold=3) if not adjoint else TileConfig(m=10, r=3, low=4, fold=3)
         return TileConfig(m=12, r=4, low=5, fold=4) if not adjoint else TileConfig(m=11, r=3, low=5, fold=4)
@@ -174,6 +193,150 @@ def _pack(gates: list[_G], capacity: int, forced: set[int], max_gates: int) -> l
     return groups
 
 
+@dataclass
+class _Round:
+    """One round of a sweep: M chains (global target bit -> gates), G gates, P gates."""
+
+    mchains: dict  # target bit -> list[_G]
+    ggates: list  # list[list[_G]] (chains of length >= 1, executed by the interpreter)
+    pgates: list  # list[_G]
+    regbits: set
+
+
+def _is_perm(g: _G) -> bool:
+    return (g.kind == GK_X and len(g.ctrl) <= 1) or (g.kind == GK_SWAP and not g.ctrl)
+
+
+def _is_matrix(g: _G) -> bool:
+    return g.kind not in (GK_SWAP, GK_SCALE) and not g.ctrl
+
+
+def _pack_rounds(sgates: list[_G], r: int, tile: set[int], phases: bool) -> list[_Round]:
+    """Pack a sweep's gates (ordered) into rounds of the M / G / P shape (see b200sv_round).
+
+    Acceptance keeps execution equivalent to the original order: a gate is taken only if it commutes
+    with every deferred gate, and it may be placed in an earlier phase of the round only if it
+    commutes with everything already accepted into the later phases.
+    """
+    rounds: list[_Round] = []
+    pending = list(sgates)
+    while pending:
+        rd = _Round({}, [], [], set())
+        deferred: list[_G] = []
+        def_any: set[int] = set()
+        def_hard: set[int] = set()
+        g_any: set[int] = set()  # bits touched by accepted G gates
+        g_hard: set[int] = set()
+        p_any: set[int] = set()  # ... by accepted P gates
+        p_hard: set[int] = set()
+        open_g: dict[int, int] = {}  # target bit -> index of an open chain among G entries
+        n_pext = set()
+        n_taken = 0
+        for g in pending:
+            hard = set(g.hard)
+            ok = not (g.bits_any & def_hard) and not (hard & def_any) and n_taken < MAX_GATES_PER_SWEEP
+            placed = False
+            if ok and phases and _is_perm(g) and all(b in tile for b in g.hard):
+                ext = {c for c in g.ctrl if c not in tile}
+                if len(n_pext | ext) <= MAX_PEXT:
+                    rd.pgates.append(g)
+                    n_pext |= ext
+                    p_any |= g.bits_any
+                    p_hard |= hard
+                    placed = True
+            elif ok and phases and _is_matrix(g):
+                t = g.hard[0] if g.hard else g.soft
+                before_gp = not (g.bits_any & (g_hard | p_hard)) and not (hard & (g_any | p_any))
+                if before_gp and t in rd.mchains:
+                    rd.mchains[t].append(g)
+                    placed = True
+                elif before_gp and t in tile and len(rd.regbits | {t}) <= r:
+                    rd.mchains[t] = [g]
+                    rd.regbits.add(t)
+                    placed = True
+            if ok and not placed and not (phases and _is_perm(g) and all(b in tile for b in g.hard)):
+                # generic phase: must commute with the accepted permutation gates; needs registers for hard bits
+                before_p = not (g.bits_any & p_hard) and not (hard & p_any)
+                if before_p and len(rd.regbits | hard) <= r:
+                    one_q = g.kind not in (GK_SWAP, GK_SCALE)
+                    t = (g.hard[0] if g.hard else g.soft) if one_q else -1
+                    if one_q and not g.ctrl and t in open_g:
+                        rd.ggates[open_g[t]].append(g)
+                    else:
+                        for bit in g.bits_any:
+                            open_g.pop(bit, None)
+                        rd.ggates.append([g])
+                        if one_q and not g.ctrl:
+                            open_g[t] = len(rd.ggates) - 1
+                    rd.regbits |= hard
+                    g_any |= g.bits_any
+                    g_hard |= hard
+                    placed = True
+            if placed:
+                n_taken += 1
+            else:
+                deferred.append(g)
+                def_any |= g.bits_any
+                def_hard |= hard
+        if n_taken == 0:
+            raise RuntimeError("planner stalled while packing rounds")
+        rounds.append(rd)
+        pending = deferred
+    return rounds
+
+
+def _perm_map(pgates: list[_G], local: dict[int, int]) -> tuple[list[int], int, dict[int, int]]:
+    """Compose X / CNOT / SWAP gates into pi(i) = XOR_{bits of i} col[bit] ^ const ^ XOR_ext vec."""
+    m = len(local)
+    cols = [1 << i for i in range(m)]
+    const = 0
+    ext: dict[int, int] = {}
+
+    def each(fn):
+        nonlocal const
+        for i in range(m):
+            cols[i] = fn(cols[i])
+        const = fn(const)
+        for k in list(ext):
+            ext[k] = fn(ext[k])
+
+    for g in pgates:
+        if g.kind == GK_X and not g.ctrl:
+            const ^= 1 << local[g.hard[0]]
+        elif g.kind == GK_X:
+            t = local[g.hard[0]]
+            c = g.ctrl[0]
+            if c in local:
+                lc = local[c]
+                each(lambda v: v ^ (((v >> lc) & 1) << t))
+            else:
+                ext[c] = ext.get(c, 0) ^ (1 << t)
+        elif g.kind == GK_SWAP:
+            a, b = local[g.hard[0]], local[g.hard[1]]
+
+            def sw(v, a=a, b=b):
+                x = ((v >> a) ^ (v >> b)) & 1
+                return v ^ ((x << a) | (x << b))
+
+            each(sw)
+        else:
+            raise ValueError("not a permutation gate")
+    return cols, const, ext
+
+
+def _chain_xkind(chain: list[_G]) -> int:
+    if len(chain) == 1:
+        return _XK_SINGLE[chain[0].kind]
+    kinds = {g.kind for g in chain}
+    if kinds <= {GK_RZ, GK_PHASE, GK_DIAG}:
+        return XK_DIAG
+    if kinds <= {GK_RY, GK_REAL, GK_X}:
+        return XK_REAL
+    if kinds == {GK_RX}:
+        return XK_RX
+    return XK_MAT
+
+
 def _thread_positions(m: int, regpos: list[int], fold: int) -> list[int]:
     avail = [p for p in range(m) if p not in regpos]
     chosen: list[int] = []
@@ -210,7 +373,7 @@ class SweepPlan:
         return [i for sw in self.order for rd in sw for i in rd]
 
 
-def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig) -> SweepPlan:
+def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig, chains: bool = True) -> SweepPlan:
     pool = ConstPool()
     m = min(cfg.m, n)
     r = max(1, min(cfg.r, m)) if n > 0 else 1
@@ -243,10 +406,11 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         sw["first_round"], sw["first_gate"] = n_rounds_total, n_gates_total
         sw["tile_bits"][:m] = tile
         sw["outer_bits"][: len(outer)] = outer
-        round_groups = _pack(sgates, r, set(), MAX_GATES_PER_SWEEP)
+        round_list = _pack_rounds(sgates, r, set(tile), chains)
         sw_order: list[list[int]] = []
-        for rgates, rbits in round_groups:
-            regs = sorted(local[p] for p in rbits)
+        n_exec_sweep = 0
+        for rnd in round_list:
+            regs = sorted(local[p] for p in rnd.regbits)
             for p in range(m):  # pad register set to exactly r positions (prefer high tile bits: keeps low bits on threads)
                 if len(regs) >= r:
                     break
@@ -255,41 +419,77 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
                     regs.append(cand)
             regs = sorted(regs)
             reg_index = {tile[lp]: a for a, lp in enumerate(regs)}  # global bit -> register index
+            m_entries = [rnd.mchains[t] for t in sorted(rnd.mchains, key=lambda t: reg_index[t])]
+            entries = m_entries + rnd.ggates
+            ordered = [g for ch in entries for g in ch] + list(rnd.pgates)
             rd = np.zeros(1, dtype=ROUND_DT)
-            rd["first_gate"], rd["n_gates"] = n_gates_total, len(rgates)
+            rd["first_gate"], rd["n_gates"] = n_gates_total, len(ordered)
             rd["regpos"][0, :r] = regs
             thr = _thread_positions(m, regs, cfg.fold)
             rd["thrpos"][0, : len(thr)] = thr
-            rounds_l.append(rd)
-            ga = np.zeros(len(rgates), dtype=GATE_DT)
-            for gi, g in enumerate(rgates):
+            rd["mslot"][0, :] = -1
+            ga = np.zeros(len(ordered), dtype=GATE_DT)
+            gi = 0
+            for ei, ch in enumerate(entries):
+                is_m = ei < len(m_entries)
+                xk = _chain_xkind(ch)
+                if is_m:
+                    rd["mslot"][0, reg_index[ch[0].hard[0] if ch[0].hard else ch[0].soft]] = n_exec_sweep
+                elif ei == len(m_entries):
+                    rd["first_exec"] = n_exec_sweep
+                for ci, g in enumerate(ch):
+                    rec = ga[gi]
+                    gi += 1
+                    rec["kind"], rec["slot"], rec["cidx"] = g.kind, g.slot, g.cidx
+                    rec["a"], rec["a2"], rec["ext_bit"] = -1, -1, 0
+                    rec["grad_row"] = g.slot if g.grad else -1
+                    rec["flags"] = (GF_GRAD if g.grad else 0) | (GF_MSLOT if is_m else 0)
+                    rec["chain"] = len(ch) if ci == 0 else 0
+                    rec["xidx"], rec["xkind"] = n_exec_sweep, xk
+                    if g.kind == GK_SWAP:
+                        rec["a"], rec["a2"] = reg_index[g.hard[0]], reg_index[g.hard[1]]
+                    elif g.hard:
+                        rec["a"] = reg_index[g.hard[0]]
+                    elif g.soft >= 0:
+                        if g.soft in reg_index:
+                            rec["a"] = reg_index[g.soft]
+                        else:
+                            rec["ext_bit"] = g.soft
+                    cext, creg = 0, 0
+                    for cb in g.ctrl:
+                        if cb in reg_index:
+                            creg |= 1 << reg_index[cb]
+                        else:
+                            cext |= 1 << cb
+                    rec["ctrl_ext"], rec["ctrl_reg"] = cext, creg
+                n_exec_sweep += 1
+            if not rnd.ggates:
+                rd["first_exec"] = n_exec_sweep
+            rd["n_exec"] = len(rnd.ggates)
+            for g in rnd.pgates:  # kept as records for diagnostics / emulation; folded into the address map
                 rec = ga[gi]
-                rec["kind"], rec["slot"], rec["cidx"] = g.kind, g.slot, g.cidx
-                rec["a"], rec["a2"], rec["ext_bit"] = -1, -1, 0
-                rec["grad_row"] = g.slot if g.grad else -1
-                rec["flags"] = GF_GRAD if g.grad else 0
-                if g.kind == GK_SWAP:
-                    rec["a"], rec["a2"] = reg_index[g.hard[0]], reg_index[g.hard[1]]
-                elif g.hard:
-                    rec["a"] = reg_index[g.hard[0]]
-                elif g.soft >= 0:
-                    if g.soft in reg_index:
-                        rec["a"] = reg_index[g.soft]
-                    else:
-                        rec["ext_bit"] = g.soft
-                cext, creg = 0, 0
-                for cb in g.ctrl:
-                    if cb in reg_index:
-                        creg |= 1 << reg_index[cb]
-                    else:
-                        cext |= 1 << cb
-                rec["ctrl_ext"], rec["ctrl_reg"] = cext, creg
+                gi += 1
+                rec["kind"], rec["slot"], rec["cidx"], rec["grad_row"] = g.kind, -1, -1, -1
+                rec["a"], rec["a2"] = local[g.hard[0]], (local[g.hard[1]] if len(g.hard) > 1 else -1)  # TILE-local bits
+                rec["ext_bit"] = g.ctrl[0] if g.ctrl else -1  # GLOBAL control bit
+                rec["chain"], rec["xidx"], rec["xkind"] = 0, -1, XK_PERM
+            cols, const, ext = _perm_map(rnd.pgates, local)
+            rd["pcol"][0, :m] = cols
+            rd["pconst"] = const
+            ext = {k: v for k, v in ext.items() if v}
+            rd["n_pext"] = len(ext)
+            for k, (bit, vec) in enumerate(sorted(ext.items())):
+                rd["pext"][0, k]["bit"], rd["pext"][0, k]["vec"] = bit, vec
+            if const or ext or cols != [1 << i for i in range(m)]:
+                rd["flags"] = RF_PERM
+            rounds_l.append(rd)
             gates_l.append(ga)
-            sw_order.append([g.src for g in rgates])
-            n_gates_total += len(rgates)
+            sw_order.append([g.src for g in ordered])
+            n_gates_total += len(ordered)
             n_rounds_total += 1
-        sw["n_rounds"] = len(round_groups)
+        sw["n_rounds"] = len(round_list)
         sw["n_gates"] = n_gates_total - int(sw["first_gate"])
+        sw["n_exec"] = n_exec_sweep
         order.append(sw_order)
     rounds = np.concatenate(rounds_l) if rounds_l else np.zeros(0, dtype=ROUND_DT)
     gates = np.concatenate(gates_l) if gates_l else np.zeros(0, dtype=GATE_DT)

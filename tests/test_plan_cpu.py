@@ -10,7 +10,7 @@ import torch
 from oracle import statevec as oracle
 from qadence_b200.plan import TileConfig, build_plan
 from qadence_b200.program import CONST_MATS, OpKind, ProgramBuilder, hea_program
-from tests.plan_emulator import emulate
+from tests.plan_emulator import emulate, emulate_adjoint
 
 
 def random_program(n: int, n_gates: int, rng: np.random.Generator, n_params: int = 6):
@@ -97,3 +97,35 @@ def test_dagger_plan_inverts() -> None:
     fwd = emulate(plan, psi0, params)
     back = emulate(plan, fwd, params, dagger=True)
     np.testing.assert_allclose(back, psi0 * 1.5**2, atol=1e-12)  # Scale is not unitary: s·conj(s)
+
+
+@pytest.mark.parametrize("cfg", [TileConfig(m=10, r=3, low=4, fold=3), TileConfig(m=4, r=2, low=2, fold=3)], ids=lambda c: f"m{c.m}r{c.r}")
+def test_chain_moment_gradients_match_oracle(cfg: TileConfig) -> None:
+    """The adjoint algebra of sweep.cuh (merged chains + four Bloch moments) == the gate-by-gate adjoint."""
+    from qadence_b200.program import PauliSum, PauliTerm
+
+    rng = np.random.default_rng(3)
+    n, B = 5, 2
+    b = ProgramBuilder(n)
+    for q in range(n):
+        b.RX(q, f"a{q}").RY(q, "shared").RX(q, f"b{q}").PHASE(q, f"p{q}").RZ(q, "shared").H(q).RY(q, f"c{q}")
+    for q in range(n - 1):
+        b.CNOT(q, q + 1).CRX(q + 1, q, f"cr{q}").CPHASE(q, (q + 2) % n, f"cp{q}").CRZ(q, q + 1, "shared")
+    b.scale("s")
+    for q in range(n):
+        b.RZ(q, f"z{q}").PHASE(q, f"z{q}").RX(q, 0.3).RY(q, f"y{q}")
+    prog = b.build()
+    obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.5, (), ((0, "X"), (3, "Y")))])
+    values = {nm: torch.tensor(rng.uniform(0.2, 1.5, size=B)) for nm in prog.param_names}
+    want_e, want_g = oracle.adjoint_expectation_and_grads(prog, obs, values)
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, cfg)
+    assert any(int(g["chain"]) > 1 for g in plan.gates)
+    params = np.stack([values[nm].numpy() for nm in prog.param_names])
+    psi0 = oracle.zero_state(n, B).numpy()
+    psi = emulate(plan, psi0, params)
+    lam = oracle.from_pyq_shape(oracle.paulisum_apply(obs, oracle.to_pyq_shape(torch.tensor(psi), n), values)).numpy()
+    back_psi, _, grads = emulate_adjoint(plan, psi, lam, params)
+    np.testing.assert_allclose(back_psi, psi0, atol=1e-12)
+    for nm, i in slot_of.items():
+        np.testing.assert_allclose(grads[i], want_g[nm].numpy(), atol=1e-11, err_msg=nm)

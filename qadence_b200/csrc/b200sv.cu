@@ -30,7 +30,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
                  int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
-  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec);
+  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds);
   auto kern = sweep_kernel<real, R, ADJ>;
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {

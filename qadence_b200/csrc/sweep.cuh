@@ -38,6 +38,8 @@ template <typename T> __device__ __forceinline__ T cmul(T a, T b) {
   return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+constexpr int RT_STRIDE = 40;  // words per per-round index table
+
 // flat opcodes of resolved gates: base + register index
 enum {
   OP_NOP = 0, OP_SCALE = 1, OP_DIAGEXT = 2,
@@ -362,10 +364,16 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 // ------------------------------------------------------------------------------------------------
 // the sweep kernel
 // ------------------------------------------------------------------------------------------------
+#ifndef B200SV_MINB_FWD_D
+#define B200SV_MINB_FWD_D 3  // complex128 forward, r >= 3: CTAs per SM the register allocation targets
+#endif
+#ifndef B200SV_MINB_ADJ_D
+#define B200SV_MINB_ADJ_D 4  // complex128 adjoint (128-thread CTAs)
+#endif
 // launch geometry per instantiation: (max threads per CTA, min CTAs per SM)
 template <typename real, int R, bool ADJ> struct SweepCfg {
   static constexpr int MAXT = (ADJ && sizeof(real) == 8) ? 128 : 256;
-  static constexpr int MINB = (ADJ && sizeof(real) == 8) ? 3 : ((sizeof(real) == 8 && R >= 3) || ADJ ? 2 : 3);
+  static constexpr int MINB = (ADJ && sizeof(real) == 8) ? B200SV_MINB_ADJ_D : ((sizeof(real) == 8 && R >= 3) ? B200SV_MINB_FWD_D : (ADJ ? 2 : 3));
 };
 
 template <typename real, int R, bool ADJ>
@@ -393,7 +401,11 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   unsigned long long* t_lo = reinterpret_cast<unsigned long long*>(tile_lam + tile);
   unsigned long long* t_hi = t_lo + 64;
   ExecGate<real>* eg = reinterpret_cast<ExecGate<real>*>(t_hi + 64);
-  double* gsum = reinterpret_cast<double*>(eg + n_exec);  // ADJ: 4 doubles per exec entry
+  double* gsum = reinterpret_cast<double*>(eg + n_exec);  // ADJ: [n_exec][nwarps][4] moment partials
+  const int nwarps = (nt + 31) >> 5;
+  // per-round index tables (RT_STRIDE words each): [0,16) low thread nibble, [16,32) high nibble,
+  // [32,32+R) register bits; each word = swz(plain tile index part) | swz(permuted part) << 16
+  unsigned* rtab = reinterpret_cast<unsigned*>(gsum + (ADJ ? 4 * n_exec * nwarps : 0));
 
   const long long tiles_per_state = 1ll << sw.n_outer;
   const long long b = blockIdx.x / tiles_per_state;
@@ -401,7 +413,9 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   unsigned long long cta_base = 0;
   for (int k = 0; k < sw.n_outer; ++k) cta_base |= ((c >> k) & 1ull) << sw.outer_bits[k];
 
-  // ---- prologue: offset tables, resolved gates ----
+  // ---- prologue 1: offset tables (global offsets of tile indices, per-round index tables) ----
+  const int nthr_bits = m - R;
+  const unsigned long long cta_index = cta_base | index_hi;
   for (int v = tid; v < 64; v += nt) {
     unsigned long long lo = 0, hi = 0;
     for (int i = 0; i < 6; ++i) {
@@ -410,85 +424,100 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     }
     t_lo[v] = lo; t_hi[v] = hi;
   }
-  for (int g = tid; g < n_gates; g += nt) {
-    const b200sv_gate* rec = gates + sw.first_gate + g;
-    if (rec->chain >= 1) resolve_gate<real>(rec, eg[rec->xidx], params, consts, batch, b, dir, ADJ);
+  for (int w = tid; w < sw.n_rounds * RT_STRIDE; w += nt) {
+    const int rloc = w / RT_STRIDE, i = w % RT_STRIDE;
+    const b200sv_round& rd = rounds[sw.first_round + rloc];
+    const bool perm = (rd.flags & B200SV_RF_PERM) != 0;
+    unsigned plain = 0, permd = 0;
+    if (i < 32) {
+      const int half = i >> 4;
+      for (int k = 0; k < 4; ++k) {
+        const int tb = k + 4 * half;
+        if (tb < nthr_bits && ((i >> k) & 1)) {
+          const int pos = rd.thrpos[tb];
+          plain |= 1u << pos;
+          permd ^= perm ? (unsigned)rd.pcol[pos] : (1u << pos);
+        }
+      }
+      if (half == 0 && perm) {
+        permd ^= rd.pconst;
+        for (int k = 0; k < (int)rd.n_pext; ++k)
+          if ((cta_index >> rd.pext[k].bit) & 1ull) permd ^= rd.pext[k].vec;
+      }
+    } else if (i - 32 < R) {
+      const int pos = rd.regpos[i - 32];
+      plain = 1u << pos;
+      permd = perm ? (unsigned)rd.pcol[pos] : (1u << pos);
+    }
+    rtab[w] = (unsigned)swz<real>((int)plain) | ((unsigned)swz<real>((int)permd) << 16);
   }
-  if (ADJ) for (int g = tid; g < 4 * n_exec; g += nt) gsum[g] = 0.0;
   __syncthreads();
 
-  // ---- stage the tile: coalesced global -> swizzled shared ----
+  // ---- prologue 2: issue the tile loads, resolve the gates while they are in flight ----
   const long long state_off = b << n;
   {
     c2 buf[NV];
+    c2 buf2[ADJ ? NV : 1];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = i * nt + tid;
       buf[i] = psi_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])];
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) tile_psi[swz<real>(i * nt + tid)] = buf[i];
-    if (ADJ) {
+    if constexpr (ADJ) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int e = i * nt + tid;
-        buf[i] = lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])];
+        buf2[i] = lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])];
       }
+    }
+    for (int g = tid; g < n_gates; g += nt) {
+      const b200sv_gate* rec = gates + sw.first_gate + g;
+      if (rec->chain >= 1) resolve_gate<real>(rec, eg[rec->xidx], params, consts, batch, b, dir, ADJ);
+    }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) tile_lam[swz<real>(i * nt + tid)] = buf[i];
+    for (int i = 0; i < NV; ++i) tile_psi[swz<real>(i * nt + tid)] = buf[i];
+    if constexpr (ADJ) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) tile_lam[swz<real>(i * nt + tid)] = buf2[i];
     }
   }
   __syncthreads();
 
   // ---- rounds ----
-  const int nthr_bits = m - R;
-  const unsigned long long cta_index = cta_base | index_hi;
   for (int rr = 0; rr < sw.n_rounds; ++rr) {
-    const int ridx = dir > 0 ? sw.first_round + rr : sw.first_round + sw.n_rounds - 1 - rr;
+    const int rloc = dir > 0 ? rr : sw.n_rounds - 1 - rr;
+    const int ridx = sw.first_round + rloc;
     const uint4* rq = reinterpret_cast<const uint4*>(rounds + ridx);
-    const uint4 rw0 = rq[0];  // first_gate n_gates regpos thrpos[0:4]
     const uint4 rw1 = rq[1];  // thrpos[4:12] first_exec n_exec
     const uint4 rw2 = rq[2];  // mslot[0:4]
-    const unsigned long long regw = rw0.z;
-    const unsigned long long thrw = (unsigned long long)rw0.w | ((unsigned long long)rw1.x << 32);  // m - r <= 8
     const int first_exec = (int)rw1.z, n_ex = (int)rw1.w;
     const int ms[4] = {(int)rw2.x, (int)rw2.y, (int)rw2.z, (int)rw2.w};
-    const b200sv_round& rdr = rounds[ridx];
-    const bool has_perm = (rdr.flags & B200SV_RF_PERM) != 0;
-
-    int tbase = 0;
-    for (int i = 0; i < nthr_bits; ++i) tbase |= ((tid >> i) & 1) << byte_of(thrw, i);
-    int rb[R];
+    const bool has_perm = (rounds[ridx].flags & B200SV_RF_PERM) != 0;
+    const unsigned* T = rtab + rloc * RT_STRIDE;
+    const unsigned u = T[tid & 15] ^ T[16 + (tid >> 4)];
+    const int st = (int)(u & 0xffffu), sp = (int)(u >> 16);  // swizzled plain / permuted base index
+    int ro[R], rp[R];
 #pragma unroll
-    for (int a = 0; a < R; ++a) rb[a] = 1 << byte_of(regw, a);
-    // permuted addressing: pi(tbase | off_j) = pbase ^ XOR_a pcol[regpos[a]]
-    int pbase = tbase, pb[R];
-#pragma unroll
-    for (int a = 0; a < R; ++a) pb[a] = rb[a];
-    if (has_perm) {
-      pbase = rdr.pconst;
-      for (int i = 0; i < nthr_bits; ++i)
-        if ((tid >> i) & 1) pbase ^= rdr.pcol[byte_of(thrw, i)];
-      for (int k = 0; k < (int)rdr.n_pext; ++k)
-        if ((cta_index >> rdr.pext[k].bit) & 1ull) pbase ^= rdr.pext[k].vec;
-#pragma unroll
-      for (int a = 0; a < R; ++a) pb[a] = rdr.pcol[byte_of(regw, a)];
-    }
+    for (int a = 0; a < R; ++a) { const unsigned w = T[32 + a]; ro[a] = (int)(w & 0xffffu); rp[a] = (int)(w >> 16); }
     auto sidx = [&](int j) {  // swizzled tile index of register j before the permutation phase
-      int o = tbase;
+      int o = st;
 #pragma unroll
       for (int a = 0; a < R; ++a)
-        if ((j >> a) & 1) o |= rb[a];
-      return swz<real>(o);
+        if ((j >> a) & 1) o ^= ro[a];
+      return o;
     };
     auto pidx = [&](int j) {  // ... after it
-      int o = pbase;
+      int o = sp;
 #pragma unroll
       for (int a = 0; a < R; ++a)
-        if ((j >> a) & 1) o ^= pb[a];
-      return swz<real>(o);
+        if ((j >> a) & 1) o ^= rp[a];
+      return o;
     };
-    const unsigned long long gthr = cta_base | t_lo[tbase & 63] | t_hi[tbase >> 6] | index_hi;
+    unsigned long long gthr = 0;
+    if (n_ex > 0) {  // index bits of this thread (controls / external diagonals of the generic phase)
+      const int tbase = swz<real>(st);  // swz is an involution
+      gthr = cta_base | t_lo[tbase & 63] | t_hi[tbase >> 6] | index_hi;
+    }
 
     c2 p[NV];
     c2 l[ADJ ? NV : 1];
@@ -525,20 +554,22 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
 #pragma unroll
       for (int j = 0; j < NV; ++j) tile_psi[pidx(j)] = p[j];
     } else {
+      // every resolved entry lives in exactly one round, so each warp owns one gsum slot per entry:
+      // plain stores, no atomics (nt < 32: a single partial warp, lanes reduce through full-mask shuffles
+      // of the active lanes only)
       auto reduce_moments = [&](double (&mo)[4], int nmo, int x) {
-        if (nt >= 32) {
+        const unsigned mask = nt >= 32 ? 0xffffffffu : ((1u << nt) - 1u);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < nmo) {
+        for (int q = 0; q < 4; ++q) {
+          if (q < nmo) {
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) mo[q] += __shfl_xor_sync(0xffffffffu, mo[q], o);
+            for (int o = 16; o > 0; o >>= 1) {
+              if (o < nt) mo[q] += __shfl_xor_sync(mask, mo[q], o);
             }
           }
-          if ((tid & 31) == 0)
-            for (int q = 0; q < nmo; ++q) atomicAdd(&gsum[4 * x + q], mo[q]);
-        } else {
-          for (int q = 0; q < nmo; ++q) atomicAdd(&gsum[4 * x + q], mo[q]);
         }
+        if ((tid & 31) == 0)
+          for (int q = 0; q < nmo; ++q) gsum[(x * nwarps + (tid >> 5)) * 4 + q] = mo[q];
       };
       // ---- G phase, reversed ----
       for (int gi = n_ex - 1; gi >= 0; --gi) {
@@ -614,21 +645,26 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
         const b200sv_gate* rec = gates + sw.first_gate + g;
         if (rec->chain < 1) continue;
         const ExecGate<real>& e = eg[rec->xidx];
-        if (e.gr == GR_CHAIN) chain_gradients(rec, gsum + 4 * rec->xidx, params, consts, grads, batch, b);
+        if (e.gr == GR_NONE) continue;
+        double mom[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < nwarps; ++w)
+          for (int q = 0; q < 4; ++q) mom[q] += gsum[(rec->xidx * nwarps + w) * 4 + q];
+        if (e.gr == GR_CHAIN) chain_gradients(rec, mom, params, consts, grads, batch, b);
         else if (e.gr == GR_SCALE && rec->grad_row >= 0)
-          atomicAdd(&grads[(long long)rec->grad_row * batch + b], gsum[4 * rec->xidx]);
+          atomicAdd(&grads[(long long)rec->grad_row * batch + b], mom[0]);
       }
     }
   }
 }
 
 template <typename real, bool ADJ>
-inline size_t sweep_smem_bytes(int m, int n_exec) {
+inline size_t sweep_smem_bytes(int m, int n_exec, int n_rounds) {
   size_t tile = (size_t)1 << m;
   size_t s = tile * 2 * sizeof(real) * (ADJ ? 2 : 1);
   s += 128 * sizeof(unsigned long long);
   s += (size_t)n_exec * sizeof(ExecGate<real>);
-  s += (size_t)n_exec * 4 * sizeof(double);
+  s += (size_t)n_exec * 4 * sizeof(double) * 8;  // up to 8 warps per CTA
+  s += (size_t)n_rounds * RT_STRIDE * sizeof(unsigned);
   return s;
 }
 

@@ -1,0 +1,230 @@
+"""The qadence `Backend` of the B200-native state-vector simulator.
+
+Drop-in for `/root/reference/qadence/backends/pyqtorch/backend.py:82-323`: same dataclass fields,
+same method names, argument meaning and error behaviour (`validate_state` TypeError / ValueError,
+`assign_parameters` NotImplementedError, split `{"circuit":…, "observables":…}` dicts, pyqtorch-shaped
+`[2]*n+[B]` initial states, `Endianness.LITTLE` views, `list[Counter]` samples).
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from collections import Counter
+from dataclasses import dataclass, field
+from logging import getLogger
+from typing import Any
+
+import torch
+from torch import Tensor
+
+from qadence.backend import Backend as BackendInterface
+from qadence.backend import Converted, ConvertedCircuit, ConvertedObservable
+from qadence.backends.utils import infer_batchsize, is_pyq_shape, unpyqify, validate_state
+from qadence.blocks import AbstractBlock
+from qadence.circuit import QuantumCircuit
+from qadence.measurements import Measurements
+from qadence.mitigations import Mitigations
+from qadence.noise import NoiseHandler
+from qadence.transpile import flatten, scale_primitive_blocks_only, transpile
+from qadence.types import BackendName, Endianness, Engine, ParamDictType
+
+from .. import engine
+from ..program import Program
+from .config import Configuration, default_passes
+from .convert_ops import convert_block, convert_observable
+
+logger = getLogger(__name__)
+_DTYPES = {"complex128": torch.complex128, "complex64": torch.complex64}
+
+
+class NativeCircuit:
+    """What `ConvertedCircuit.native` holds: the flat program + its compiled (planned) form.
+
+    Duck-types the attributes qadence reads on pyqtorch circuits: `n_qubits`,
+    `dtype`, `device`, `to()`, `operations`, `init_state`, `readout_noise`."""
+
+    def __init__(self, program: Program, dtype: torch.dtype, device: str | None):
+        self.program = program
+        self.compiled = engine.CompiledProgram(program)
+        self.n_qubits = program.n_qubits
+        self.dtype = dtype
+        self._device = device
+        self.readout_noise = None
+
+    @property
+    def operations(self) -> list:
+        return self.program.ops
+
+    @property
+    def device(self) -> torch.device:
+        return torch.device(self._device) if self._device else torch.device("cuda")
+
+    def to(self, *args: Any, **kwargs: Any) -> "NativeCircuit":
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.dtype) and a in (torch.complex64, torch.complex128):
+                self.dtype = a
+            elif isinstance(a, (str, torch.device)) and torch.device(a).type == "cuda":
+                self._device = str(a)
+        return self
+
+    def init_state(self, batch_size: int = 1) -> Tensor:
+        return engine.zero_state(self.n_qubits, batch_size, self.dtype, engine._dev(self._device))
+
+
+class NativeObservable:
+    def __init__(self, obs: Any, dtype: torch.dtype):
+        self.compiled = engine.CompiledObservable(obs)
+        self.obs = obs
+        self.dtype = dtype
+
+    def to(self, *args: Any, **kwargs: Any) -> "NativeObservable":
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.dtype) and a in (torch.complex64, torch.complex128):
+                self.dtype = a
+        return self
+
+
+def _split(param_values: ParamDictType) -> tuple[dict, dict]:
+    """`{"circuit":…, "observables":…}` or a flat dict (pyqtorch/backend.py:192-195)."""
+    pc = param_values["circuit"] if "circuit" in param_values else param_values
+    po = param_values["observables"] if "observables" in param_values else param_values
+    return pc, po
+
+
+def _result_device(cfg: Configuration, *dicts: Any) -> torch.device | None:
+    if not cfg.results_on_input_device:
+        return None
+    devs = set()
+    for d in dicts:
+        if isinstance(d, Tensor):
+            devs.add(d.device)
+        elif isinstance(d, dict):
+            devs |= {v.device for v in d.values() if isinstance(v, Tensor)}
+    if any(dv.type == "cuda" for dv in devs):
+        return None
+    return torch.device("cpu")
+
+
+@dataclass(frozen=True, eq=True)
+class Backend(BackendInterface):
+    """B200-native state-vector backend (hand-written sm_100a CUDA kernels behind a C-ABI)."""
+
+    name: BackendName = BackendName("b200sv")
+    supports_ad: bool = True
+    support_bp: bool = True
+    supports_adjoint: bool = True
+    is_remote: bool = False
+    with_measurements: bool = True
+    with_noise: bool = False
+    native_endianness: Endianness = Endianness.BIG
+    config: Configuration = field(default_factory=Configuration)
+    engine: Engine = Engine("b200sv")
+
+    # ------------------------------------------------------------------ conversion
+    def convert(self, circuit: QuantumCircuit, observable: list[AbstractBlock] | AbstractBlock | None = None) -> Converted:
+        """Inherited algorithm (qadence/backend.py:188-253); parameter embedding is torch's.
+
+        `self.engine` names the differentiation engine `backend_factory` imports
+        (qadence/backends/api.py:52), while `embedding()` needs the array library (torch)."""
+        proxy = dataclasses.replace(self, engine=Engine.TORCH)
+        return BackendInterface.convert(proxy, circuit, observable)
+
+    def circuit(self, circuit: QuantumCircuit) -> ConvertedCircuit:
+        passes = self.config.transpilation_passes
+        if passes is None:
+            passes = default_passes(self.config)
+        original = circuit
+        if len(passes) > 0:
+            circuit = transpile(*passes)(circuit)
+        if self.config.noise:
+            raise NotImplementedError("b200sv is a pure state-vector backend: `noise` is not supported")
+        ops = convert_block(circuit.block, n_qubits=circuit.n_qubits, config=self.config)
+        native = NativeCircuit(Program(circuit.n_qubits, ops), _DTYPES[self.config.dtype], self.config.device)
+        return ConvertedCircuit(native=native, abstract=circuit, original=original)
+
+    def observable(self, observable: AbstractBlock, n_qubits: int) -> ConvertedObservable:
+        block = transpile(flatten, scale_primitive_blocks_only)(observable)  # type: ignore[call-overload]
+        native = NativeObservable(convert_observable(block, n_qubits, self.config), _DTYPES[self.config.dtype])
+        return ConvertedObservable(native=native, abstract=block, original=observable)
+
+    # ------------------------------------------------------------------ execution
+    def _state_in(self, state: Tensor | None, n_qubits: int) -> Tensor | None:
+        if state is None:
+            return None
+        validate_state(state, n_qubits)
+        if is_pyq_shape(state, n_qubits) and not (state.dim() == 2 and state.shape[1] == 2**n_qubits):
+            state = unpyqify(state)
+        return state
+
+    def run(
+        self,
+        circuit: ConvertedCircuit,
+        param_values: dict[str, Tensor] = {},
+        state: Tensor | None = None,
+        endianness: Endianness = Endianness.BIG,
+        pyqify_state: bool = True,
+        unpyqify_state: bool = True,
+    ) -> Tensor:
+        n = circuit.abstract.n_qubits
+        nat: NativeCircuit = circuit.native
+        out = engine.run(nat.compiled, param_values, self._state_in(state, n), dtype=nat.dtype, device=nat._device)
+        if endianness != self.native_endianness:
+            out = engine.bit_reverse(out)
+        dev = _result_device(self.config, param_values, state)
+        return out if dev is None else out.to(dev)
+
+    def expectation(
+        self,
+        circuit: ConvertedCircuit,
+        observable: list[ConvertedObservable] | ConvertedObservable,
+        param_values: ParamDictType = {},
+        state: Tensor | None = None,
+        measurement: Measurements | None = None,
+        noise: NoiseHandler | None = None,
+        mitigation: Mitigations | None = None,
+        endianness: Endianness = Endianness.BIG,
+    ) -> Tensor:
+        if noise is not None and measurement is None:
+            logger.warning(f"Errors of type {noise} are not implemented for exact expectation yet. This is ignored for now.")
+        pc, po = _split(param_values)
+        n = circuit.abstract.n_qubits
+        nat: NativeCircuit = circuit.native
+        observable = observable if isinstance(observable, list) else [observable]
+        values = dict(pc)
+        if po is not pc:
+            values.update(po)
+        out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, self._state_in(state, n),
+                                 dtype=nat.dtype, device=nat._device)
+        dev = _result_device(self.config, pc, po, state)
+        return out if dev is None else out.to(dev)
+
+    def sample(
+        self,
+        circuit: ConvertedCircuit,
+        param_values: ParamDictType = {},
+        n_shots: int = 1,
+        state: Tensor | None = None,
+        noise: NoiseHandler | None = None,
+        mitigation: Mitigations | None = None,
+        endianness: Endianness = Endianness.BIG,
+        pyqify_state: bool = True,
+    ) -> list[Counter]:
+        if noise is not None or mitigation is not None:
+            raise NotImplementedError("b200sv is a pure state-vector backend: readout noise / mitigation are not supported")
+        n = circuit.abstract.n_qubits
+        nat: NativeCircuit = circuit.native
+        return engine.sample(nat.compiled, param_values, n_shots, self._state_in(state, n), dtype=nat.dtype,
+                             device=nat._device, little_endian=endianness != Endianness.BIG)
+
+    def assign_parameters(self, circuit: ConvertedCircuit, param_values: ParamDictType) -> Any:
+        raise NotImplementedError
+
+    @staticmethod
+    def _overlap(bras: Tensor, kets: Tensor) -> Tensor:
+        from qadence.overlap import overlap_exact
+
+        return overlap_exact(bras, kets)
+
+    @staticmethod
+    def default_configuration() -> Configuration:
+        return Configuration()

@@ -1,0 +1,51 @@
+"""`Configuration` of the b200sv backend — mirrors
+`/root/reference/qadence/backends/pyqtorch/config.py:21-90` (same option names so that user
+configuration dicts keep working; options that only make sense for pyqtorch are accepted and
+ignored, those that would need density matrices raise at convert time)."""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+from qadence.analog import add_background_hamiltonian
+from qadence.backend import BackendConfiguration
+from qadence.transpile import blockfn_to_circfn, flatten, scale_primitive_blocks_only
+
+
+def default_passes(config: "Configuration") -> list[Callable]:
+    """AnalogBlocks → HamEvo, flatten, push scales to the leaves (pyqtorch/config.py:21-37).
+
+    `chain_single_qubit_ops` is not needed: the fusion planner merges 1-qubit chains itself."""
+    return [
+        add_background_hamiltonian,
+        lambda circ: blockfn_to_circfn(flatten)(circ),
+        blockfn_to_circfn(scale_primitive_blocks_only),
+    ]
+
+
+@dataclass
+class Configuration(BackendConfiguration):
+    # ---- options shared with the pyqtorch backend (same names / defaults) ----
+    algo_hevo: str = "krylov"
+    """HamEvo algorithm: diagonal generators are exponentiated on the fly, everything else uses the
+    matrix-free Lanczos–Krylov propagator converged to 1e-13 (the reference's `EXP` is a dense
+    `matrix_exp`; results agree to the parity tolerance)."""
+    n_steps_hevo: int = 100
+    loop_expectation: bool = False
+    """Accepted for compatibility; the batched path never materialises per-term states."""
+    noise: None = None
+    dropout_probability: float = 0.0
+    n_eqs: int | None = None
+    shift_prefac: float = 0.5
+    gap_step: float = 1.0
+    lb: float | None = None
+    ub: float | None = None
+    # ---- b200sv options ----
+    device: str | None = None
+    """CUDA device of the simulation (default: current device)."""
+    dtype: str = "complex128"
+    """State precision: "complex128" (default, qadence/__init__.py:13-15) or "complex64"."""
+    results_on_input_device: bool = True
+    """Return wavefunctions / expectations on the device of the parameter tensors (CPU for a default
+    `QuantumModel`), so the backend is a drop-in even though it always computes on the GPU."""

@@ -1,0 +1,57 @@
+"""`DifferentiableBackend` for b200sv — replaces the stock torch engine
+(`/root/reference/qadence/engines/torch/differentiable_backend.py:24-88`), which hard-imports
+`pyqtorch.differentiation.AdjointExpectation` (`engines/torch/differentiable_expectation.py:9`).
+
+`ad` and `adjoint` both use the backend's own adjoint-method autograd Function (fused CUDA sweeps,
+one backward pass for all observables); `gpsr` re-uses qadence's `PSRExpectation` unchanged, which
+only needs forward `expectation` calls.
+"""
+
+from __future__ import annotations
+
+from functools import partial
+from typing import Any
+
+from qadence.backend import Backend as QuantumBackend
+from qadence.backend import ConvertedCircuit, ConvertedObservable
+from qadence.backends.parameter_shift_rules import general_psr
+from qadence.engines.differentiable_backend import DifferentiableBackend as DifferentiableBackendInterface
+from qadence.measurements import Measurements
+from qadence.mitigations import Mitigations
+from qadence.noise import NoiseHandler
+from qadence.types import ArrayLike, DiffMode, Endianness, Engine, ParamDictType
+
+
+class DifferentiableBackend(DifferentiableBackendInterface):
+    def __init__(self, backend: QuantumBackend, diff_mode: DiffMode = DiffMode.AD, **psr_args: int | float | None) -> None:
+        super().__init__(backend=backend, engine=Engine.TORCH, diff_mode=diff_mode)
+        self.psr_args = psr_args
+
+    def expectation(
+        self,
+        circuit: ConvertedCircuit,
+        observable: list[ConvertedObservable] | ConvertedObservable,
+        param_values: ParamDictType = {},
+        state: ArrayLike | None = None,
+        measurement: Measurements | None = None,
+        noise: NoiseHandler | None = None,
+        mitigation: Mitigations | None = None,
+        endianness: Endianness = Endianness.BIG,
+    ) -> Any:
+        observable = observable if isinstance(observable, list) else [observable]
+        if self.diff_mode == DiffMode.GPSR:
+            # qadence's own PSR machinery; torch and its pyqtorch import are only needed lazily here
+            from qadence.engines.torch.differentiable_expectation import DifferentiableExpectation
+
+            de = DifferentiableExpectation(
+                backend=self.backend, circuit=circuit, observable=observable, param_values=param_values, state=state,
+                measurement=measurement, noise=noise, mitigation=mitigation, endianness=endianness,
+            )
+            return partial(de.psr, psr_fn=general_psr, **self.psr_args)()
+        if measurement is not None:
+            raise NotImplementedError("shot-based measurement protocols are not supported by b200sv (exact expectation only)")
+        # AD and ADJOINT: the backend's expectation is itself differentiable (adjoint method)
+        return self.backend.expectation(
+            circuit=circuit, observable=observable, param_values=param_values, state=state, noise=noise,
+            mitigation=mitigation, endianness=endianness,
+        )

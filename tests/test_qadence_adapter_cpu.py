@@ -1,0 +1,248 @@
+"""The qadence-facing adapter (registration, conversion, Backend API semantics) on CPU.
+
+Needs the reference front-end (`/root/reference`, through tests/_shims) → marker `reference`.
+There is no GPU here and the product has no CPU fallback, so where a test must push numbers
+through `Backend.run/expectation/sample` the C-ABI-backed engine functions are monkeypatched with
+the CPU oracle (a test double living entirely in tests/); conversion itself is checked against the
+reference's own dense oracle `block_to_tensor`, like /root/reference/tests/qadence/test_matrices.py.
+"""
+
+from __future__ import annotations
+
+from collections import Counter
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import enable_reference
+
+pytestmark = pytest.mark.reference
+if not enable_reference():
+    pytest.skip("/root/reference not present", allow_module_level=True)
+
+import qadence  # noqa: E402
+import qadence.states as qstates  # noqa: E402
+from qadence import (  # noqa: E402
+    CNOT, CPHASE, CRX, CRZ, RX, RY, RZ, H, HamEvo, I, N, QuantumCircuit, QuantumModel, X, Y, Z, add, chain, feature_map, hea, kron,
+    qft, total_magnetization,
+)
+from qadence.backends.api import backend_factory  # noqa: E402
+from qadence.blocks.block_to_tensor import block_to_tensor  # noqa: E402
+from qadence.types import BackendName, DiffMode, Endianness, Engine  # noqa: E402
+
+from oracle import statevec as oracle  # noqa: E402
+from qadence_b200 import cabi, engine  # noqa: E402
+
+
+def _product_state(bitstring: str, batch_size: int = 1, **_: object) -> torch.Tensor:
+    s = torch.zeros(batch_size, 2 ** len(bitstring), dtype=torch.cdouble)
+    s[:, int(bitstring, 2)] = 1.0
+    return s
+
+
+qstates.product_state = _product_state
+
+
+@pytest.fixture
+def oracle_device(monkeypatch: pytest.MonkeyPatch) -> None:
+    """Replace the GPU entry points of `qadence_b200.engine` by the CPU oracle (test double)."""
+
+    def run(cp, values=None, state=None, dtype=torch.complex128, device=None):
+        return oracle.run(cp.program, {k: torch.as_tensor(v).detach() for k, v in (values or {}).items()}, state).to(dtype)
+
+    def expectation(cp, observables, values=None, state=None, dtype=torch.complex128, device=None):
+        out = oracle.expectation(cp.program, [o.obs for o in observables], values or {}, state)
+        return out.to(torch.float64 if dtype == torch.complex128 else torch.float32)
+
+    def sample(cp, values=None, n_shots=1, state=None, dtype=torch.complex128, device=None, uniforms=None, little_endian=False):
+        psi = oracle.run(cp.program, values or {}, state)
+        u = np.random.default_rng(0).random((psi.shape[0], n_shots)) if uniforms is None else uniforms.numpy()
+        idx = oracle.sample_indices(oracle.probabilities(psi), u)
+        return [Counter({(k[::-1] if little_endian else k): v for k, v in d.items()}) for d in oracle.counts_from_indices(idx, cp.n_qubits)]
+
+    monkeypatch.setattr(engine, "run", run)
+    monkeypatch.setattr(engine, "expectation", expectation)
+    monkeypatch.setattr(engine, "sample", sample)
+    monkeypatch.setattr(engine, "bit_reverse", lambda psi: oracle.invert_endianness_state(psi, int(psi.shape[1]).bit_length() - 1))
+
+
+# ------------------------------------------------------------------------------------------ registration
+def test_backend_is_registered_without_touching_qadence() -> None:
+    assert "b200sv" in BackendName.list() and BackendName("b200sv") == "b200sv"
+    assert "b200sv" in Engine.list()
+    for mode in (DiffMode.AD, DiffMode.ADJOINT, DiffMode.GPSR):
+        bk = backend_factory("b200sv", diff_mode=mode)
+        assert type(bk).__name__ == "DifferentiableBackend" and bk.backend.name == "b200sv"
+        assert bk.backend.config._use_gate_params is True
+    plain = backend_factory("b200sv", diff_mode=None)
+    assert type(plain).__name__ == "Backend"
+    # dict configuration resolves through qadence.backends.b200sv.config (import_config)
+    bk = backend_factory("b200sv", diff_mode="adjoint", configuration={"dtype": "complex64"})
+    assert bk.backend.config.dtype == "complex64"
+    from qadence.extensions import supported_gates
+
+    names = {g.__name__ for g in supported_gates("b200sv")}
+    assert {"RX", "CNOT", "HamEvo", "Toffoli", "MCPHASE", "Projector"} <= names and "TDagger" not in names
+    from dataclasses import asdict
+
+    assert "dtype" in asdict(bk.backend.config)  # QuantumModel._to_dict (model.py:487)
+
+
+def test_no_cpu_fallback() -> None:
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    bk = backend_factory("b200sv", diff_mode=None)
+    conv = bk.convert(QuantumCircuit(2, X(0)))
+    with pytest.raises(cabi.B200svError):
+        bk.run(conv.circuit, {})
+
+
+# ------------------------------------------------------------------------------------------ conversion
+BLOCKS = [
+    chain(X(0), Y(1), Z(2), H(0)),
+    chain(RX(0, 0.3), RY(1, "y"), RZ(2, "y"), CNOT(0, 2), CRX(1, 0, "y"), CPHASE(2, 1, 0.4)),
+    hea(3, 2),
+    chain(feature_map(3, param="y"), hea(3, 1)),
+    qft(3),
+    chain(HamEvo(add(0.7 * kron(Z(0), Z(1)), 0.3 * X(2), 1.1 * N(1)), 0.9), H(1)),
+    chain(kron(H(0), H(1), H(2)), add(kron(X(0), I(1)), 0.5 * Z(2))),
+    chain(2.0 * X(0), "y" * CRZ(0, 1, 0.2)),
+]
+
+
+@pytest.mark.parametrize("block", BLOCKS, ids=lambda b: type(b).__name__ + str(len(str(b)) % 97))
+def test_converted_program_equals_dense_oracle(block) -> None:
+    """Mirror of tests/qadence/test_matrices.py:68-72,582-771 for the b200sv converter."""
+    n = 3
+    bk = backend_factory("b200sv", diff_mode=None)
+    conv = bk.convert(QuantumCircuit(n, block))
+    inputs = {"y": torch.tensor([0.41])}
+    vals = conv.embedding_fn(conv.params, inputs)
+    rng = np.random.default_rng(1)
+    psi = torch.tensor(rng.normal(size=(1, 8)) + 1j * rng.normal(size=(1, 8)))
+    user = {**{k: v for k, v in conv.params.items() if not k.startswith("fix_")}, **inputs}
+    dense = block_to_tensor(block, values=user, qubit_support=tuple(range(n)))
+    want = torch.einsum("bij,bj->bi", dense, psi)
+    got = oracle.run(conv.circuit.native.program, {k: torch.as_tensor(v).detach() for k, v in vals.items()}, psi)
+    assert (got - want.detach()).abs().max().item() < 1e-12
+
+
+def test_observable_becomes_pauli_sum() -> None:
+    from qadence_b200.program import PauliSum
+
+    bk = backend_factory("b200sv", diff_mode=None)
+    obs = add(0.5 * X(0), kron(Y(1), Z(2)), 1.2 * N(2), "w" * Z(0))
+    conv = bk.convert(QuantumCircuit(3, hea(3, 1)), obs)
+    ps = conv.observable[0].native.obs
+    assert isinstance(ps, PauliSum) and len(ps.param_names) == 1
+    zz = conv = bk.convert(QuantumCircuit(3, hea(3, 1)), total_magnetization(3)).observable[0].native.obs
+    assert zz.is_diagonal and len(zz.terms) == 3
+
+
+def test_unlowered_analog_block_error() -> None:
+    from qadence import AnalogRX
+    from qadence_b200.qadence_backend.convert_ops import convert_block
+
+    with pytest.raises(NotImplementedError, match="device_specs"):
+        convert_block(AnalogRX(0.3), 2, backend_factory("b200sv", diff_mode=None).config)
+
+
+def test_cfg2_program_matches_standalone_builder() -> None:
+    """bench.py's standalone hea_program(20, 8) is the circuit qadence's hea(20, 8) converts to."""
+    from qadence_b200.program import hea_program
+
+    bk = backend_factory("b200sv", diff_mode="adjoint")
+    conv = bk.convert(QuantumCircuit(20, hea(20, 8)))
+    ours = hea_program(20, 8)
+    theirs = conv.circuit.native.program
+    assert len(theirs.ops) == len(ours.ops) == 632
+    uuid_to_name = {}
+    vals = conv.embedding_fn(conv.params, {})
+    assert len(vals) == 480
+    for a, b in zip(theirs.ops, ours.ops):
+        assert (a.kind, a.targets, a.controls) == (b.kind, b.targets, b.controls)
+        if isinstance(a.param, str):
+            uuid_to_name[a.param] = b.param
+    # gate k of the reference uses theta_k of the standalone builder
+    for u, nm in uuid_to_name.items():
+        assert torch.allclose(vals[u], conv.params[nm])
+
+
+# ------------------------------------------------------------------------------------------ Backend API semantics
+def test_state_validation_errors(oracle_device) -> None:
+    bk = backend_factory("b200sv", diff_mode=None)
+    conv = bk.convert(QuantumCircuit(2, kron(X(0), X(1))))
+    with pytest.raises(ValueError):  # test_quantum_pyq.py:164-169
+        bk.run(conv.circuit, state=torch.tensor([1.0, 0.0], dtype=torch.complex128))
+    with pytest.raises(TypeError):
+        bk.run(conv.circuit, state=torch.zeros(1, 4, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        bk.assign_parameters(conv.circuit, {})
+    # NB the reference's `is_pyq_shape` compares a torch.Size with a list (backends/utils.py:150-151) and is
+    # therefore always False: pyqtorch-shaped states are rejected by `validate_state` there too.
+    pyq_shaped = torch.zeros(2, 2, 1, dtype=torch.complex128)
+    with pytest.raises(ValueError):
+        bk.run(conv.circuit, state=pyq_shaped)
+    init = torch.tensor([[0, 0, 0, 1]], dtype=torch.complex128)
+    out = bk.run(conv.circuit, state=init)
+    assert out.shape == (1, 4) and out[0, 0] == 1
+
+
+def test_run_endianness_and_sample(oracle_device) -> None:
+    bk = backend_factory("b200sv", diff_mode=None)
+    conv = bk.convert(QuantumCircuit(3, X(0)))  # tests/backends/test_endianness.py:113-138
+    assert bk.run(conv.circuit)[0, 4] == 1
+    assert bk.run(conv.circuit, endianness=Endianness.LITTLE)[0, 1] == 1
+    assert bk.sample(conv.circuit, n_shots=100) == [Counter({"100": 100})]
+    assert bk.sample(conv.circuit, n_shots=100, endianness=Endianness.LITTLE) == [Counter({"001": 100})]
+
+
+def test_quantum_model_expectation_and_gradients(oracle_device) -> None:
+    """QuantumModel / QNN plumbing: values → embedding_fn → DifferentiableBackend → [B, n_obs], and
+    the autograd edge back to the nn.Parameters (configs[0] shape)."""
+    torch.manual_seed(0)
+    circ = QuantumCircuit(4, feature_map(4), hea(4, 2))
+    obs = [total_magnetization(4), kron(X(0), Y(1))]
+    model = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.ADJOINT)
+    x = torch.linspace(-0.9, 0.9, 16)
+    out = model.expectation({"phi": x})
+    assert out.shape == (16, 2)
+    out[:, 0].sum().backward()
+    grads = {k: p.grad.clone() for k, p in model._params.items() if p.requires_grad}
+    assert len(grads) == 24 and all(g is not None for g in grads.values())
+    user = {k: p.detach().clone().requires_grad_(p.requires_grad) for k, p in model._params.items()}
+    dense = block_to_tensor(circ.block, values={**user, "phi": x}, qubit_support=(0, 1, 2, 3))
+    psi = dense[:, :, 0]
+    om = block_to_tensor(obs[0], qubit_support=(0, 1, 2, 3))
+    e = torch.einsum("bi,ij,bj->b", psi.conj(), om[0], psi).real
+    assert torch.allclose(out[:, 0].detach(), e.detach(), atol=1e-12)
+    e.sum().backward()
+    for k, g in grads.items():
+        assert torch.allclose(g, user[k].grad, atol=1e-10), k
+
+
+def test_gpsr_equals_adjoint(oracle_device) -> None:
+    """tests/engines/test_torch.py:111-134 — adjoint == gpsr on the same circuit, through the plugin."""
+    torch.manual_seed(1)
+    circ = QuantumCircuit(2, chain(RX(0, "x"), RY(1, "t0"), CNOT(0, 1), RX(1, "t1")))
+    obs = total_magnetization(2)
+    vals = {"x": torch.tensor([0.3, 0.8])}
+    grads = {}
+    for mode in (DiffMode.ADJOINT, DiffMode.GPSR):
+        torch.manual_seed(1)
+        model = QuantumModel(circ, obs, backend="b200sv", diff_mode=mode)
+        for p in model._params.values():
+            if p.requires_grad:
+                p.data.fill_(0.7)
+        out = model.expectation(vals)
+        out.sum().backward()
+        grads[mode] = torch.stack([p.grad.reshape(()) for k, p in sorted(model._params.items()) if p.requires_grad and p.grad is not None])
+        assert grads[mode].numel() >= 2
+    assert torch.allclose(grads[DiffMode.ADJOINT], grads[DiffMode.GPSR], atol=1e-6)
+
+
+def test_parametric_observable_only_in_ad_mode() -> None:
+    bk = backend_factory("b200sv", diff_mode=DiffMode.ADJOINT)
+    with pytest.raises(ValueError):
+        bk.observable("w" * Z(0), 1)

@@ -1,0 +1,352 @@
+"""Multi-GPU execution: one process per GPU, `torch.distributed` (NCCL over NVLink 5 / NVSwitch).
+
+The reference only has data-parallel training (`qadence/ml_tools/train_utils/accelerator.py:296-305`,
+DDP over gloo/nccl); the two sharding axes below are the ones SURVEY.md §8(e) derives from the path:
+
+* **parameter / feature batches** shard trivially (every batch element is an independent state
+  vector): `shard_batch` + one all-reduce(SUM) of the gradient vector of shared parameters (C1).
+  No data-path collective.
+* **one large register** is sharded by its highest-order qubits: rank = the top g = log2(P) index
+  bits, each rank holds 2^(n-g) contiguous amplitudes.  Local gates, and any control / diagonal gate
+  on a global qubit, are communication-free (the kernels evaluate them from `index_hi`).  A
+  non-diagonal gate on a global qubit triggers a global↔local qubit exchange: because the g
+  highest LOCAL bits index P contiguous chunks, the exchange is exactly one all-to-all of
+  contiguous chunks (C2), done in place in bounded staging pieces so that a 128 GiB shard
+  (36 qubits on 8 GPUs) never needs a second copy.  Local re-indexing before / after the exchange
+  is done by in-place SWAP gates folded into the sweep kernels' permutation phase.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Mapping, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .program import Op, OpKind, PauliSum, Program
+
+A2A_STAGING_BYTES = 1 << 30
+
+
+# ---------------------------------------------------------------------------------------------------
+# process-group plumbing
+# ---------------------------------------------------------------------------------------------------
+def init_from_env(backend: str | None = None) -> tuple[int, int]:
+    """(rank, world) from torchrun's environment; initialises the default group if needed."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch sharding (configs[1]-style parameter batches, configs[3] training batches)
+# ---------------------------------------------------------------------------------------------------
+def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [lo, hi) slice of the batch owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(values: Mapping[str, Tensor], batch: int, rank: int, world: int) -> dict[str, Tensor]:
+    """Slice every `[batch]`-shaped entry; `[1]`-shaped (shared) parameters are replicated."""
+    lo, hi = shard_range(batch, rank, world)
+    out = {}
+    for k, v in values.items():
+        if isinstance(v, Tensor) and v.dim() >= 1 and v.shape[0] == batch and batch > 1:
+            out[k] = v[lo:hi]
+        else:
+            out[k] = v
+    return out
+
+
+def allreduce_shared_gradients(params: Sequence[Tensor], group=None) -> None:
+    """C1: one all-reduce(SUM) of the flattened gradient vector of the shared parameters —
+    replaces DDP's bucket all-reduce (`accelerator.py:296-305`); 576 doubles at configs[3]."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off : off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def gather_batch(local: Tensor, batch: int, group=None) -> Tensor:
+    """All-gather per-rank `[b_r, ...]` results into `[batch, ...]` (only when a caller needs it)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_range(batch, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((mx, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)])
+
+
+# ---------------------------------------------------------------------------------------------------
+# global-qubit sharding: layout planning (pure host logic, unit-tested on CPU)
+# ---------------------------------------------------------------------------------------------------
+def hard_qubits(op: Op) -> tuple[int, ...]:
+    """Qubits an op acts on NON-diagonally (they must be local when the op runs)."""
+    if op.kind in (OpKind.RZ, OpKind.PHASE, OpKind.SCALE):
+        return ()
+    if op.kind == OpKind.MAT1:
+        m = op.matrix
+        return () if (m[0, 1] == 0 and m[1, 0] == 0) else tuple(op.targets)
+    if op.kind in (OpKind.RX, OpKind.RY, OpKind.SWAP):
+        return tuple(op.targets)
+    raise NotImplementedError(f"{op.kind.name} is not supported on a qubit-sharded register yet")
+
+
+@dataclass
+class LayoutStep:
+    kind: str  # "gates" | "a2a"
+    ops: list[Op] = field(default_factory=list)  # "gates": ops relabelled to PHYSICAL qubit labels
+
+
+@dataclass
+class LayoutPlan:
+    n_qubits: int
+    g: int  # number of global (rank) qubits
+    steps: list[LayoutStep]
+    final_layout: list[int]  # final_layout[q] = physical label of logical qubit q (identity if restored)
+    n_exchanges: int
+
+
+def _relabel(op: Op, layout: Sequence[int]) -> Op:
+    return Op(op.kind, tuple(layout[q] for q in op.targets), tuple(layout[q] for q in op.controls), op.param, op.matrix, None, None, op.label)
+
+
+def plan_layout(ops: Sequence[Op], n: int, g: int, restore: bool = True) -> LayoutPlan:
+    """Insert global↔local exchanges so that every non-diagonal target is local when its gate runs.
+
+    Physical label k < g is a rank bit (label 0 = MSB of the rank); labels g..2g-1 are the g
+    highest local bits.  An exchange ("a2a") swaps label k with label g+k for every k < g.  Victims
+    (logical qubits sent to the rank bits) are the local qubits whose next non-diagonal use is
+    farthest away (Belady); they are first moved to labels g..2g-1 by in-place local SWAP gates.
+    """
+    if g == 0:
+        return LayoutPlan(n, 0, [LayoutStep("gates", list(ops))], list(range(n)), 0)
+    if n < 2 * g:
+        raise ValueError("a register sharded over 2^g ranks needs at least 2g qubits")
+    layout = list(range(n))  # logical -> physical
+    hard = [hard_qubits(op) for op in ops]
+    INF = len(ops) + 1
+    # next_use[i][q]: first j >= i with q in hard[j]
+    nxt = [INF] * n
+    next_use: list[list[int]] = [[]] * (len(ops) + 1)
+    next_use[len(ops)] = list(nxt)
+    for i in range(len(ops) - 1, -1, -1):
+        for q in hard[i]:
+            nxt[q] = i
+        next_use[i] = list(nxt)
+
+    steps: list[LayoutStep] = [LayoutStep("gates")]
+    n_ex = 0
+
+    def emit(op: Op) -> None:
+        if steps[-1].kind != "gates":
+            steps.append(LayoutStep("gates"))
+        steps[-1].ops.append(op)
+
+    def local_swap(la: int, lb: int) -> None:
+        """Swap the contents of physical labels la, lb (both local) and update the layout."""
+        if la == lb:
+            return
+        emit(Op(OpKind.SWAP, (la, lb), (), label="layout-swap"))
+        qa, qb = layout.index(la), layout.index(lb)
+        layout[qa], layout[qb] = lb, la
+
+    def exchange(victims: Sequence[int]) -> None:
+        nonlocal n_ex
+        # move victims to labels g..2g-1 (any order), then swap label k <-> g+k
+        top = list(range(g, 2 * g))
+        free = [lab for lab in top if layout.index(lab) not in victims]
+        for v in victims:
+            if layout[v] not in top:
+                local_swap(layout[v], free.pop())
+        steps.append(LayoutStep("a2a"))
+        n_ex += 1
+        for q in range(n):
+            if layout[q] < g:
+                layout[q] += g
+            elif layout[q] < 2 * g:
+                layout[q] -= g
+
+    for i, op in enumerate(ops):
+        need = [q for q in hard[i] if layout[q] < g]
+        if need:
+            local_qs = [q for q in range(n) if layout[q] >= g and q not in hard[i]]
+            local_qs.sort(key=lambda q: (-next_use[i][q], -q))
+            exchange(local_qs[:g])
+            assert all(layout[q] >= g for q in hard[i])
+        emit(_relabel(op, layout))
+
+    if restore and layout != list(range(n)):
+        if any(layout[q] < g for q in range(g)):  # some of logical 0..g-1 sit on rank bits in the wrong place
+            local_qs = [q for q in range(n) if layout[q] >= g and q >= g]
+            exchange(local_qs[:g])
+        if any(layout[q] != q for q in range(g)):
+            for k in range(g):  # logical k -> label g+k, then one exchange puts it on rank bit k
+                local_swap(layout[k], g + k)
+            steps.append(LayoutStep("a2a"))
+            n_ex += 1
+            for q in range(n):
+                if layout[q] < g:
+                    layout[q] += g
+                elif layout[q] < 2 * g:
+                    layout[q] -= g
+        for q in range(g, n):  # remaining local permutation, cycle by cycle
+            if layout[q] != q:
+                local_swap(layout[q], q)
+        assert layout == list(range(n)), layout
+    steps = [s for s in steps if s.kind == "a2a" or s.ops]
+    return LayoutPlan(n, g, steps, list(layout), n_ex)
+
+
+# ---------------------------------------------------------------------------------------------------
+# C2: in-place chunked all-to-all of the g highest local bits with the rank bits
+# ---------------------------------------------------------------------------------------------------
+def exchange_global_local(state: Tensor, world: int, group=None, staging_bytes: int = A2A_STAGING_BYTES) -> int:
+    """In place: the amplitude block with (rank=r, top-local=s) moves to (rank=s, top-local=r).
+
+    `state` is this rank's `[2^n_local]` (or `[1, 2^n_local]`) contiguous shard.  Returns the number
+    of bytes this rank sent over the fabric (S_local·(1 − 1/P))."""
+    flat = state.view(-1)
+    total = flat.numel()
+    assert total % world == 0
+    chunk = total // world  # contiguous block per destination (top-local index = destination rank)
+    esz = flat.element_size()
+    piece = max(1, min(chunk, staging_bytes // (esz * world)))
+    send = torch.empty(world * piece, dtype=flat.dtype, device=flat.device)
+    recv = torch.empty_like(send)
+    view = flat.view(world, chunk)
+    sent = 0
+    for off in range(0, chunk, piece):
+        w = min(piece, chunk - off)
+        s = send[: world * w].view(world, w)
+        r = recv[: world * w].view(world, w)
+        s.copy_(view[:, off : off + w])
+        dist.all_to_all_single(r.view(-1), s.view(-1), group=group)
+        view[:, off : off + w].copy_(r)
+        sent += (world - 1) * w * esz
+    return sent
+
+
+# ---------------------------------------------------------------------------------------------------
+# qubit-sharded simulator
+# ---------------------------------------------------------------------------------------------------
+class QubitShardedSimulator:
+    """Runs a Program of simple gates on an n-qubit register sharded over `world` = 2^g GPUs."""
+
+    def __init__(self, program: Program, rank: int, world: int, device: torch.device | str | None = None, group=None):
+        from . import engine
+
+        if world & (world - 1):
+            raise ValueError("world size must be a power of two")
+        self.program = program
+        self.n = program.n_qubits
+        self.g = world.bit_length() - 1
+        self.n_local = self.n - self.g
+        self.rank, self.world, self.group = rank, world, group
+        self.device = engine._dev(device)
+        self.names = program.param_names
+        self.slot_of = {nm: i for i, nm in enumerate(self.names)}
+        self.layout = plan_layout(program.ops, self.n, self.g, restore=True)
+        self.index_hi = rank << self.n_local
+        self._plans: dict = {}
+        self.bytes_sent = 0
+        self.stats = {"exchanges": self.layout.n_exchanges, "gate_steps": sum(1 for s in self.layout.steps if s.kind == "gates")}
+
+    def _device_plan(self, i: int, dtype: torch.dtype):
+        from .engine import DevicePlan
+        from .plan import TileConfig, build_plan
+
+        key = (i, dtype)
+        if key not in self._plans:
+            cfg = TileConfig.default(dtype == torch.complex128, False)
+            self._plans[key] = DevicePlan(build_plan(self.layout.steps[i].ops, self.n_local, self.slot_of, cfg, n_total=self.n), self.device)
+        return self._plans[key]
+
+    def n_sweeps(self, dtype: torch.dtype = torch.complex128) -> int:
+        return sum(self._device_plan(i, dtype).n_sweeps for i, s in enumerate(self.layout.steps) if s.kind == "gates")
+
+    def zero_state(self, dtype: torch.dtype = torch.complex128) -> Tensor:
+        from . import engine
+
+        st = engine.zero_state(self.n_local, 1, dtype, self.device)
+        if self.rank != 0:
+            st[0, 0] = 0
+        return st
+
+    def run(self, values: Mapping[str, Tensor] | None = None, state: Tensor | None = None, dtype: torch.dtype = torch.complex128) -> Tensor:
+        """Returns this rank's `[1, 2^n_local]` shard of U|ψ> in the standard layout (rank = top bits)."""
+        from . import cabi, engine
+
+        lib = cabi.load()
+        values = values or {}
+        st = self.zero_state(dtype) if state is None else state
+        ptable = engine.pack_params(self.names, values, 1, self.device)
+        self.bytes_sent = 0
+        for i, step in enumerate(self.layout.steps):
+            if step.kind == "a2a":
+                self.bytes_sent += exchange_global_local(st, self.world, self.group)
+                continue
+            dp = self._device_plan(i, dtype)
+            rc = lib.b200sv_apply_plan(st.data_ptr(), engine._DT[dtype], self.n_local, 1, ptable.data_ptr(), C.byref(dp.struct), 0,
+                                       dp.n_sweeps, self.index_hi, engine._stream_ptr(self.device))
+            cabi.check(rc, "apply_plan (sharded)")
+        return st
+
+    def expectation_diagonal(self, state: Tensor, obs: PauliSum) -> Tensor:
+        """Re<ψ|O|ψ> for a diagonal (Z-string) observable: local partial sum + all-reduce of one scalar."""
+        from . import engine
+
+        if not obs.is_diagonal:
+            raise NotImplementedError("only diagonal observables are supported on a qubit-sharded register")
+        cps = engine.CompiledPauliSum.build(obs)
+        out = self._pauli_expectation(cps, state)
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def _pauli_expectation(self, cps, state: Tensor) -> Tensor:
+        from . import cabi, engine
+
+        dev = state.device
+        coef = cps.coef({}, dev)
+        # terms are packed for n_total qubits: bit = n-1-q, rank bits resolved through index_hi
+        out = torch.zeros(1, dtype=torch.float64, device=dev)
+        cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+        rc = cabi.load().b200sv_pauli_expectation(state.data_ptr(), engine._DT[state.dtype], self.n_local, 1, cps.terms(dev).data_ptr(),
+                                                  cps.n_terms, cf.data_ptr(), coef.shape[1], out.data_ptr(), self.index_hi, engine._stream_ptr(dev))
+        cabi.check(rc, "pauli_expectation (sharded)")
+        return out
+
+    def norm2(self, state: Tensor) -> Tensor:
+        from . import engine
+
+        out = engine.dot(state, state).real.clone()
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out

@@ -126,6 +126,7 @@ class ConstPool:
 
 
 def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, r: int = 2) -> list[_G]:
+    """`n` is the TOTAL qubit count: bit positions >= n_local refer to the rank bits of a sharded state."""
     out: list[_G] = []
     for i, op in enumerate(ops):
         bit = lambda q: n - 1 - q  # noqa: E731
@@ -373,13 +374,21 @@ class SweepPlan:
         return [i for sw in self.order for rd in sw for i in rd]
 
 
-def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig, chains: bool = True) -> SweepPlan:
+def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig, chains: bool = True,
+               n_total: int | None = None) -> SweepPlan:
+    """Plan a run of simple gates on `n` LOCAL qubits.  With `n_total > n` the state is sharded by its
+    highest-order qubits: qubit q maps to bit n_total-1-q, bits >= n are rank bits and may only be
+    touched diagonally / as controls (evaluated from `index_hi` by the kernels)."""
+    n_total = n if n_total is None else n_total
     pool = ConstPool()
     m = min(cfg.m, n)
     r = max(1, min(cfg.r, m)) if n > 0 else 1
     if m - r > 8:
         m = r + 8
-    lowered = _lower(ops, n, slot_of, pool, r)
+    lowered = _lower(ops, n_total, slot_of, pool, r)
+    for g_ in lowered:
+        if any(b >= n for b in g_.hard):
+            raise ValueError("non-diagonal gate on a global (rank) qubit: make it local first (dist.plan_layout)")
     forced = set(range(min(cfg.low, m)))
     sweep_groups = _pack(lowered, m, forced, MAX_GATES_PER_SWEEP)
 

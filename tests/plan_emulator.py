@@ -54,8 +54,9 @@ def _gate_matrix(plan: P.SweepPlan, g, params: np.ndarray, b: int, dagger: bool)
     return ("mat", m.conj().T if dagger else m)
 
 
-def _perm_src(g, tile, idx: np.ndarray) -> np.ndarray:
+def _perm_src(g, tile, idx: np.ndarray, gidx: np.ndarray | None = None) -> np.ndarray:
     """Index map of one X / CNOT / SWAP record (self-inverse): new[i] = old[src[i]]."""
+    gidx = idx if gidx is None else gidx
     ta = tile[int(g["a"])]
     if int(g["kind"]) == P.GK_SWAP:
         tb = tile[int(g["a2"])]
@@ -65,12 +66,12 @@ def _perm_src(g, tile, idx: np.ndarray) -> np.ndarray:
     c = int(g["ext_bit"])
     if c < 0:
         return (idx ^ np.uint64(1 << ta)).astype(np.int64)
-    cb = (idx >> np.uint64(c)) & np.uint64(1)
+    cb = (gidx >> np.uint64(c)) & np.uint64(1)
     return (idx ^ (cb * np.uint64(1 << ta))).astype(np.int64)
 
 
-def _apply_perm_record(st: np.ndarray, g, tile, idx: np.ndarray) -> np.ndarray:
-    return st[:, _perm_src(g, tile, idx)]
+def _apply_perm_record(st: np.ndarray, g, tile, idx: np.ndarray, gidx: np.ndarray | None = None) -> np.ndarray:
+    return st[:, _perm_src(g, tile, idx, gidx)]
 
 
 def _check_perm_map(plan: P.SweepPlan, sw, rd, tile, n: int) -> None:
@@ -113,12 +114,13 @@ def _check_perm_map(plan: P.SweepPlan, sw, rd, tile, n: int) -> None:
             assert int(leaders[0]["ctrl_ext"]) == 0 and int(leaders[0]["ctrl_reg"]) == 0
 
 
-def emulate(plan: P.SweepPlan, state: np.ndarray, params: np.ndarray, dagger: bool = False) -> np.ndarray:
+def emulate(plan: P.SweepPlan, state: np.ndarray, params: np.ndarray, dagger: bool = False, index_hi: int = 0) -> np.ndarray:
     """state [B, 2^n] complex → new state after all sweeps (forward, or reversed with daggers)."""
     st = state.astype(np.complex128).copy()
     B, N = st.shape
     n = plan.n_qubits
     idx = np.arange(N, dtype=np.uint64)
+    gidx = idx | np.uint64(index_hi)  # index seen by control / diagonal predicates (rank bits of a shard)
     sweeps = list(range(plan.n_sweeps))
     for s in (reversed(sweeps) if dagger else sweeps):
         sw = plan.sweeps[s]
@@ -140,7 +142,7 @@ def emulate(plan: P.SweepPlan, state: np.ndarray, params: np.ndarray, dagger: bo
             for gi in (reversed(gl) if dagger else gl):
                 g = plan.gates[gi]
                 if int(g["xkind"]) == P.XK_PERM:
-                    st = _apply_perm_record(st, g, tile, idx)
+                    st = _apply_perm_record(st, g, tile, idx, gidx)
                     continue
                 cext = int(g["ctrl_ext"])
                 assert cext & regmask == 0
@@ -148,7 +150,7 @@ def emulate(plan: P.SweepPlan, state: np.ndarray, params: np.ndarray, dagger: bo
                 for a in range(r):
                     if (int(g["ctrl_reg"]) >> a) & 1:
                         cmask |= 1 << regbit[a]
-                active = (idx & np.uint64(cmask)) == np.uint64(cmask)
+                active = (gidx & np.uint64(cmask)) == np.uint64(cmask)
                 for b in range(B):
                     what = _gate_matrix(plan, g, params, b, dagger)
                     v = st[b]
@@ -168,9 +170,12 @@ def emulate(plan: P.SweepPlan, state: np.ndarray, params: np.ndarray, dagger: bo
                     tbit = regbit[a] if a >= 0 else int(g["ext_bit"])
                     if a < 0:
                         assert mat[0, 1] == 0 and mat[1, 0] == 0, "external targets must be diagonal"
-                    bit = ((idx >> np.uint64(tbit)) & np.uint64(1)).astype(np.int64)
-                    partner = (idx ^ np.uint64(1 << tbit)).astype(np.int64)
-                    new = mat[bit, bit] * v + mat[bit, 1 - bit] * v[partner]
+                    bit = ((gidx >> np.uint64(tbit)) & np.uint64(1)).astype(np.int64)
+                    if tbit >= n:  # external diagonal on a rank bit
+                        new = mat[bit, bit] * v
+                    else:
+                        partner = (idx ^ np.uint64(1 << tbit)).astype(np.int64)
+                        new = mat[bit, bit] * v + mat[bit, 1 - bit] * v[partner]
                     st[b] = np.where(active, new, v)
     return st
 

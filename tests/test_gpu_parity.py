@@ -189,3 +189,24 @@ def test_hamevo_krylov_and_diagonal() -> None:
     assert (out[:, 0].detach().cpu() - e).abs().max().item() < 1e-10
     assert (vals["t"].grad - gr["t"]).abs().max().item() < 1e-8
     assert abs(vals["a"].grad.item() - gr["a"].sum().item()) < 1e-8
+
+
+def test_sharded_simulator_world_1_matches_engine() -> None:
+    """The qubit-sharded driver with a single rank (g = 0) is the plain engine."""
+    import numpy as np
+
+    from qadence_b200 import dist as qdist
+    from qadence_b200.program import Program
+    from tests.test_dist_cpu import qft_program
+
+    n = 12
+    prog = Program(n, qft_program(n).ops + hea_program(n, 1).ops)
+    g = torch.Generator().manual_seed(3)
+    values = {nm: 2 * torch.pi * torch.rand(1, generator=g, dtype=torch.float64) for nm in prog.param_names}
+    sim = qdist.QubitShardedSimulator(prog, 0, 1, "cuda:0")
+    st = sim.run(values)
+    want = oracle.run(prog, values)
+    assert (st.cpu() - want).abs().max().item() < 1e-10
+    assert abs(sim.norm2(st).item() - 1.0) < 1e-10
+    e = sim.expectation_diagonal(st, total_magnetization(n)).item()
+    assert abs(e - oracle.expectation(prog, [total_magnetization(n)], values).item()) < 1e-10

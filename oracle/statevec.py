@@ -285,7 +285,7 @@ def infer_batch(values: Mapping[str, torch.Tensor]) -> int:
     b = 1
     for v in values.values():
         v = torch.as_tensor(v)
-        if v.dim() >= 1:
+        if v.dim() in (1, 3):
             b = max(b, v.shape[0])
     return b
 

@@ -195,7 +195,7 @@ def infer_batch(values: Mapping[str, Any] | None) -> int:
     """Max leading length of the tensor values (`qadence/backends/utils.py:169-184`)."""
     b = 1
     for v in (values or {}).values():
-        if isinstance(v, Tensor) and v.dim() >= 1:
+        if isinstance(v, Tensor) and v.dim() in (1, 3):  # [B] scalars or [B, k, k] generator matrices; a bare [k, k] matrix is not a batch
             b = max(b, v.shape[0])
     return b
 

@@ -1,6 +1,6 @@
 """configs[4]: chain(qft(n), hea(n, depth)) on a register sharded by its highest-order qubits.
 
-    torchrun --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/sharded_check.py --n 28 [--verify]
+    torchrun --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 tools/sharded_check.py --qubits 28 [--verify]
 
 --verify: rank 0 also runs the same program on ONE GPU (n <= 29) and every rank compares its shard.
 Always checks norm == 1; prints gates/s, HBM fraction of the local sweeps and NVLink bytes.
@@ -32,7 +32,7 @@ def qft_program(n):
 
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=26)
+ap.add_argument("--qubits", type=int, default=26)
 ap.add_argument("--depth", type=int, default=1)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
@@ -41,7 +41,7 @@ rank, world = qdist.init_from_env("nccl")
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
-n = args.n
+n = args.qubits
 prog = Program(n, qft_program(n).ops + hea_program(n, args.depth).ops)
 g = torch.Generator().manual_seed(7)
 values = {nm: 2 * torch.pi * torch.rand(1, generator=g, dtype=torch.float64) for nm in prog.param_names}

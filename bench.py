@@ -183,7 +183,9 @@ def main() -> None:
     fwd = cp.device_plan(seg, dtype, False, dev)
     adj = cp.device_plan(seg, dtype, True, dev)
     coef = cob.pauli.coef({}, dev)
-    launches_per_step = 1 + fwd.n_sweeps + 1 + 1 + adj.n_sweeps
+    launches_per_step = 1 + (1 + fwd.n_sweeps) + 1 + 1 + (1 + adj.n_sweeps + 1)  # init, resolve+fwd sweeps, <O>, λ=Oψ, resolve+adj sweeps+grad
+    ws_f = fwd.workspace(dtype, BATCH, False).data_ptr()
+    ws_a = adj.workspace(dtype, BATCH, True).data_ptr()
 
     # ---------------- device-resident step (inputs already in HBM) ----------------
     ptable = host_params.to(dev)
@@ -195,11 +197,11 @@ def main() -> None:
     def device_step():
         st = _stream_ptr(dev)
         cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st), "init")
-        cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, st), "fwd")
+        cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
         e = engine.pauli_expectation(cob.pauli, coef, psi)
         engine.pauli_apply(cob.pauli, coef, psi, out=lam)
         grads.zero_()
-        cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0, adj.n_sweeps, 0, st), "adj")
+        cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0, adj.n_sweeps, 0, ws_a, st), "adj")
         return e
 
     def sync_all():
@@ -255,13 +257,13 @@ def main() -> None:
     st = _stream_ptr(dev)
     device_step()
     cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st), "init")
-    cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, st), "fwd")
+    cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
     engine.pauli_apply(cob.pauli, coef, psi, out=lam)
     torch.cuda.synchronize(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(adj.n_sweeps + 1)]
     ev[0].record()
     for i, s in enumerate(range(adj.n_sweeps - 1, -1, -1)):
-        cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), s, s + 1, 0, st), "adj")
+        cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), s, s + 1, 0, ws_a, st), "adj")
         ev[i + 1].record()
     torch.cuda.synchronize(dev)
     adj_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(adj.n_sweeps)]
@@ -269,7 +271,7 @@ def main() -> None:
     evf = [torch.cuda.Event(enable_timing=True) for _ in range(fwd.n_sweeps + 1)]
     evf[0].record()
     for s in range(fwd.n_sweeps):
-        cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), s, s + 1, 0, st), "fwd")
+        cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), s, s + 1, 0, ws_f, st), "fwd")
         evf[s + 1].record()
     torch.cuda.synchronize(dev)
     fwd_ms = [evf[i].elapsed_time(evf[i + 1]) for i in range(fwd.n_sweeps)]

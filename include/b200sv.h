@@ -108,7 +108,7 @@ typedef struct b200sv_round {  /* 96 bytes */
   int32_t flags;      /* B200SV_RF_*                                                               */
 } b200sv_round;
 
-typedef struct b200sv_sweep {  /* 96 bytes: one kernel launch = one read + one write of the state  */
+typedef struct b200sv_sweep {  /* 128 bytes: one kernel launch = one read + one write of the state */
   int32_t m;            /* tile bits: 2^m amplitudes staged in shared memory per CTA               */
   int32_t r;            /* register bits: 2^r amplitudes per thread per round                      */
   int32_t first_round;
@@ -119,6 +119,9 @@ typedef struct b200sv_sweep {  /* 96 bytes: one kernel launch = one read + one w
   int32_t n_exec;       /* resolved entries (chains) in this sweep                                  */
   uint8_t tile_bits[16];  /* global bit position of tile-local bit i (ascending)                   */
   uint8_t outer_bits[48]; /* global bit positions enumerated by the CTA index (ascending)          */
+  int32_t first_exec;   /* offset of this sweep's resolved entries in the plan-wide tables          */
+  int32_t n_seg;        /* CTA index -> base index: sum_s ((c >> src) & (2^len - 1)) << dst         */
+  struct { uint8_t src, len, dst, pad; } seg[6];
 } b200sv_sweep;
 
 /* Device-resident plan: the three arrays above plus the constant pool, uploaded once at convert
@@ -130,7 +133,8 @@ typedef struct b200sv_plan {
   const double* consts;         /* device, complex128 pool as (re, im) pairs */
   const b200sv_sweep* sweeps_host; /* host copy of `sweeps` (launch geometry) */
   int32_t n_sweeps;
-  int32_t pad;
+  int32_t n_exec_total;         /* resolved entries over all sweeps */
+  const int32_t* exec_leader;   /* device: gate-record index of the leader of resolved entry x */
 } b200sv_plan;
 
 /* ---- Pauli-sum records (observables, Rydberg / Pauli-like HamEvo generators) ----------------- */
@@ -153,12 +157,18 @@ int b200sv_device_sm_count(void);
  * (backends/pyqtorch/backend.py:171). */
 int b200sv_init_zero_state(void* state, int dtype, int n_qubits, int64_t batch, void* stream);
 
+/* Workspace (device bytes) that apply / adjoint need for `batch` states: the table of resolved gates
+ * (one 2x2 per chain and batch element, sincos evaluated ONCE per launch by a small resolve kernel
+ * instead of once per CTA) and, for the adjoint, the moment accumulators.  Never allocated here. */
+int64_t b200sv_plan_workspace_bytes(const b200sv_plan* plan, int dtype, int64_t batch, int adjoint);
+
 /* Forward execution of sweeps [first, last) of a plan, in place.  Replaces the per-gate einsum loop
  * `circuit.native.run(state, values)` (backends/pyqtorch/backend.py:176).
  * `index_hi` is OR-ed into the basis index seen by control / diagonal predicates (rank bits of a
  * state sharded by its highest-order qubits); 0 on a single GPU. */
 int b200sv_apply_plan(void* state, int dtype, int n_qubits, int64_t batch, const double* params,
-                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* stream);
+                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* workspace,
+                      void* stream);
 
 /* Adjoint (reverse) execution of sweeps [first, last) of a plan on psi AND lambda, accumulating
  * grads[grad_row][b] += 2 Re<lambda| dU/dθ |psi> for every gate flagged B200SV_GF_GRAD.
@@ -166,7 +176,7 @@ int b200sv_apply_plan(void* state, int dtype, int n_qubits, int64_t batch, const
  * (call site engines/torch/differentiable_expectation.py:153-165). */
 int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n_qubits, int64_t batch,
                         const double* params, double* grads, const b200sv_plan* plan, int first,
-                        int last, uint64_t index_hi, void* stream);
+                        int last, uint64_t index_hi, void* workspace, void* stream);
 
 /* out[b] (+)= Re <psi_b| sum_t coef[row_t][b] P_t |psi_b>.  coef is a device table
  * `double[n_rows][coef_ld][2]` (complex), coef_ld = batch or 1 (broadcast).

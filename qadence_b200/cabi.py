@@ -22,6 +22,7 @@ EXPORTS = [
     "b200sv_abi_version",
     "b200sv_device_sm_count",
     "b200sv_init_zero_state",
+    "b200sv_plan_workspace_bytes",
     "b200sv_apply_plan",
     "b200sv_adjoint_plan",
     "b200sv_pauli_expectation",
@@ -48,7 +49,8 @@ class PlanStruct(C.Structure):
         ("consts", C.c_void_p),
         ("sweeps_host", C.c_void_p),
         ("n_sweeps", C.c_int32),
-        ("pad", C.c_int32),
+        ("n_exec_total", C.c_int32),
+        ("exec_leader", C.c_void_p),
     ]
 
 
@@ -80,8 +82,9 @@ def load() -> C.CDLL:
         "b200sv_abi_version": [],
         "b200sv_device_sm_count": [],
         "b200sv_init_zero_state": [vp, i32, i32, i64, vp],
-        "b200sv_apply_plan": [vp, i32, i32, i64, vp, vp, i32, i32, u64, vp],
-        "b200sv_adjoint_plan": [vp, vp, i32, i32, i64, vp, vp, vp, i32, i32, u64, vp],
+        "b200sv_plan_workspace_bytes": [vp, i32, i64, i32],
+        "b200sv_apply_plan": [vp, i32, i32, i64, vp, vp, i32, i32, u64, vp, vp],
+        "b200sv_adjoint_plan": [vp, vp, i32, i32, i64, vp, vp, vp, i32, i32, u64, vp, vp],
         "b200sv_pauli_expectation": [vp, i32, i32, i64, vp, i32, vp, i64, vp, u64, vp],
         "b200sv_pauli_apply": [vp, vp, vp, i32, i32, i64, vp, i32, vp, i64, f64, f64, f64, f64, u64, vp],
         "b200sv_diag_evolve": [vp, i32, i32, i64, vp, i32, vp, i64, vp, i64, f64, u64, vp],
@@ -97,7 +100,7 @@ def load() -> C.CDLL:
     for name, args in protos.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name == "b200sv_plan_workspace_bytes" else C.c_int
     if lib.b200sv_abi_version() != 1:
         raise B200svError("libb200sv.so ABI version mismatch")
     _lib = lib

@@ -1,7 +1,12 @@
 // b200sv C-ABI implementation (see include/b200sv.h).  sm_100a only; no CPU fallback.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+
+#ifndef B200SV_PERSISTENT_DEFAULT
+#define B200SV_PERSISTENT_DEFAULT 0
+#endif
 
 #include "b200sv.h"
 #include "sweep.cuh"
@@ -25,12 +30,37 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // sweep launchers
 // ------------------------------------------------------------------------------------------------
+template <typename real> struct Workspace {
+  ExecGate<real>* xtab;
+  double* mom;
+};
+
+template <typename real>
+Workspace<real> carve_workspace(void* ws, const b200sv_plan* plan, int64_t batch) {
+  Workspace<real> w;
+  w.xtab = reinterpret_cast<ExecGate<real>*>(ws);
+  size_t bytes = (size_t)plan->n_exec_total * (size_t)batch * sizeof(ExecGate<real>);
+  bytes = (bytes + 255) & ~(size_t)255;
+  w.mom = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + bytes);
+  return w;
+}
+
+template <typename real>
+size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool adjoint) {
+  size_t bytes = (size_t)plan->n_exec_total * (size_t)batch * sizeof(ExecGate<real>);
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (adjoint) bytes += (size_t)plan->n_exec_total * (size_t)batch * 4 * sizeof(double);
+  return bytes + 256;
+}
+
 template <typename real, int R, bool ADJ>
 int launch_sweep(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
-                 int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
+                 const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
-  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds);
+  static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
+  const int nbuf = persistent ? 2 : 1;
+  const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
   auto kern = sweep_kernel<real, R, ADJ>;
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
@@ -39,27 +69,71 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   }
   const int nt = 1 << (sw.m - R);
   if (nt > SweepCfg<real, R, ADJ>::MAXT) return B200SV_E_ARG;
-  const long long grid = ((long long)batch) << sw.n_outer;
-  if (grid <= 0 || grid > 2147483647ll) return B200SV_E_ARG;
+  const long long total = ((long long)batch) << sw.n_outer;
+  if (total <= 0) return B200SV_E_ARG;
+  static int resident = 0;  // persistent grid: CTAs that fit on the device at once
+  if (resident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SweepCfg<real, R, ADJ>::MAXT, smem));
+    resident = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  long long grid = (!persistent || total < resident) ? total : resident;
+  const long long per_cta = (total + grid - 1) / grid;
+  grid = (total + per_cta - 1) / per_cta;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
   kern<<<(unsigned)grid, nt, smem, st>>>((c2*)psi, (c2*)lam, params, grads, plan->sweeps, plan->rounds,
-                                         plan->gates, plan->consts, s, n, (long long)batch,
-                                         (unsigned long long)index_hi, dir);
+                                         plan->gates, plan->consts, ws.xtab, ws.mom, s, n, (long long)batch,
+                                         (unsigned long long)index_hi, dir, per_cta, nbuf);
   LAUNCH_CK();
   return 0;
 }
 
 template <typename real, bool ADJ>
 int launch_sweep_r(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
-                   int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
+                   const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   const b200sv_sweep& sw = plan->sweeps_host[s];
   if (sw.m < sw.r || sw.m - sw.r > 8 || sw.m > 12 || sw.n_outer != n - sw.m) return B200SV_E_ARG;
   switch (sw.r) {
-    case 1: return launch_sweep<real, 1, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
-    case 2: return launch_sweep<real, 2, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
-    case 3: return launch_sweep<real, 3, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
-    case 4: return launch_sweep<real, 4, ADJ>(psi, lam, params, grads, plan, s, n, batch, index_hi, dir, st);
+    case 1: return launch_sweep<real, 1, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
+    case 2: return launch_sweep<real, 2, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
+    case 3: return launch_sweep<real, 3, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
+    case 4: return launch_sweep<real, 4, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
     default: return B200SV_E_ARG;
   }
+}
+
+// forward (ADJ = false) or adjoint (ADJ = true) execution of sweeps [first, last)
+template <typename real, bool ADJ>
+int run_plan(void* psi, void* lam, int n, int64_t batch, const double* params, double* grads,
+             const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* workspace, cudaStream_t st) {
+  if (first >= last) return 0;
+  const Workspace<real> ws = carve_workspace<real>(workspace, plan, batch);
+  const int x_first = plan->sweeps_host[first].first_exec;
+  const int x_last = plan->sweeps_host[last - 1].first_exec + plan->sweeps_host[last - 1].n_exec;
+  const int x_count = x_last - x_first;
+  const long long nthreads = (long long)x_count * batch;
+  const unsigned rgrid = (unsigned)((nthreads + 127) / 128);
+  if (x_count > 0) {
+    resolve_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab, x_first,
+                                                x_count, (long long)batch, ADJ ? -1 : +1, ADJ ? 1 : 0);
+    LAUNCH_CK();
+    if (ADJ) CK(cudaMemsetAsync(ws.mom + (size_t)x_first * batch * 4, 0, (size_t)x_count * batch * 4 * sizeof(double), st));
+  }
+  if (!ADJ) {
+    for (int s = first; s < last; ++s)
+      if (int rc = launch_sweep_r<real, false>(psi, nullptr, params, nullptr, plan, ws, s, n, batch, index_hi, +1, st)) return rc;
+  } else {
+    for (int s = last - 1; s >= first; --s)
+      if (int rc = launch_sweep_r<real, true>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, -1, st)) return rc;
+    if (x_count > 0) {
+      gradient_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab, ws.mom,
+                                                   grads, x_first, x_count, (long long)batch);
+      LAUNCH_CK();
+    }
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -464,33 +538,31 @@ int b200sv_init_zero_state(void* state, int dtype, int n, int64_t batch, void* s
   return 0;
 }
 
+int64_t b200sv_plan_workspace_bytes(const b200sv_plan* plan, int dtype, int64_t batch, int adjoint) {
+  if (!plan || batch <= 0) return B200SV_E_ARG;
+  if (dtype == B200SV_C128) return (int64_t)workspace_bytes<double>(plan, batch, adjoint != 0);
+  if (dtype == B200SV_C64) return (int64_t)workspace_bytes<float>(plan, batch, adjoint != 0);
+  return B200SV_E_ARG;
+}
+
 int b200sv_apply_plan(void* state, int dtype, int n, int64_t batch, const double* params,
-                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* stream) {
-  if (!state || !plan || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
+                      const b200sv_plan* plan, int first, int last, uint64_t index_hi, void* workspace,
+                      void* stream) {
+  if (!state || !plan || !workspace || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int s = first; s < last; ++s) {
-    int rc;
-    if (dtype == B200SV_C128) rc = launch_sweep_r<double, false>(state, nullptr, params, nullptr, plan, s, n, batch, index_hi, +1, st);
-    else if (dtype == B200SV_C64) rc = launch_sweep_r<float, false>(state, nullptr, params, nullptr, plan, s, n, batch, index_hi, +1, st);
-    else return B200SV_E_ARG;
-    if (rc) return rc;
-  }
-  return 0;
+  if (dtype == B200SV_C128) return run_plan<double, false>(state, nullptr, n, batch, params, nullptr, plan, first, last, index_hi, workspace, st);
+  if (dtype == B200SV_C64) return run_plan<float, false>(state, nullptr, n, batch, params, nullptr, plan, first, last, index_hi, workspace, st);
+  return B200SV_E_ARG;
 }
 
 int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n, int64_t batch, const double* params,
                         double* grads, const b200sv_plan* plan, int first, int last, uint64_t index_hi,
-                        void* stream) {
-  if (!psi || !lam || !plan || !grads || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
+                        void* workspace, void* stream) {
+  if (!psi || !lam || !plan || !grads || !workspace || first < 0 || last > plan->n_sweeps || batch <= 0) return B200SV_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int s = last - 1; s >= first; --s) {
-    int rc;
-    if (dtype == B200SV_C128) rc = launch_sweep_r<double, true>(psi, lam, params, grads, plan, s, n, batch, index_hi, -1, st);
-    else if (dtype == B200SV_C64) rc = launch_sweep_r<float, true>(psi, lam, params, grads, plan, s, n, batch, index_hi, -1, st);
-    else return B200SV_E_ARG;
-    if (rc) return rc;
-  }
-  return 0;
+  if (dtype == B200SV_C128) return run_plan<double, true>(psi, lam, n, batch, params, grads, plan, first, last, index_hi, workspace, st);
+  if (dtype == B200SV_C64) return run_plan<float, true>(psi, lam, n, batch, params, grads, plan, first, last, index_hi, workspace, st);
+  return B200SV_E_ARG;
 }
 
 static int check_terms(int n_terms) { return (n_terms < 0 || n_terms > MAX_TERMS_SMEM) ? B200SV_E_UNSUPPORTED : 0; }

@@ -376,13 +376,27 @@ template <typename real, int R, bool ADJ> struct SweepCfg {
   static constexpr int MINB = (ADJ && sizeof(real) == 8) ? B200SV_MINB_ADJ_D : ((sizeof(real) == 8 && R >= 3) ? B200SV_MINB_FWD_D : (ADJ ? 2 : 3));
 };
 
+// 16-byte (complex128) / 8-byte (complex64) asynchronous global -> shared copies (LDGSTS)
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const void* gmem);
+template <> __device__ __forceinline__ void cp_async<16>(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+template <> __device__ __forceinline__ void cp_async<8>(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// Persistent kernel: each CTA owns a contiguous range of tiles and double-buffers them — the
+// cp.async loads of tile k+1 are in flight while tile k is processed.
 template <typename real, int R, bool ADJ>
 __global__ void __launch_bounds__(SweepCfg<real, R, ADJ>::MAXT, SweepCfg<real, R, ADJ>::MINB)
 sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::type* __restrict__ lam_g,
              const double* __restrict__ params, double* __restrict__ grads,
              const b200sv_sweep* __restrict__ sweeps, const b200sv_round* __restrict__ rounds,
-             const b200sv_gate* __restrict__ gates, const double* __restrict__ consts, int sweep_idx,
-             int n, long long batch, unsigned long long index_hi, int dir) {
+             const b200sv_gate* __restrict__ gates, const double* __restrict__ consts,
+             const ExecGate<real>* __restrict__ xtab, double* __restrict__ mom_g, int sweep_idx,
+             int n, long long batch, unsigned long long index_hi, int dir, long long tiles_per_cta, int nbuf) {
   using c2 = typename C2<real>::type;
   using RG = Regs<real, R>;
   constexpr int NV = 1 << R;
@@ -393,29 +407,30 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   const int tile = 1 << m;
   const int nt = blockDim.x;  // == 2^(m-R)
   const int tid = threadIdx.x;
-  const int n_gates = sw.n_gates;
   const int n_exec = sw.n_exec;
+  const int n_rounds = sw.n_rounds;
+  constexpr int NSTATE = ADJ ? 2 : 1;
 
-  c2* tile_psi = reinterpret_cast<c2*>(smem_raw);
-  c2* tile_lam = tile_psi + (ADJ ? tile : 0);
-  unsigned long long* t_lo = reinterpret_cast<unsigned long long*>(tile_lam + tile);
+  // shared memory: 2 buffers x (psi [, lambda]) tiles | offset tables | resolved gates | moments | round tables
+  c2* bufs = reinterpret_cast<c2*>(smem_raw);
+  unsigned long long* t_lo = reinterpret_cast<unsigned long long*>(bufs + nbuf * NSTATE * tile);
   unsigned long long* t_hi = t_lo + 64;
   ExecGate<real>* eg = reinterpret_cast<ExecGate<real>*>(t_hi + 64);
   double* gsum = reinterpret_cast<double*>(eg + n_exec);  // ADJ: [n_exec][nwarps][4] moment partials
   const int nwarps = (nt + 31) >> 5;
   // per-round index tables (RT_STRIDE words each): [0,16) low thread nibble, [16,32) high nibble,
-  // [32,32+R) register bits; each word = swz(plain tile index part) | swz(permuted part) << 16
+  // [32,32+R) register bits, [36] per-tile external-control constant; each word =
+  // swz(plain tile index part) | swz(permuted part) << 16
   unsigned* rtab = reinterpret_cast<unsigned*>(gsum + (ADJ ? 4 * n_exec * nwarps : 0));
 
   const long long tiles_per_state = 1ll << sw.n_outer;
-  const long long b = blockIdx.x / tiles_per_state;
-  const unsigned long long c = blockIdx.x % tiles_per_state;
-  unsigned long long cta_base = 0;
-  for (int k = 0; k < sw.n_outer; ++k) cta_base |= ((c >> k) & 1ull) << sw.outer_bits[k];
+  const long long total_tiles = batch << sw.n_outer;
+  const long long tile_first = (long long)blockIdx.x * tiles_per_cta;
+  long long tile_end = tile_first + tiles_per_cta;
+  if (tile_end > total_tiles) tile_end = total_tiles;
 
-  // ---- prologue 1: offset tables (global offsets of tile indices, per-round index tables) ----
+  // ---- one-time prologue: offset tables (global offsets of tile indices, per-round index tables) ----
   const int nthr_bits = m - R;
-  const unsigned long long cta_index = cta_base | index_hi;
   for (int v = tid; v < 64; v += nt) {
     unsigned long long lo = 0, hi = 0;
     for (int i = 0; i < 6; ++i) {
@@ -424,7 +439,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     }
     t_lo[v] = lo; t_hi[v] = hi;
   }
-  for (int w = tid; w < sw.n_rounds * RT_STRIDE; w += nt) {
+  for (int w = tid; w < n_rounds * RT_STRIDE; w += nt) {
     const int rloc = w / RT_STRIDE, i = w % RT_STRIDE;
     const b200sv_round& rd = rounds[sw.first_round + rloc];
     const bool perm = (rd.flags & B200SV_RF_PERM) != 0;
@@ -439,11 +454,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
           permd ^= perm ? (unsigned)rd.pcol[pos] : (1u << pos);
         }
       }
-      if (half == 0 && perm) {
-        permd ^= rd.pconst;
-        for (int k = 0; k < (int)rd.n_pext; ++k)
-          if ((cta_index >> rd.pext[k].bit) & 1ull) permd ^= rd.pext[k].vec;
-      }
+      if (half == 0 && perm) permd ^= rd.pconst;
     } else if (i - 32 < R) {
       const int pos = rd.regpos[i - 32];
       plain = 1u << pos;
@@ -451,37 +462,79 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     }
     rtab[w] = (unsigned)swz<real>((int)plain) | ((unsigned)swz<real>((int)permd) << 16);
   }
+  if (ADJ) for (int g = tid; g < 4 * n_exec * nwarps; g += nt) gsum[g] = 0.0;
   __syncthreads();
 
-  // ---- prologue 2: issue the tile loads, resolve the gates while they are in flight ----
-  const long long state_off = b << n;
-  {
-    c2 buf[NV];
-    c2 buf2[ADJ ? NV : 1];
+  auto tile_base = [&](long long t) -> unsigned long long {  // CTA-index bits of tile t deposited into the basis index
+    const unsigned long long c = (unsigned long long)(t % tiles_per_state);
+    unsigned long long base = 0;
+    if (sw.n_seg >= 0) {  // runs of consecutive outer bits: a few shifts instead of a bit loop
+      for (int k = 0; k < sw.n_seg; ++k)
+        base |= ((c >> sw.seg[k].src) & ((1ull << sw.seg[k].len) - 1ull)) << sw.seg[k].dst;
+    } else {
+      for (int k = 0; k < sw.n_outer; ++k) base |= ((c >> k) & 1ull) << sw.outer_bits[k];
+    }
+    return base;
+  };
+  auto issue_loads = [&](long long t, unsigned long long base, int which) {  // asynchronous coalesced global -> swizzled shared
+    const long long off = ((t / tiles_per_state) << n) + (long long)base;
+    c2* dst = bufs + which * NSTATE * tile;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = i * nt + tid;
-      buf[i] = psi_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])];
+      const long long g = off + (long long)(t_lo[e & 63] + t_hi[e >> 6]);
+      cp_async<sizeof(c2)>(dst + swz<real>(e), psi_g + g);
+      if constexpr (ADJ) cp_async<sizeof(c2)>(dst + tile + swz<real>(e), lam_g + g);
     }
-    if constexpr (ADJ) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int e = i * nt + tid;
-        buf2[i] = lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])];
+    cp_async_commit();
+  };
+  auto flush_moments = [&](long long bb) {  // ADJ: this CTA's partial moments of batch element bb -> global
+    for (int x = tid; x < n_exec; x += nt) {
+      if (eg[x].gr == GR_NONE) continue;
+      double* dst = mom_g + ((long long)(sw.first_exec + x) * batch + bb) * 4;
+      const int nq = eg[x].gr == GR_SCALE ? 1 : 4;
+      for (int q = 0; q < 4; ++q) {
+        double acc = 0.0;
+        for (int w = 0; w < nwarps; ++w) { acc += gsum[(x * nwarps + w) * 4 + q]; gsum[(x * nwarps + w) * 4 + q] = 0.0; }
+        if (q < nq) atomicAdd(dst + q, acc);
       }
     }
-    for (int g = tid; g < n_gates; g += nt) {
-      const b200sv_gate* rec = gates + sw.first_gate + g;
-      if (rec->chain >= 1) resolve_gate<real>(rec, eg[rec->xidx], params, consts, batch, b, dir, ADJ);
+  };
+
+  long long cur_b = -1;
+  unsigned long long next_base = 0;
+  if (tile_first < tile_end) { next_base = tile_base(tile_first); issue_loads(tile_first, next_base, 0); }
+  for (long long t = tile_first; t < tile_end; ++t) {
+  const int which = (int)((t - tile_first) & (nbuf - 1));
+  const long long b = t / tiles_per_state;
+  const unsigned long long cta_base = next_base;
+  const unsigned long long cta_index = cta_base | index_hi;
+  c2* tile_psi = bufs + which * NSTATE * tile;
+  c2* tile_lam = tile_psi + (ADJ ? tile : 0);
+  if (t + 1 < tile_end && nbuf == 2) { next_base = tile_base(t + 1); issue_loads(t + 1, next_base, which ^ 1); cp_async_wait<1>(); }
+  else if (t > tile_first && nbuf == 1) { issue_loads(t, cta_base, 0); cp_async_wait<0>(); }
+  else cp_async_wait<0>();
+  if (nbuf == 1 && t + 1 < tile_end) next_base = tile_base(t + 1);
+  if (b != cur_b) {  // new batch element: its resolved gates (one coalesced copy from the plan-wide table)
+    if (ADJ && cur_b >= 0) { flush_moments(cur_b); __syncthreads(); }  // eg[].gr is read by the flush
+    constexpr int W = sizeof(ExecGate<real>) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(xtab);
+    uint4* dst = reinterpret_cast<uint4*>(eg);
+    for (int w = tid; w < n_exec * W; w += nt) {
+      const int x = w / W, k = w % W;
+      dst[w] = src[((long long)(sw.first_exec + x) * batch + b) * W + k];
     }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) tile_psi[swz<real>(i * nt + tid)] = buf[i];
-    if constexpr (ADJ) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) tile_lam[swz<real>(i * nt + tid)] = buf2[i];
-    }
+    cur_b = b;
   }
-  __syncthreads();
+  if (tid < n_rounds) {  // per-tile constant of the permutation phase: external (outer / rank bit) controls
+    const b200sv_round& rd = rounds[sw.first_round + tid];
+    unsigned ext = 0;
+    for (int k = 0; k < (int)rd.n_pext; ++k)
+      if ((cta_index >> rd.pext[k].bit) & 1ull) ext ^= rd.pext[k].vec;
+    rtab[tid * RT_STRIDE + 36] = (unsigned)swz<real>((int)ext) << 16;
+  }
+  __syncthreads();  // tile `which` has landed; eg / rtab[36] visible
+  const long long state_off = b << n;
 
   // ---- rounds ----
   for (int rr = 0; rr < sw.n_rounds; ++rr) {
@@ -494,7 +547,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     const int ms[4] = {(int)rw2.x, (int)rw2.y, (int)rw2.z, (int)rw2.w};
     const bool has_perm = (rounds[ridx].flags & B200SV_RF_PERM) != 0;
     const unsigned* T = rtab + rloc * RT_STRIDE;
-    const unsigned u = T[tid & 15] ^ T[16 + (tid >> 4)];
+    const unsigned u = T[tid & 15] ^ T[16 + (tid >> 4)] ^ T[36];
     const int st = (int)(u & 0xffffu), sp = (int)(u >> 16);  // swizzled plain / permuted base index
     int ro[R], rp[R];
 #pragma unroll
@@ -558,6 +611,20 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
       // plain stores, no atomics (nt < 32: a single partial warp, lanes reduce through full-mask shuffles
       // of the active lanes only)
       auto reduce_moments = [&](double (&mo)[4], int nmo, int x) {
+        if (nt >= 32 && nmo == 4) {
+          // transposed butterfly: 6 double shuffles for 4 values instead of 20; totals land in lanes 0, 8, 16, 24
+          const int lane = tid & 31;
+          const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+          const double r0 = __shfl_xor_sync(0xffffffffu, h16 ? mo[0] : mo[2], 16);
+          const double r1 = __shfl_xor_sync(0xffffffffu, h16 ? mo[1] : mo[3], 16);
+          const double a0 = (h16 ? mo[2] : mo[0]) + r0, a1 = (h16 ? mo[3] : mo[1]) + r1;
+          double v = (h8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, h8 ? a0 : a1, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          if ((lane & 7) == 0) gsum[(x * nwarps + (tid >> 5)) * 4 + (lane >> 3)] += v;
+          return;
+        }
         const unsigned mask = nt >= 32 ? 0xffffffffu : ((1u << nt) - 1u);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -569,7 +636,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
           }
         }
         if ((tid & 31) == 0)
-          for (int q = 0; q < nmo; ++q) gsum[(x * nwarps + (tid >> 5)) * 4 + q] = mo[q];
+          for (int q = 0; q < nmo; ++q) gsum[(x * nwarps + (tid >> 5)) * 4 + q] += mo[q];
       };
       // ---- G phase, reversed ----
       for (int gi = n_ex - 1; gi >= 0; --gi) {
@@ -641,26 +708,53 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
         const int e = i * nt + tid;
         lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])] = tile_lam[swz<real>(e)];
       }
-      for (int g = tid; g < n_gates; g += nt) {
-        const b200sv_gate* rec = gates + sw.first_gate + g;
-        if (rec->chain < 1) continue;
-        const ExecGate<real>& e = eg[rec->xidx];
-        if (e.gr == GR_NONE) continue;
-        double mom[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int w = 0; w < nwarps; ++w)
-          for (int q = 0; q < 4; ++q) mom[q] += gsum[(rec->xidx * nwarps + w) * 4 + q];
-        if (e.gr == GR_CHAIN) chain_gradients(rec, mom, params, consts, grads, batch, b);
-        else if (e.gr == GR_SCALE && rec->grad_row >= 0)
-          atomicAdd(&grads[(long long)rec->grad_row * batch + b], mom[0]);
-      }
     }
   }
+  __syncthreads();  // buffer `which` is free again before the next iteration's prefetch overwrites it
+  }  // tile loop
+  if (ADJ && cur_b >= 0) flush_moments(cur_b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve kernel: one thread per (resolved entry, batch element) evaluates sincos of the parametric
+// angles and multiplies the chain into one 2x2 — once per launch instead of once per CTA
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void resolve_kernel(const b200sv_gate* __restrict__ gates, const int* __restrict__ exec_leader,
+                               const double* __restrict__ params, const double* __restrict__ consts,
+                               ExecGate<real>* __restrict__ xtab, int x_first, int x_count, long long batch,
+                               int dir, int adj) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)x_count * batch) return;
+  const int x = x_first + (int)(t / batch);
+  const long long b = t % batch;
+  ExecGate<real> e;
+  resolve_gate<real>(gates + exec_leader[x], e, params, consts, batch, b, dir, adj != 0);
+  xtab[(long long)x * batch + b] = e;
+}
+
+// gradient kernel: moments of every chain -> gradient of every parametric gate of the chain
+template <typename real>
+__global__ void gradient_kernel(const b200sv_gate* __restrict__ gates, const int* __restrict__ exec_leader,
+                                const double* __restrict__ params, const double* __restrict__ consts,
+                                const ExecGate<real>* __restrict__ xtab, const double* __restrict__ mom_g,
+                                double* __restrict__ grads, int x_first, int x_count, long long batch) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)x_count * batch) return;
+  const int x = x_first + (int)(t / batch);
+  const long long b = t % batch;
+  const int gr = xtab[(long long)x * batch + b].gr;
+  if (gr == GR_NONE) return;
+  const b200sv_gate* rec = gates + exec_leader[x];
+  const double* mom = mom_g + ((long long)x * batch + b) * 4;
+  if (gr == GR_CHAIN) chain_gradients(rec, mom, params, consts, grads, batch, b);
+  else if (rec->grad_row >= 0) atomicAdd(&grads[(long long)rec->grad_row * batch + b], mom[0]);
 }
 
 template <typename real, bool ADJ>
-inline size_t sweep_smem_bytes(int m, int n_exec, int n_rounds) {
+inline size_t sweep_smem_bytes(int m, int n_exec, int n_rounds, int nbuf) {
   size_t tile = (size_t)1 << m;
-  size_t s = tile * 2 * sizeof(real) * (ADJ ? 2 : 1);
+  size_t s = (size_t)nbuf * tile * 2 * sizeof(real) * (ADJ ? 2 : 1);  // nbuf = 2: double-buffered persistent CTAs
   s += 128 * sizeof(unsigned long long);
   s += (size_t)n_exec * sizeof(ExecGate<real>);
   s += (size_t)n_exec * 4 * sizeof(double) * 8;  // up to 8 warps per CTA

@@ -314,7 +314,7 @@ class QubitShardedSimulator:
                 continue
             dp = self._device_plan(i, dtype)
             rc = lib.b200sv_apply_plan(st.data_ptr(), engine._DT[dtype], self.n_local, 1, ptable.data_ptr(), C.byref(dp.struct), 0,
-                                       dp.n_sweeps, self.index_hi, engine._stream_ptr(self.device))
+                                       dp.n_sweeps, self.index_hi, dp.workspace(dtype, 1, False).data_ptr(), engine._stream_ptr(self.device))
             cabi.check(rc, "apply_plan (sharded)")
         return st
 

@@ -59,6 +59,7 @@ class DevicePlan:
         self._rounds = up(plan.rounds)
         self._gates = up(plan.gates)
         self._consts = up(plan.consts)
+        self._leaders = up(plan.exec_leader)
         self.struct = cabi.PlanStruct(
             self._sweeps.data_ptr(),
             self._rounds.data_ptr(),
@@ -66,8 +67,20 @@ class DevicePlan:
             self._consts.data_ptr(),
             self._host_sweeps.ctypes.data,
             plan.n_sweeps,
-            0,
+            plan.n_exec_total,
+            self._leaders.data_ptr(),
         )
+        self._workspaces: dict = {}
+
+    def workspace(self, dtype: torch.dtype, batch: int, adjoint: bool) -> Tensor:
+        """Device scratch for the resolved-gate table (+ adjoint moments); cached per (dtype, batch, mode)."""
+        key = (dtype, batch, adjoint)
+        if key not in self._workspaces:
+            nbytes = cabi.load().b200sv_plan_workspace_bytes(C.byref(self.struct), _DT[dtype], batch, int(adjoint))
+            if nbytes < 0:
+                cabi.check(int(nbytes), "plan_workspace_bytes")
+            self._workspaces = {key: torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)}
+        return self._workspaces[key]
 
     @property
     def n_sweeps(self) -> int:
@@ -340,7 +353,8 @@ def _run_segments(cp: CompiledProgram, state: Tensor, ptable: Tensor, values: Ma
     for seg in cp.segments:
         if seg.gates is not None:
             dp = cp.device_plan(seg, state.dtype, False, dev)
-            rc = lib.b200sv_apply_plan(state.data_ptr(), _DT[state.dtype], cp.n_qubits, B, ptable.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, index_hi, _stream_ptr(dev))
+            rc = lib.b200sv_apply_plan(state.data_ptr(), _DT[state.dtype], cp.n_qubits, B, ptable.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps,
+                                       index_hi, dp.workspace(state.dtype, B, False).data_ptr(), _stream_ptr(dev))
             cabi.check(rc, "apply_plan")
             continue
         op = seg.op
@@ -462,7 +476,8 @@ class _AdjointExpectation(torch.autograd.Function):
             if seg.gates is not None:
                 dp = cp.device_plan(seg, psi.dtype, True, dev)
                 rc = lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[psi.dtype], cp.n_qubits, B, ptable.data_ptr(),
-                                             grads.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, 0, _stream_ptr(dev))
+                                             grads.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, 0,
+                                             dp.workspace(psi.dtype, B, True).data_ptr(), _stream_ptr(dev))
                 cabi.check(rc, "adjoint_plan")
                 continue
             op = seg.op

@@ -44,10 +44,11 @@ SWEEP_DT = np.dtype(
     [
         ("m", "<i4"), ("r", "<i4"), ("first_round", "<i4"), ("n_rounds", "<i4"), ("first_gate", "<i4"),
         ("n_gates", "<i4"), ("n_outer", "<i4"), ("n_exec", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
+        ("first_exec", "<i4"), ("n_seg", "<i4"), ("seg", np.dtype([("src", "u1"), ("len", "u1"), ("dst", "u1"), ("pad", "u1")]), (6,)),
     ]
 )
 PTERM_DT = np.dtype([("xmask", "<u8"), ("zmask", "<u8"), ("coef_row", "<i4"), ("n_y", "<i4"), ("pad", "<i4", (2,))])
-assert GATE_DT.itemsize == 56 and ROUND_DT.itemsize == 96 and SWEEP_DT.itemsize == 96 and PTERM_DT.itemsize == 32
+assert GATE_DT.itemsize == 56 and ROUND_DT.itemsize == 96 and SWEEP_DT.itemsize == 128 and PTERM_DT.itemsize == 32
 
 GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
 GF_GRAD = 1
@@ -363,12 +364,17 @@ class SweepPlan:
     gates: np.ndarray
     consts: np.ndarray  # [n_const, 2] float64
     n_source_gates: int
+    exec_leader: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))  # gate-record index per resolved entry
     # diagnostics: for each sweep, list of rounds, each a list of source-op indices (execution order)
     order: list[list[list[int]]] = field(default_factory=list)
 
     @property
     def n_sweeps(self) -> int:
         return int(self.sweeps.shape[0])
+
+    @property
+    def n_exec_total(self) -> int:
+        return int(self.exec_leader.shape[0])
 
     def execution_order(self) -> list[int]:
         return [i for sw in self.order for rd in sw for i in rd]
@@ -398,6 +404,7 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
     order: list[list[list[int]]] = []
     n_gates_total = 0
     n_rounds_total = 0
+    n_exec_plan = 0
     for si, (sgates, bits) in enumerate(sweep_groups):
         # complete the tile with the lowest unused bit positions
         tile = sorted(bits)
@@ -415,6 +422,19 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         sw["first_round"], sw["first_gate"] = n_rounds_total, n_gates_total
         sw["tile_bits"][:m] = tile
         sw["outer_bits"][: len(outer)] = outer
+        # runs of consecutive outer bit positions -> (src bit of the CTA index, length, dst bit)
+        segs: list[list[int]] = []
+        for k, p in enumerate(outer):
+            if segs and segs[-1][2] + segs[-1][1] == p:
+                segs[-1][1] += 1
+            else:
+                segs.append([k, 1, p])
+        if len(segs) <= 6:
+            sw["n_seg"] = len(segs)
+            for k, (src, ln, dst) in enumerate(segs):
+                sw["seg"][k]["src"], sw["seg"][k]["len"], sw["seg"][k]["dst"] = src, ln, dst
+        else:
+            sw["n_seg"] = -1
         round_list = _pack_rounds(sgates, r, set(tile), chains)
         sw_order: list[list[int]] = []
         n_exec_sweep = 0
@@ -499,10 +519,18 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         sw["n_rounds"] = len(round_list)
         sw["n_gates"] = n_gates_total - int(sw["first_gate"])
         sw["n_exec"] = n_exec_sweep
+        sw["first_exec"] = n_exec_plan
+        n_exec_plan += n_exec_sweep
         order.append(sw_order)
     rounds = np.concatenate(rounds_l) if rounds_l else np.zeros(0, dtype=ROUND_DT)
     gates = np.concatenate(gates_l) if gates_l else np.zeros(0, dtype=GATE_DT)
-    return SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), order)
+    leaders = np.zeros(n_exec_plan, dtype=np.int32)
+    for si in range(len(sweeps)):
+        fg, ng, fx = int(sweeps[si]["first_gate"]), int(sweeps[si]["n_gates"]), int(sweeps[si]["first_exec"])
+        for gi in range(fg, fg + ng):
+            if gates[gi]["chain"] >= 1:
+                leaders[fx + int(gates[gi]["xidx"])] = gi
+    return SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), leaders, order)
 
 
 # ---- Pauli sums -----------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ def lib() -> C.CDLL:
 
 def test_every_declared_symbol_is_exported(lib: C.CDLL) -> None:
     header = (ROOT / "include" / "b200sv.h").read_text()
-    declared = set(re.findall(r"^int (b200sv_\w+)\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t) (b200sv_\w+)\(", header, flags=re.M))
     assert len(declared) >= 16
     assert declared == set(cabi.EXPORTS)
     for name in declared:
@@ -39,7 +39,7 @@ def test_record_layouts_match_header() -> None:
     for struct, dt in (("b200sv_gate", plan.GATE_DT), ("b200sv_round", plan.ROUND_DT), ("b200sv_sweep", plan.SWEEP_DT), ("b200sv_pterm", plan.PTERM_DT)):
         m = re.search(r"typedef struct %s \{\s*/\* (\d+) bytes" % struct, header)
         assert m and int(m.group(1)) == dt.itemsize, struct
-    assert C.sizeof(cabi.PlanStruct) == 48
+    assert C.sizeof(cabi.PlanStruct) == 56
 
 
 def test_fails_loudly_without_a_device(lib: C.CDLL) -> None:

@@ -67,7 +67,7 @@ def test_tile_geometries(cfg: TileConfig) -> None:
     dp = DevicePlan(build_plan(prog.ops, n, slot_of, cfg), dev)
     tab = engine.pack_params(prog.param_names, values, B, dev)
     st = psi0.to(dev).clone()
-    rc = cabi.load().b200sv_apply_plan(st.data_ptr(), _DT[st.dtype], n, B, tab.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, 0, _stream_ptr(dev))
+    rc = cabi.load().b200sv_apply_plan(st.data_ptr(), _DT[st.dtype], n, B, tab.data_ptr(), C.byref(dp.struct), 0, dp.n_sweeps, 0, dp.workspace(st.dtype, B, False).data_ptr(), _stream_ptr(dev))
     assert rc == 0
     assert (st.cpu() - want).abs().max().item() <= 1e-10 * max(1.0, want.abs().max().item())
 

@@ -120,7 +120,8 @@ typedef struct b200sv_sweep {  /* 128 bytes: one kernel launch = one read + one 
   uint8_t tile_bits[16];  /* global bit position of tile-local bit i (ascending)                   */
   uint8_t outer_bits[48]; /* global bit positions enumerated by the CTA index (ascending)          */
   int32_t first_exec;   /* offset of this sweep's resolved entries in the plan-wide tables          */
-  int32_t n_seg;        /* CTA index -> base index: sum_s ((c >> src) & (2^len - 1)) << dst         */
+  int16_t n_seg;        /* CTA index -> base index: sum_s ((c >> src) & (2^len - 1)) << dst; -1: bit loop */
+  int16_t n_gen;        /* generic-phase entries in this sweep (0: the lean kernel variant is launched) */
   struct { uint8_t src, len, dst, pad; } seg[6];
 } b200sv_sweep;
 

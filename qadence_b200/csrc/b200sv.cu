@@ -53,7 +53,7 @@ size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool adjoint) {
   return bytes + 256;
 }
 
-template <typename real, int R, bool ADJ>
+template <typename real, int R, bool ADJ, bool GEN>
 int launch_sweep(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
                  const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   using c2 = typename C2<real>::type;
@@ -61,7 +61,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
   const int nbuf = persistent ? 2 : 1;
   const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
-  auto kern = sweep_kernel<real, R, ADJ>;
+  auto kern = sweep_kernel<real, R, ADJ, GEN>;
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -95,13 +95,27 @@ int launch_sweep_r(void* psi, void* lam, const double* params, double* grads, co
                    const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
   const b200sv_sweep& sw = plan->sweeps_host[s];
   if (sw.m < sw.r || sw.m - sw.r > 8 || sw.m > 12 || sw.n_outer != n - sw.m) return B200SV_E_ARG;
+  bool gen = false;  // any generic-phase entry in this sweep?
+  int n_m = 0;
+  {
+    // resolved entries that are not matrix-phase slots belong to the generic phase; the planner stores the
+    // count of generic entries per round, their sum is n_exec minus the number of M slots — recomputed from
+    // the host copy of the sweep: n_gen is kept in `sw.n_gen`.
+    static const int force_gen = [] { const char* e = getenv("B200SV_FORCE_GEN"); return e ? atoi(e) : 0; }();
+    gen = sw.n_gen > 0 || force_gen;
+    (void)n_m;
+  }
+#define B200SV_LAUNCH(RR)                                                                                                   \
+  return gen ? launch_sweep<real, RR, ADJ, true>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st)           \
+             : launch_sweep<real, RR, ADJ, false>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st)
   switch (sw.r) {
-    case 1: return launch_sweep<real, 1, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
-    case 2: return launch_sweep<real, 2, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
-    case 3: return launch_sweep<real, 3, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
-    case 4: return launch_sweep<real, 4, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, dir, st);
+    case 1: B200SV_LAUNCH(1);
+    case 2: B200SV_LAUNCH(2);
+    case 3: B200SV_LAUNCH(3);
+    case 4: B200SV_LAUNCH(4);
     default: return B200SV_E_ARG;
   }
+#undef B200SV_LAUNCH
 }
 
 // forward (ADJ = false) or adjoint (ADJ = true) execution of sweeps [first, last)

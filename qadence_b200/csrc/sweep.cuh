@@ -365,7 +365,13 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 // the sweep kernel
 // ------------------------------------------------------------------------------------------------
 #ifndef B200SV_MINB_FWD_D
-#define B200SV_MINB_FWD_D 3  // complex128 forward, r >= 3: CTAs per SM the register allocation targets
+#define B200SV_MINB_FWD_D 4  // complex128 forward, r >= 3: CTAs per SM the register allocation targets
+#endif
+#ifndef B200SV_MINB_FWD_D_R2
+#define B200SV_MINB_FWD_D_R2 3
+#endif
+#ifndef B200SV_MINB_ADJ_D_R2
+#define B200SV_MINB_ADJ_D_R2 4
 #endif
 #ifndef B200SV_MINB_ADJ_D
 #define B200SV_MINB_ADJ_D 4  // complex128 adjoint (128-thread CTAs)
@@ -373,7 +379,8 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 // launch geometry per instantiation: (max threads per CTA, min CTAs per SM)
 template <typename real, int R, bool ADJ> struct SweepCfg {
   static constexpr int MAXT = (ADJ && sizeof(real) == 8) ? 128 : 256;
-  static constexpr int MINB = (ADJ && sizeof(real) == 8) ? B200SV_MINB_ADJ_D : ((sizeof(real) == 8 && R >= 3) ? B200SV_MINB_FWD_D : (ADJ ? 2 : 3));
+  static constexpr int MINB = (ADJ && sizeof(real) == 8) ? (R <= 2 ? B200SV_MINB_ADJ_D_R2 : B200SV_MINB_ADJ_D)
+                              : ((sizeof(real) == 8 && R >= 3) ? B200SV_MINB_FWD_D : ((sizeof(real) == 8 && R == 2) ? B200SV_MINB_FWD_D_R2 : (ADJ ? 2 : 3)));
 };
 
 // 16-byte (complex128) / 8-byte (complex64) asynchronous global -> shared copies (LDGSTS)
@@ -389,7 +396,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // Persistent kernel: each CTA owns a contiguous range of tiles and double-buffers them — the
 // cp.async loads of tile k+1 are in flight while tile k is processed.
-template <typename real, int R, bool ADJ>
+// GEN = false: the sweep has no generic-phase entries (pure merged-2x2 + permutation rounds, e.g.
+// every sweep of an HEA): the interpreter is compiled out, which shrinks registers and code.
+template <typename real, int R, bool ADJ, bool GEN>
 __global__ void __launch_bounds__(SweepCfg<real, R, ADJ>::MAXT, SweepCfg<real, R, ADJ>::MINB)
 sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::type* __restrict__ lam_g,
              const double* __restrict__ params, double* __restrict__ grads,
@@ -567,9 +576,11 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
       return o;
     };
     unsigned long long gthr = 0;
-    if (n_ex > 0) {  // index bits of this thread (controls / external diagonals of the generic phase)
-      const int tbase = swz<real>(st);  // swz is an involution
-      gthr = cta_base | t_lo[tbase & 63] | t_hi[tbase >> 6] | index_hi;
+    if constexpr (GEN) {
+      if (n_ex > 0) {  // index bits of this thread (controls / external diagonals of the generic phase)
+        const int tbase = swz<real>(st);  // swz is an involution
+        gthr = cta_base | t_lo[tbase & 63] | t_hi[tbase >> 6] | index_hi;
+      }
     }
 
     c2 p[NV];
@@ -600,9 +611,11 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
         }
       }
       // ---- G phase ----
-      for (int gi = 0; gi < n_ex; ++gi) {
-        const ExecGate<real>& e = eg[first_exec + gi];
-        if ((gthr & e.ctrl_ext) == e.ctrl_ext) RG::apply(p, e, gthr, false);
+      if constexpr (GEN) {
+        for (int gi = 0; gi < n_ex; ++gi) {
+          const ExecGate<real>& e = eg[first_exec + gi];
+          if ((gthr & e.ctrl_ext) == e.ctrl_ext) RG::apply(p, e, gthr, false);
+        }
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) tile_psi[pidx(j)] = p[j];
@@ -639,6 +652,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
           for (int q = 0; q < nmo; ++q) gsum[(x * nwarps + (tid >> 5)) * 4 + q] += mo[q];
       };
       // ---- G phase, reversed ----
+      if constexpr (GEN) {
       for (int gi = n_ex - 1; gi >= 0; --gi) {
         const int x = first_exec + gi;
         const ExecGate<real>& e = eg[x];
@@ -662,6 +676,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
         } else {
           if (active) RG::apply(p, e, gthr, false);
         }
+      }
       }
       // ---- M phase, reversed: moments of the post-chain states, then un-apply the merged 2x2 ----
 #pragma unroll

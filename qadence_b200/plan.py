@@ -44,7 +44,7 @@ SWEEP_DT = np.dtype(
     [
         ("m", "<i4"), ("r", "<i4"), ("first_round", "<i4"), ("n_rounds", "<i4"), ("first_gate", "<i4"),
         ("n_gates", "<i4"), ("n_outer", "<i4"), ("n_exec", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
-        ("first_exec", "<i4"), ("n_seg", "<i4"), ("seg", np.dtype([("src", "u1"), ("len", "u1"), ("dst", "u1"), ("pad", "u1")]), (6,)),
+        ("first_exec", "<i4"), ("n_seg", "<i2"), ("n_gen", "<i2"), ("seg", np.dtype([("src", "u1"), ("len", "u1"), ("dst", "u1"), ("pad", "u1")]), (6,)),
     ]
 )
 PTERM_DT = np.dtype([("xmask", "<u8"), ("zmask", "<u8"), ("coef_row", "<i4"), ("n_y", "<i4"), ("pad", "<i4", (2,))])
@@ -519,6 +519,7 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         sw["n_rounds"] = len(round_list)
         sw["n_gates"] = n_gates_total - int(sw["first_gate"])
         sw["n_exec"] = n_exec_sweep
+        sw["n_gen"] = sum(len(rnd.ggates) for rnd in round_list)
         sw["first_exec"] = n_exec_plan
         n_exec_plan += n_exec_sweep
         order.append(sw_order)

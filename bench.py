@@ -26,6 +26,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_QUBITS, DEPTH, BATCH = 20, 8, 256
+CPU_SAMPLE_BATCH = 4  # parameter sets per CPU step (≈ 10-20 s of host work)
+WORKLOAD = ("cfg2: hea(n_qubits=20, depth=8) expectation of total_magnetization + adjoint gradients of 480 parameters, "
+            "batch 256 per GPU, complex128")
 METRIC = "expectation+grad evals/s (HEA n=20 depth=8, batch 256, complex128, adjoint)"
 UNIT = "evals/s"
 
@@ -117,7 +120,7 @@ def run_reference(args) -> None:
     import torch
 
     threads = os.cpu_count() or 1
-    sample_batch = 1
+    sample_batch = CPU_SAMPLE_BATCH
     for _ in range(min(args.warmup, 1)):
         _cpu_eval(sample_batch, threads)
     ts = [_cpu_eval(sample_batch, threads)[0] for _ in range(args.steps)]
@@ -127,9 +130,9 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "hea(n=20,depth=8) <Z_tot> + adjoint grads, complex128; CPU step = batch 1 of 256 (per-eval throughput)"},
+        "config": {"workload": WORKLOAD, "reference_step": f"{sample_batch} of the 256 parameter sets per step on the host cores (per-eval throughput)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"batch {sample_batch} of 256 parameter sets per step, torch {torch.__version__} einsum-per-gate + adjoint loop (oracle/statevec.py)"},
+                         "sample": f"{sample_batch} of the 256 parameter sets per step, torch {torch.__version__} einsum-per-gate + adjoint loop (oracle/statevec.py; pyqtorch is not installable here)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -285,16 +288,16 @@ def main() -> None:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            dt, v = _cpu_eval(1, threads)
+            dt, v = _cpu_eval(CPU_SAMPLE_BATCH, threads)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"1 of the 256 parameter sets (one full expectation+adjoint eval, {dt:.1f} s), einsum-per-gate restatement of the pyqtorch path (oracle/statevec.py)"}
+                   "sample": f"{CPU_SAMPLE_BATCH} of the 256 parameter sets (one full expectation+adjoint eval of that sub-batch, {dt:.1f} s), einsum-per-gate restatement of the pyqtorch path (oracle/statevec.py)"}
         n_gates = len(prog.ops)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (complex128)", "data": "synthetic",
             "config": {
-                "workload": "cfg2: hea(n_qubits=20, depth=8) expectation of total_magnetization + adjoint gradients of 480 parameters, batch 256 per GPU, complex128",
+                "workload": WORKLOAD,
                 "l2": "inputs larger than L2 (state 4 GiB per GPU)", "gates": n_gates, "params": n_slots,
                 "fwd_sweeps": fwd.n_sweeps, "adj_sweeps": adj.n_sweeps,
                 "gates_per_s": world * n_gates * BATCH / (ms_per_step * 1e-3),
@@ -303,7 +306,7 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": n_slots * BATCH * 8, "d2h_bytes_per_step": BATCH * 8 + n_slots * BATCH * 8},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "sweep_kernel<double,3,ADJ> (adjoint sweep: psi+lambda read+write, gradients reduced)",
+            "roofline": {"bound": "hbm", "kernel": "sweep_kernel<double,3,true,false> (adjoint sweep: psi+lambda read+write, gradient moments reduced)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_per_launch": 4 * S, "avg_launch_ms": adj_avg,
                          "forward_sweep": {"achieved": fwd_achieved, "frac": fwd_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": fwd_avg}},

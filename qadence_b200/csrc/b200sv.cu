@@ -60,6 +60,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   const b200sv_sweep& sw = plan->sweeps_host[s];
   static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
   const int nbuf = persistent ? 2 : 1;
+  static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
   auto kern = sweep_kernel<real, R, ADJ, GEN>;
   static size_t configured = 0;  // per instantiation
@@ -85,7 +86,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   if (grid > 2147483647ll) return B200SV_E_ARG;
   kern<<<(unsigned)grid, nt, smem, st>>>((c2*)psi, (c2*)lam, params, grads, plan->sweeps, plan->rounds,
                                          plan->gates, plan->consts, ws.xtab, ws.mom, s, n, (long long)batch,
-                                         (unsigned long long)index_hi, dir, per_cta, nbuf);
+                                         (unsigned long long)index_hi, (dir < 0 ? 0x100 : 0) | dbg_flags, per_cta, nbuf);
   LAUNCH_CK();
   return 0;
 }

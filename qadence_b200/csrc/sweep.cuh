@@ -314,6 +314,8 @@ template <typename real, int R> struct Regs {
   // ---- adjoint: four moments Im<λ|P|ψ>, P = I, X, Y, Z, on the control-active subspace ----------
   template <int A>
   static __device__ __forceinline__ void moments_(const c2 (&p)[NV], const c2 (&l)[NV], int cr, double (&mo)[4]) {
+    // the kernel is issue-bound (an FP64 instruction occupies the issue port for two cycles): pure FMA
+    // chains, 12 per amplitude pair, no separate adds
     double s00 = 0, s11 = 0, x_im = 0, y_re = 0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -322,10 +324,12 @@ template <typename real, int R> struct Regs {
       const int k = j | (1 << A);
       const double p0x = p[j].x, p0y = p[j].y, p1x = p[k].x, p1y = p[k].y;
       const double l0x = l[j].x, l0y = l[j].y, l1x = l[k].x, l1y = l[k].y;
-      s00 += l0x * p0y - l0y * p0x;                                  // Im conj(l0) p0
-      s11 += l1x * p1y - l1y * p1x;                                  // Im conj(l1) p1
-      x_im += (l0x * p1y - l0y * p1x) + (l1x * p0y - l1y * p0x);     // Im<λ|X|ψ>
-      y_re += (l1x * p0x + l1y * p0y) - (l0x * p1x + l0y * p1y);     // Im<λ|Y|ψ>
+      s00 = fma(l0x, p0y, s00); s00 = fma(-l0y, p0x, s00);      // Im conj(l0) p0
+      s11 = fma(l1x, p1y, s11); s11 = fma(-l1y, p1x, s11);      // Im conj(l1) p1
+      x_im = fma(l0x, p1y, x_im); x_im = fma(-l0y, p1x, x_im);  // Im<λ|X|ψ> = Im(conj(l0) p1 + conj(l1) p0)
+      x_im = fma(l1x, p0y, x_im); x_im = fma(-l1y, p0x, x_im);
+      y_re = fma(l1x, p0x, y_re); y_re = fma(l1y, p0y, y_re);   // Im<λ|Y|ψ> = Re(conj(l1) p0 - conj(l0) p1)
+      y_re = fma(-l0x, p1x, y_re); y_re = fma(-l0y, p1y, y_re);
     }
     mo[0] = s00 + s11; mo[1] = x_im; mo[2] = y_re; mo[3] = s00 - s11;
   }
@@ -351,6 +355,37 @@ template <typename real, int R> struct Regs {
       default: break;
     }
   }
+  // ---- straight-line matrix phases, specialised on the set MASK of occupied register slots ----------
+  template <int MASK>
+  static __device__ __forceinline__ void mphase_fwd(c2 (&p)[NV], const ExecGate<real>* eg, const int* ms) {
+    if constexpr (MASK & 1) mat_<0, false>(p, eg[ms[0]].m, 0);
+    if constexpr (R > 1 && (MASK & 2)) mat_<1, false>(p, eg[ms[1]].m, 0);
+    if constexpr (R > 2 && (MASK & 4)) mat_<2, false>(p, eg[ms[2]].m, 0);
+    if constexpr (R > 3 && (MASK & 8)) mat_<3, false>(p, eg[ms[3]].m, 0);
+  }
+  template <int MASK, int A, bool WITH_L, typename RED>
+  static __device__ __forceinline__ void mslot_bwd(c2 (&p)[NV], c2 (&l)[WITH_L ? NV : 1], const ExecGate<real>* eg, const int* ms, RED& reduce) {
+    if constexpr (A < R && ((MASK >> A) & 1)) {
+      const ExecGate<real>& e = eg[ms[A]];
+      if constexpr (WITH_L) {
+        if (e.gr == GR_CHAIN) {  // uniform across the CTA
+          double mo[4];
+          moments_<A>(p, l, 0, mo);
+          reduce(mo, 4, ms[A]);
+        }
+      }
+      mat_<A, false>(p, e.m, 0);
+      if constexpr (WITH_L) mat_<A, false>(l, e.m, 0);
+    }
+  }
+  template <int MASK, bool WITH_L, typename RED>
+  static __device__ __forceinline__ void mphase_bwd(c2 (&p)[NV], c2 (&l)[WITH_L ? NV : 1], const ExecGate<real>* eg, const int* ms, RED& reduce) {
+    mslot_bwd<MASK, 3, WITH_L>(p, l, eg, ms, reduce);
+    mslot_bwd<MASK, 2, WITH_L>(p, l, eg, ms, reduce);
+    mslot_bwd<MASK, 1, WITH_L>(p, l, eg, ms, reduce);
+    mslot_bwd<MASK, 0, WITH_L>(p, l, eg, ms, reduce);
+  }
+
   static __device__ __forceinline__ double grad_scale(const c2 (&p)[NV], const c2 (&l)[NV]) {
     double acc = 0.0;  // 2 Re <λ|ψ_before>
 #pragma unroll
@@ -367,6 +402,9 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 #ifndef B200SV_MINB_FWD_D
 #define B200SV_MINB_FWD_D 4  // complex128 forward, r >= 3: CTAs per SM the register allocation targets
 #endif
+#ifndef B200SV_MINB_FWD_D_R4
+#define B200SV_MINB_FWD_D_R4 2
+#endif
 #ifndef B200SV_MINB_FWD_D_R2
 #define B200SV_MINB_FWD_D_R2 3
 #endif
@@ -378,9 +416,9 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 #endif
 // launch geometry per instantiation: (max threads per CTA, min CTAs per SM)
 template <typename real, int R, bool ADJ> struct SweepCfg {
-  static constexpr int MAXT = (ADJ && sizeof(real) == 8) ? 128 : 256;
+  static constexpr int MAXT = (ADJ && sizeof(real) == 8 && R >= 3) ? 128 : 256;
   static constexpr int MINB = (ADJ && sizeof(real) == 8) ? (R <= 2 ? B200SV_MINB_ADJ_D_R2 : B200SV_MINB_ADJ_D)
-                              : ((sizeof(real) == 8 && R >= 3) ? B200SV_MINB_FWD_D : ((sizeof(real) == 8 && R == 2) ? B200SV_MINB_FWD_D_R2 : (ADJ ? 2 : 3)));
+                              : ((sizeof(real) == 8 && R >= 4) ? B200SV_MINB_FWD_D_R4 : (sizeof(real) == 8 && R == 3) ? B200SV_MINB_FWD_D : ((sizeof(real) == 8 && R == 2) ? B200SV_MINB_FWD_D_R2 : (ADJ ? 2 : 3)));
 };
 
 // 16-byte (complex128) / 8-byte (complex64) asynchronous global -> shared copies (LDGSTS)
@@ -405,7 +443,9 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
              const b200sv_sweep* __restrict__ sweeps, const b200sv_round* __restrict__ rounds,
              const b200sv_gate* __restrict__ gates, const double* __restrict__ consts,
              const ExecGate<real>* __restrict__ xtab, double* __restrict__ mom_g, int sweep_idx,
-             int n, long long batch, unsigned long long index_hi, int dir, long long tiles_per_cta, int nbuf) {
+             int n, long long batch, unsigned long long index_hi, int dir_dbg, long long tiles_per_cta, int nbuf) {
+  constexpr int dir = ADJ ? -1 : +1;  // the adjoint kernel always walks backwards, the plain one forwards
+  const int dbg = dir_dbg & 0xff;  // timing experiments only (B200SV_DBG): 1 = skip math, 2 = skip rounds
   using c2 = typename C2<real>::type;
   using RG = Regs<real, R>;
   constexpr int NV = 1 << R;
@@ -546,7 +586,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   const long long state_off = b << n;
 
   // ---- rounds ----
-  for (int rr = 0; rr < sw.n_rounds; ++rr) {
+  for (int rr = 0; rr < ((dbg & 2) ? 0 : sw.n_rounds); ++rr) {
     const int rloc = dir > 0 ? rr : sw.n_rounds - 1 - rr;
     const int ridx = sw.first_round + rloc;
     const uint4* rq = reinterpret_cast<const uint4*>(rounds + ridx);
@@ -585,7 +625,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
 
     c2 p[NV];
     c2 l[ADJ ? NV : 1];
-    if (dir > 0) {
+    if constexpr (dir > 0) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) p[j] = tile_psi[sidx(j)];
     } else {
@@ -598,16 +638,25 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     }
     if (has_perm) __syncthreads();  // every register file is loaded before anyone stores at permuted addresses
 
-    if (dir > 0) {
-      // ---- M phase: one merged 2x2 per register bit, straight-line ----
+    if constexpr (dir > 0) {
+      // ---- M phase: one merged 2x2 per occupied register bit; straight-line code per slot mask ----
+      {
+        const int mask = (dbg & 1) ? 0 : (ms[0] >= 0 ? 1 : 0) | (ms[1] >= 0 ? 2 : 0) | (ms[2] >= 0 ? 4 : 0) | (ms[3] >= 0 ? 8 : 0);
+        // full rounds take the straight-line path; partial rounds a compact per-slot path (specialising
+        // every mask bloats the kernel past the instruction cache)
+        constexpr int FULL = (1 << R) - 1;
+        if (mask == FULL) RG::template mphase_fwd<FULL>(p, eg, ms);
+        else {
 #pragma unroll
-      for (int a = 0; a < R; ++a) {
-        if (ms[a] >= 0) {
-          const real* mm = eg[ms[a]].m;
-          if (a == 0) RG::template mat_<0, false>(p, mm, 0);
-          if constexpr (R > 1) { if (a == 1) RG::template mat_<1, false>(p, mm, 0); }
-          if constexpr (R > 2) { if (a == 2) RG::template mat_<2, false>(p, mm, 0); }
-          if constexpr (R > 3) { if (a == 3) RG::template mat_<3, false>(p, mm, 0); }
+          for (int a = 0; a < R; ++a) {
+            if (mask & (1 << a)) {
+              const real* mm = eg[ms[a]].m;
+              if (a == 0) RG::template mat_<0, false>(p, mm, 0);
+              if constexpr (R > 1) { if (a == 1) RG::template mat_<1, false>(p, mm, 0); }
+              if constexpr (R > 2) { if (a == 2) RG::template mat_<2, false>(p, mm, 0); }
+              if constexpr (R > 3) { if (a == 3) RG::template mat_<3, false>(p, mm, 0); }
+            }
+          }
         }
       }
       // ---- G phase ----
@@ -679,25 +728,15 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
       }
       }
       // ---- M phase, reversed: moments of the post-chain states, then un-apply the merged 2x2 ----
-#pragma unroll
-      for (int a = R - 1; a >= 0; --a) {
-        if (ms[a] >= 0) {
-          const ExecGate<real>& e = eg[ms[a]];
-          if constexpr (ADJ) {
-            if (e.gr == GR_CHAIN) {
-              double mo[4] = {0.0, 0.0, 0.0, 0.0};
-              if (a == 0) RG::template moments_<0>(p, l, 0, mo);
-              if constexpr (R > 1) { if (a == 1) RG::template moments_<1>(p, l, 0, mo); }
-              if constexpr (R > 2) { if (a == 2) RG::template moments_<2>(p, l, 0, mo); }
-              if constexpr (R > 3) { if (a == 3) RG::template moments_<3>(p, l, 0, mo); }
-              reduce_moments(mo, 4, ms[a]);
-            }
-          }
-          const real* mm = e.m;
-          if (a == 0) { RG::template mat_<0, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<0, false>(l, mm, 0); }
-          if constexpr (R > 1) { if (a == 1) { RG::template mat_<1, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<1, false>(l, mm, 0); } }
-          if constexpr (R > 2) { if (a == 2) { RG::template mat_<2, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<2, false>(l, mm, 0); } }
-          if constexpr (R > 3) { if (a == 3) { RG::template mat_<3, false>(p, mm, 0); if constexpr (ADJ) RG::template mat_<3, false>(l, mm, 0); } }
+      {
+        const int mask = (dbg & 1) ? 0 : (ms[0] >= 0 ? 1 : 0) | (ms[1] >= 0 ? 2 : 0) | (ms[2] >= 0 ? 4 : 0) | (ms[3] >= 0 ? 8 : 0);
+        constexpr int FULL = (1 << R) - 1;
+        if (mask == FULL) RG::template mphase_bwd<FULL, ADJ>(p, l, eg, ms, reduce_moments);
+        else {
+          if constexpr (R > 3) { if (mask & 8) RG::template mphase_bwd<8, ADJ>(p, l, eg, ms, reduce_moments); }
+          if constexpr (R > 2) { if (mask & 4) RG::template mphase_bwd<4, ADJ>(p, l, eg, ms, reduce_moments); }
+          if constexpr (R > 1) { if (mask & 2) RG::template mphase_bwd<2, ADJ>(p, l, eg, ms, reduce_moments); }
+          if (mask & 1) RG::template mphase_bwd<1, ADJ>(p, l, eg, ms, reduce_moments);
         }
       }
 #pragma unroll

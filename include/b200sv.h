@@ -217,6 +217,13 @@ int b200sv_scal(const double* a, void* x, int dtype, int n_qubits, int64_t batch
 int b200sv_lincomb(const double* c, const void* V, int K, void* out, int dtype, int n_qubits,
                    int64_t batch, void* stream);
 
+/* Krylov plumbing: y_b = exp(-i t_b T_b) e_1 for the batched real symmetric tridiagonal T_b built by
+ * Lanczos (diagonal alpha[j][b], off-diagonal beta[j][b], j < m <= 64), by scaled Taylor series on
+ * the device (no dense eigendecomposition, no host round trip), plus the a-posteriori error estimate
+ * err[b] = |beta[m-1][b]| * |y_b[m-1]|.  y is `double[m][batch][2]`. */
+int b200sv_tridiag_expm(const double* alpha, const double* beta, const double* t, int m, int64_t batch,
+                        double* y, double* err, void* stream);
+
 /* Constant dense 2^k x 2^k matrix (complex128, row-major, targets[0] = most significant operand
  * bit) applied out of place: out = (M ⊗ I) psi.  MatrixBlock / Projector(ket,bra)
  * (backends/pyqtorch/convert_ops.py:271-272, 287-294).  k <= 10. */

@@ -32,6 +32,7 @@ EXPORTS = [
     "b200sv_axpy",
     "b200sv_scal",
     "b200sv_lincomb",
+    "b200sv_tridiag_expm",
     "b200sv_apply_dense",
     "b200sv_sample",
     "b200sv_bit_reverse",
@@ -92,6 +93,7 @@ def load() -> C.CDLL:
         "b200sv_axpy": [vp, vp, vp, i32, i32, i64, vp],
         "b200sv_scal": [vp, vp, i32, i32, i64, vp],
         "b200sv_lincomb": [vp, vp, i32, vp, i32, i32, i64, vp],
+        "b200sv_tridiag_expm": [vp, vp, vp, i32, i64, vp, vp, vp],
         "b200sv_apply_dense": [vp, vp, i32, i32, i64, vp, vp, i32, vp],
         "b200sv_sample": [vp, i32, i32, i64, vp, vp, vp, i64, vp, vp],
         "b200sv_bit_reverse": [vp, vp, i32, i32, i64, vp],

@@ -29,6 +29,7 @@ from .program import Op, PauliSum, Program
 KRYLOV_TOL = 1e-13
 KRYLOV_MAX_DIM = 64
 KRYLOV_MEM_BYTES = 48 << 30  # basis storage budget
+KRYLOV_RHO_PER_STEP = 24.0  # ||G||·|t| handled per time sub-step (Krylov dimension ≈ ρ + O(ρ^(1/3)) stays < 64)
 
 
 def _time(op: Op, values: Mapping[str, Tensor], batch: int, device: torch.device) -> Tensor:
@@ -72,6 +73,20 @@ def generator_apply(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Ten
     return _matvec(op, compiled, values, n, psi.device)(psi)
 
 
+def _norm_bound(op: Op, compiled: Any, values: Mapping[str, Tensor]) -> float | None:
+    """Cheap upper bound of ||G|| (sum of |coefficients| / Frobenius norm), host side; None if unknown."""
+    g = op.generator
+    if isinstance(g, PauliSum):
+        if compiled.is_parametric:
+            return float(compiled.coef(values, torch.device("cpu")).abs().sum(0).max())
+        return float(np.abs(compiled.consts).sum())
+    if isinstance(g, np.ndarray):
+        return float(np.linalg.norm(np.asarray(g), ord="fro"))
+    if isinstance(g, str):
+        return float(torch.linalg.matrix_norm(torch.as_tensor(values[g]).detach().to(torch.complex128).reshape(-1, *values[g].shape[-2:])).max())
+    return None
+
+
 def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
     dev = psi.device
     B = psi.shape[0]
@@ -88,7 +103,16 @@ def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: 
         cabi.check(rc, "diag_evolve")
         return psi
     mv = _matvec(op, compiled, values, n, dev)
-    return krylov_expm(mv, psi, sign * t)
+    # time sub-stepping chosen up front from a norm bound, so that each step converges within the basis budget
+    bound = _norm_bound(op, compiled, values)
+    steps = 1
+    if bound is not None:
+        tmax = float(t.abs().max())
+        steps = max(1, int(np.ceil(bound * tmax / KRYLOV_RHO_PER_STEP)))
+    out = psi
+    for _ in range(steps):
+        out = krylov_expm(mv, out, (sign / steps) * t)
+    return out
 
 
 def krylov_expm(matvec: Callable[[Tensor], Tensor], psi: Tensor, t: Tensor, tol: float = KRYLOV_TOL, depth: int = 0) -> Tensor:
@@ -102,8 +126,8 @@ def krylov_expm(matvec: Callable[[Tensor], Tensor], psi: Tensor, t: Tensor, tol:
     V = torch.empty(m_max + 1, B, N, dtype=psi.dtype, device=dev)
     V[0].copy_(psi)
     E.scal((1.0 / safe).to(torch.complex128), V[0])
-    alphas: list[Tensor] = []
-    betas: list[Tensor] = []
+    alphas = torch.zeros(m_max, B, dtype=torch.float64, device=dev)
+    betas = torch.zeros(m_max, B, dtype=torch.float64, device=dev)
     y = None
     converged = False
     m = 0
@@ -118,15 +142,15 @@ def krylov_expm(matvec: Callable[[Tensor], Tensor], psi: Tensor, t: Tensor, tol:
         E.axpy(-c, V[j], w)
         a = a + c.real
         b = torch.sqrt(E.dot(w, w).real)
-        alphas.append(a)
-        betas.append(b)
+        alphas[j] = a
         m = j + 1
         tiny = b <= 1e-14 * torch.clamp(a.abs(), min=1.0)
+        betas[j] = torch.where(tiny, torch.zeros_like(b), b)
         inv = torch.where(tiny, torch.zeros_like(b), 1.0 / torch.where(tiny, torch.ones_like(b), b))
         V[j + 1].copy_(w)
         E.scal(inv.to(torch.complex128), V[j + 1])
-        if m >= min(4, m_max) and (m % 4 == 0 or m == m_max or m == N):
-            y, err = _small_expm(alphas, betas, t)
+        if m >= min(8, m_max) and (m % 8 == 0 or m == m_max or m == N):
+            y, err = _small_expm(alphas[:m], betas[:m], t)
             if float(err.max()) < tol or m == N:
                 converged = True
                 break
@@ -137,21 +161,21 @@ def krylov_expm(matvec: Callable[[Tensor], Tensor], psi: Tensor, t: Tensor, tol:
         half = krylov_expm(matvec, psi, 0.5 * t, tol, depth + 1)
         return krylov_expm(matvec, half, 0.5 * t, tol, depth + 1)
     out = torch.empty_like(psi)
-    coeff = (y * nrm[:, None].to(torch.complex128)).transpose(0, 1).contiguous()  # [m, B]
+    coeff = (y * nrm[None, :].to(torch.complex128)).contiguous()  # [m, B]
     E.lincomb(coeff, V[:m], out)
     return out
 
 
-def _small_expm(alphas: list[Tensor], betas: list[Tensor], t: Tensor) -> tuple[Tensor, Tensor]:
-    """y = exp(−i t T_m) e_1 for the batched tridiagonal T_m, and the a-posteriori error |β_m y_m|."""
-    m = len(alphas)
-    A = torch.stack(alphas, dim=1)  # [B, m]
-    T = torch.diag_embed(A)
-    if m > 1:
-        Bt = torch.stack(betas[:-1], dim=1)
-        T = T + torch.diag_embed(Bt, offset=1) + torch.diag_embed(Bt, offset=-1)
-    evals, evecs = torch.linalg.eigh(T)  # tiny [B, m, m] problem: host-side plumbing
-    phase = torch.exp(-1j * t[:, None] * evals)
-    y = torch.einsum("bij,bj->bi", evecs.to(torch.complex128), phase * evecs[:, 0, :].to(torch.complex128))
-    err = betas[-1].abs() * y[:, -1].abs()
-    return y, err
+def _small_expm(alphas: Tensor, betas: Tensor, t: Tensor) -> tuple[Tensor, Tensor]:
+    """y[m, B] = exp(−i t T_m) e_1 for the batched Lanczos tridiagonal and the a-posteriori error
+    |β_m y_m|, on the device (`b200sv_tridiag_expm`: scaled Taylor, no eigendecomposition)."""
+    m, B = alphas.shape
+    dev = alphas.device
+    a = alphas.contiguous()
+    b = betas.contiguous()
+    tt = t.to(torch.float64).contiguous()
+    y = torch.empty(m, B, 2, dtype=torch.float64, device=dev)
+    err = torch.empty(B, dtype=torch.float64, device=dev)
+    rc = cabi.load().b200sv_tridiag_expm(a.data_ptr(), b.data_ptr(), tt.data_ptr(), m, B, y.data_ptr(), err.data_ptr(), E._stream_ptr(dev))
+    cabi.check(rc, "tridiag_expm")
+    return torch.view_as_complex(y), err

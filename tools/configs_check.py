@@ -1,0 +1,122 @@
+"""Timing + sanity of the other BASELINE.json configs on one GPU (standalone builders; parity of the
+same circuit shapes is covered by tests/golden at small sizes).
+
+  cfg1  QNN hea(4,2) + feature map, batch 16            -> latency (evals/s)
+  cfg3  12-atom Rydberg register: AnalogRX / AnalogInteraction / AnalogRY as HamEvo, batch 1024
+  cfg4  feature map + hea(16,12), batch 512 per GPU     -> one training step (fwd + adjoint)
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np
+import torch
+
+from qadence_b200 import engine
+from qadence_b200.program import OpKind, PauliSum, PauliTerm, ProgramBuilder, hea_program, total_magnetization
+
+dev = torch.device("cuda:0")
+out = {}
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+# ---- cfg1 ----
+n, B = 4, 16
+b = ProgramBuilder(n)
+for q in range(n):
+    b.RX(q, "phi")
+prog = b.build()
+prog.ops += hea_program(n, 2).ops
+cp = engine.CompiledProgram(prog)
+cob = engine.CompiledObservable(total_magnetization(n))
+vals = {nm: torch.rand(1, dtype=torch.float64, device=dev).requires_grad_(True) for nm in prog.param_names if nm != "phi"}
+vals["phi"] = torch.linspace(-0.9, 0.9, B, dtype=torch.float64, device=dev)
+
+
+def cfg1():
+    e = engine.expectation(cp, [cob], vals, device=dev)
+    e.sum().backward()
+
+
+ms = timeit(cfg1, reps=50, warm=5)
+out["cfg1"] = {"n": n, "batch": B, "ms_per_fwd_bwd": ms, "evals_per_s": B / (ms * 1e-3), "sweeps_fwd": cp.n_sweeps(), "note": "launch-latency bound (4 KiB state); one fused sweep per direction"}
+
+# ---- cfg3: 3x4 lattice, spacing 8 um; H_int = sum C6/r^6 N_i N_j, drive Omega/2 (cos phi X - sin phi Y) ----
+n, B = 12, 1024
+coords = [(8.0 * (i // 4), 8.0 * (i % 4)) for i in range(n)]
+C6 = 865723.02
+terms_int = []
+for i in range(n):
+    for j in range(i + 1, n):
+        r = np.hypot(coords[i][0] - coords[j][0], coords[i][1] - coords[j][1])
+        c = C6 / r**6 / 4.0  # N_i N_j = (1 - Z_i - Z_j + Z_i Z_j) / 4
+        terms_int += [PauliTerm(c, (), ()), PauliTerm(-c, (), ((i, "Z"),)), PauliTerm(-c, (), ((j, "Z"),)), PauliTerm(c, (), ((i, "Z"), (j, "Z")))]
+h_int = PauliSum(n, terms_int).simplified()
+omega = np.pi
+h_rx = PauliSum(n, h_int.terms + [PauliTerm(omega / 2, (), ((q, "X"),)) for q in range(n)]).simplified()
+h_ry = PauliSum(n, h_int.terms + [PauliTerm(omega / 2, (), ((q, "Y"),)) for q in range(n)]).simplified()
+prog3 = ProgramBuilder(n).hamevo(h_rx, "ta").hamevo(h_int, "tt").hamevo(h_ry, "tb").build()
+g = torch.Generator().manual_seed(0)
+v3 = {"ta": torch.rand(B, generator=g, dtype=torch.float64) * np.pi / omega, "tt": torch.rand(B, generator=g, dtype=torch.float64),
+      "tb": torch.rand(B, generator=g, dtype=torch.float64) * np.pi / omega}
+cp3 = engine.CompiledProgram(prog3)
+cob3 = engine.CompiledObservable(total_magnetization(n))
+res = {}
+
+
+def cfg3():
+    res["e"] = engine.expectation(cp3, [cob3], v3, device=dev)
+
+
+ms3 = timeit(cfg3, reps=3, warm=1)
+psi = engine.run(cp3, v3, device=dev)
+norm_err = float((engine.dot(psi, psi).real - 1).abs().max())
+# parity of a batch slice against the dense-matrix oracle (n = 12 -> 4096 x 4096 expm is feasible for a few elements)
+from oracle import statevec as oracle
+
+sl = {k: v[:2] for k, v in v3.items()}
+want = oracle.run(prog3, sl)
+err = float((psi[:2].cpu() - want).abs().max())
+out["cfg3"] = {"n": n, "batch": B, "ms": ms3, "hamevo_applications_per_s": 3 * B / (ms3 * 1e-3), "generator_terms": len(h_rx.terms),
+               "norm_err": norm_err, "max_abs_err_vs_dense_expm_oracle(first 2 batch elements)": err}
+
+# ---- cfg4: feature map (RX(x) per qubit here) + hea(16, 12), 512 per GPU ----
+n, B = 16, 512
+b = ProgramBuilder(n)
+for q in range(n):
+    b.RX(q, "x")
+prog4 = b.build()
+prog4.ops += hea_program(n, 12).ops
+cp4 = engine.CompiledProgram(prog4)
+cob4 = engine.CompiledObservable(total_magnetization(n))
+theta = {nm: torch.rand(1, dtype=torch.float64, device=dev).requires_grad_(True) for nm in prog4.param_names if nm != "x"}
+x = torch.rand(B, dtype=torch.float64, device=dev) * 1.98 - 0.99
+opt = torch.optim.Adam(theta.values(), lr=0.01)
+
+
+def cfg4():
+    opt.zero_grad()
+    e = engine.expectation(cp4, [cob4], {**theta, "x": x}, device=dev)
+    loss = ((e[:, 0] - x**2) ** 2).mean()
+    loss.backward()
+    opt.step()
+
+
+ms4 = timeit(cfg4, reps=5, warm=2)
+out["cfg4"] = {"n": n, "batch_per_gpu": B, "gates": len(prog4.ops), "ms_per_training_step": ms4, "samples_per_s_per_gpu": B / (ms4 * 1e-3),
+               "sweeps_fwd": cp4.n_sweeps(), "sweeps_adj": cp4.n_sweeps(adjoint=True)}
+print(json.dumps(out, indent=1))

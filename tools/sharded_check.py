@@ -46,10 +46,12 @@ prog = Program(n, qft_program(n).ops + hea_program(n, args.depth).ops)
 g = torch.Generator().manual_seed(7)
 values = {nm: 2 * torch.pi * torch.rand(1, generator=g, dtype=torch.float64) for nm in prog.param_names}
 sim = qdist.QubitShardedSimulator(prog, rank, world, dev)
-st = sim.run(values)
+st = sim.run(values)  # warm-up (plans, NCCL communicator)
 torch.cuda.synchronize()
 times = []
 for _ in range(args.reps):
+    del st  # a 36-qubit shard is 128 GiB: never hold two
+    torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -179,11 +179,15 @@ int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n_qubits, int64_t b
                         const double* params, double* grads, const b200sv_plan* plan, int first,
                         int last, uint64_t index_hi, void* workspace, void* stream);
 
+/* In the three Pauli-sum entry points the first `n_single` terms must be single-Z strings (xmask == 0,
+ * exactly one zmask bit): they are additive over index bits and are evaluated once per thread instead of
+ * once per amplitude (total_magnetization, detunings, the linear part of N_i N_j).  Pass 0 if unsorted. */
+
 /* out[b] (+)= Re <psi_b| sum_t coef[row_t][b] P_t |psi_b>.  coef is a device table
  * `double[n_rows][coef_ld][2]` (complex), coef_ld = batch or 1 (broadcast).
  * Replaces pyq.Observable.expectation (backends/pyqtorch/backend.py:208,249). */
 int b200sv_pauli_expectation(const void* psi, int dtype, int n_qubits, int64_t batch,
-                             const b200sv_pterm* terms, int n_terms, const double* coef,
+                             const b200sv_pterm* terms, int n_terms, int n_single, const double* coef,
                              int64_t coef_ld, double* out, uint64_t index_hi, void* stream);
 
 /* out = alpha * (sum_t coef_t P_t psi) + beta * acc   (acc may be NULL when beta == 0, may alias out).
@@ -192,7 +196,7 @@ int b200sv_pauli_expectation(const void* psi, int dtype, int n_qubits, int64_t b
  * (backends/pyqtorch/convert_ops.py:223,276-280).  Terms whose xmask has bits >= n_qubits are
  * rejected (global qubits must be made local first). */
 int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, int n_qubits,
-                       int64_t batch, const b200sv_pterm* terms, int n_terms, const double* coef,
+                       int64_t batch, const b200sv_pterm* terms, int n_terms, int n_single, const double* coef,
                        int64_t coef_ld, double alpha_re, double alpha_im, double beta_re,
                        double beta_im, uint64_t index_hi, void* stream);
 
@@ -201,7 +205,7 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
  * sum_{i<j} C6/r^6 N_i N_j of analog blocks (analog/hamiltonian_terms.py:16-45) takes this path.
  * Replaces pyq.HamiltonianEvolution's dense matrix_exp (backends/pyqtorch/convert_ops.py:258-269). */
 int b200sv_diag_evolve(void* psi, int dtype, int n_qubits, int64_t batch, const b200sv_pterm* terms,
-                       int n_terms, const double* coef, int64_t coef_ld, const double* t,
+                       int n_terms, int n_single, const double* coef, int64_t coef_ld, const double* t,
                        int64_t t_ld, double sign, uint64_t index_hi, void* stream);
 
 /* Batched BLAS-1 on states (Krylov / Lanczos plumbing), all per batch element b:

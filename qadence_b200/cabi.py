@@ -86,9 +86,9 @@ def load() -> C.CDLL:
         "b200sv_plan_workspace_bytes": [vp, i32, i64, i32],
         "b200sv_apply_plan": [vp, i32, i32, i64, vp, vp, i32, i32, u64, vp, vp],
         "b200sv_adjoint_plan": [vp, vp, i32, i32, i64, vp, vp, vp, i32, i32, u64, vp, vp],
-        "b200sv_pauli_expectation": [vp, i32, i32, i64, vp, i32, vp, i64, vp, u64, vp],
-        "b200sv_pauli_apply": [vp, vp, vp, i32, i32, i64, vp, i32, vp, i64, f64, f64, f64, f64, u64, vp],
-        "b200sv_diag_evolve": [vp, i32, i32, i64, vp, i32, vp, i64, vp, i64, f64, u64, vp],
+        "b200sv_pauli_expectation": [vp, i32, i32, i64, vp, i32, i32, vp, i64, vp, u64, vp],
+        "b200sv_pauli_apply": [vp, vp, vp, i32, i32, i64, vp, i32, i32, vp, i64, f64, f64, f64, f64, u64, vp],
+        "b200sv_diag_evolve": [vp, i32, i32, i64, vp, i32, i32, vp, i64, vp, i64, f64, u64, vp],
         "b200sv_dot": [vp, vp, i32, i32, i64, vp, vp],
         "b200sv_axpy": [vp, vp, vp, i32, i32, i64, vp],
         "b200sv_scal": [vp, vp, i32, i32, i64, vp],

@@ -185,12 +185,26 @@ struct TermS {  // per-CTA resolved term
   double cr, ci;
 };
 
+// Single-Z diagonal terms (the first n_single terms; total_magnetization, detunings, the linear part of
+// N_i N_j expansions) are additive over index bits:  sum_t c_t (-1)^{bit_t(i)} = c0 - 2 sum_{bits set in i} cbit[bit],
+// so a thread evaluates them once for its fixed index bits and adds a per-k correction.
+struct SingleZ {
+  double cbr[64], cbi[64];
+  double c0r, c0i;
+};
+
 constexpr int MAX_TERMS_SMEM = 1024;
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_PER_THREAD = 8;
 
 __device__ __forceinline__ void resolve_terms(TermS* sh, const b200sv_pterm* terms, int T,
-                                              const double* coef, long long coef_ld, long long b) {
+                                              const double* coef, long long coef_ld, long long b,
+                                              SingleZ* sz = nullptr, int n_single = 0) {
+  if (sz != nullptr) {
+    for (int q = threadIdx.x; q < 64; q += blockDim.x) { sz->cbr[q] = 0.0; sz->cbi[q] = 0.0; }
+    if (threadIdx.x == 0) { sz->c0r = 0.0; sz->c0i = 0.0; }
+    __syncthreads();
+  }
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const b200sv_pterm tm = terms[t];
     const long long bb = coef_ld == 1 ? 0 : b;
@@ -203,33 +217,55 @@ __device__ __forceinline__ void resolve_terms(TermS* sh, const b200sv_pterm* ter
       case 3: { const double t0 = cr; cr = -ci; ci = t0; } break;
       default: break;
     }
-    sh[t].x = tm.xmask; sh[t].z = tm.zmask; sh[t].cr = cr; sh[t].ci = ci;
+    if (t < n_single) {  // xmask == 0, exactly one z bit (guaranteed by the caller)
+      const int bit = __ffsll((long long)tm.zmask) - 1;
+      atomicAdd(&sz->cbr[bit], cr); atomicAdd(&sz->cbi[bit], ci);
+      atomicAdd(&sz->c0r, cr); atomicAdd(&sz->c0i, ci);
+    } else {
+      sh[t - n_single].x = tm.xmask; sh[t - n_single].z = tm.zmask; sh[t - n_single].cr = cr; sh[t - n_single].ci = ci;
+    }
   }
+}
+
+// weight of the single-Z terms at index gi: c0 - 2 * sum over set bits
+__device__ __forceinline__ void single_z_weight(const SingleZ& sz, unsigned long long gi, double& wr, double& wi) {
+  double ar = 0.0, ai = 0.0;
+  while (gi) {
+    const int bit = __ffsll((long long)gi) - 1;
+    gi &= gi - 1;
+    ar += sz.cbr[bit]; ai += sz.cbi[bit];
+  }
+  wr = sz.c0r - 2.0 * ar; wi = sz.c0i - 2.0 * ai;
 }
 
 // E[b] += Re sum_i conj(psi_i) sum_t c_t (-1)^{popc(i&z_t)} psi[i^x_t]
 template <typename c2>
 __global__ void __launch_bounds__(EXP_THREADS)
 pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b200sv_pterm* __restrict__ terms,
-                    int T, const double* __restrict__ coef, long long coef_ld, double* __restrict__ out,
+                    int T, int n_single, const double* __restrict__ coef, long long coef_ld, double* __restrict__ out,
                     unsigned long long index_hi, long long blocks_per_state) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
+  __shared__ SingleZ sz;
   __shared__ double red[32];
   const long long b = blockIdx.x / blocks_per_state;
   const long long blk = blockIdx.x % blocks_per_state;
-  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
+  T -= n_single;
   const long long N = 1ll << n;
   const c2* p = psi + (b << n);
   double acc = 0.0;
   const long long base = blk * (long long)(EXP_THREADS * EXP_PER_THREAD);
+  double w0r = 0.0, w0i = 0.0;  // single-Z weight of this thread's k = 0 index
+  if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
 #pragma unroll 1
   for (int k = 0; k < EXP_PER_THREAD; ++k) {
     const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
     if (i >= N) break;
     const c2 a = p[i];
     const unsigned long long gi = (unsigned long long)i | index_hi;
-    double wr = 0.0;             // diagonal weight
+    double wr = w0r;             // diagonal weight (k only changes the bits above log2(EXP_THREADS))
+    if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * EXP_THREADS, kr, ki); wr += kr - sz.c0r; }
     double sr = 0.0, si = 0.0;   // off-diagonal sum
     for (int t = 0; t < T; ++t) {
       const TermS tm = sh[t];
@@ -253,24 +289,29 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
 template <typename c2>
 __global__ void __launch_bounds__(256)
 pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
-                   const b200sv_pterm* __restrict__ terms, int T, const double* __restrict__ coef,
+                   const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
                    long long coef_ld, double ar, double ai, double br, double bi,
                    unsigned long long index_hi, long long blocks_per_state) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
+  __shared__ SingleZ sz;
   const long long b = blockIdx.x / blocks_per_state;
   const long long blk = blockIdx.x % blocks_per_state;
-  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
+  T -= n_single;
   const long long N = 1ll << n;
   const c2* p = psi + (b << n);
   const long long base = blk * (long long)(256 * 4);
+  double w0r = 0.0, w0i = 0.0;
+  if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     const long long i = base + (long long)k * 256 + threadIdx.x;
     if (i >= N) break;
     const unsigned long long gi = (unsigned long long)i | index_hi;
     const c2 a = p[i];
-    double wr = 0.0, wi = 0.0, sr = 0.0, si = 0.0;
+    double wr = w0r, wi = w0i, sr = 0.0, si = 0.0;
+    if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * 256, kr, ki); wr += kr - sz.c0r; wi += ki - sz.c0i; }
     for (int t = 0; t < T; ++t) {
       const TermS tm = sh[t];
       const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
@@ -298,14 +339,16 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
 // psi[i] *= exp(-i * sign * t_b * d(i))
 template <typename c2>
 __global__ void __launch_bounds__(256)
-diag_evolve_kernel(c2* psi, int n, long long batch, const b200sv_pterm* __restrict__ terms, int T,
+diag_evolve_kernel(c2* psi, int n, long long batch, const b200sv_pterm* __restrict__ terms, int T, int n_single,
                    const double* __restrict__ coef, long long coef_ld, const double* __restrict__ tt,
                    long long t_ld, double sign, unsigned long long index_hi, long long blocks_per_state) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
+  __shared__ SingleZ sz;
   const long long b = blockIdx.x / blocks_per_state;
   const long long blk = blockIdx.x % blocks_per_state;
-  resolve_terms(sh, terms, T, coef, coef_ld, b);
+  resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
+  T -= n_single;
   const double t = tt[t_ld == 1 ? 0 : b] * sign;
   const long long N = 1ll << n;
   c2* p = psi + (b << n);
@@ -316,6 +359,7 @@ diag_evolve_kernel(c2* psi, int n, long long batch, const b200sv_pterm* __restri
     if (i >= N) break;
     const unsigned long long gi = (unsigned long long)i | index_hi;
     double d = 0.0;
+    if (n_single > 0) { double di; single_z_weight(sz, gi, d, di); }
     for (int q = 0; q < T; ++q) {
       const TermS tm = sh[q];
       d += (__popcll(gi & tm.z) & 1) ? -tm.cr : tm.cr;
@@ -622,13 +666,16 @@ int b200sv_adjoint_plan(void* psi, void* lam, int dtype, int n, int64_t batch, c
   return B200SV_E_ARG;
 }
 
-static int check_terms(int n_terms) { return (n_terms < 0 || n_terms > MAX_TERMS_SMEM) ? B200SV_E_UNSUPPORTED : 0; }
+static int check_terms(int n_terms, int n_single = 0) {
+  if (n_single < 0 || n_single > n_terms) return B200SV_E_ARG;
+  return (n_terms < 0 || n_terms - n_single > MAX_TERMS_SMEM) ? B200SV_E_UNSUPPORTED : 0;
+}
 
 int b200sv_pauli_expectation(const void* psi, int dtype, int n, int64_t batch, const b200sv_pterm* terms,
-                             int n_terms, const double* coef, int64_t coef_ld, double* out,
+                             int n_terms, int n_single, const double* coef, int64_t coef_ld, double* out,
                              uint64_t index_hi, void* stream) {
   if (!psi || !out || batch <= 0 || (coef_ld != 1 && coef_ld != batch)) return B200SV_E_ARG;
-  if (int rc = check_terms(n_terms)) return rc;
+  if (int rc = check_terms(n_terms, n_single)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
   const long long per = EXP_THREADS * EXP_PER_THREAD;
@@ -636,19 +683,19 @@ int b200sv_pauli_expectation(const void* psi, int dtype, int n, int64_t batch, c
   const long long grid = bps * batch;
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (dtype == B200SV_C128)
-    pauli_expect_kernel<double2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, coef, coef_ld, out, index_hi, bps);
+    pauli_expect_kernel<double2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps);
   else if (dtype == B200SV_C64)
-    pauli_expect_kernel<float2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, coef, coef_ld, out, index_hi, bps);
+    pauli_expect_kernel<float2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;
 }
 
 int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, int n, int64_t batch,
-                       const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld,
+                       const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, int64_t coef_ld,
                        double ar, double ai, double br, double bi, uint64_t index_hi, void* stream) {
   if (!psi || !out || psi == out || batch <= 0 || (coef_ld != 1 && coef_ld != batch)) return B200SV_E_ARG;
-  if (int rc = check_terms(n_terms)) return rc;
+  if (int rc = check_terms(n_terms, n_single)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
   const long long bps = (N + 1023) / 1024;
@@ -656,28 +703,28 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (br == 0.0 && bi == 0.0) acc = nullptr;
   if (dtype == B200SV_C128)
-    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
   else if (dtype == B200SV_C64)
-    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;
 }
 
 int b200sv_diag_evolve(void* psi, int dtype, int n, int64_t batch, const b200sv_pterm* terms, int n_terms,
-                       const double* coef, int64_t coef_ld, const double* t, int64_t t_ld, double sign,
+                       int n_single, const double* coef, int64_t coef_ld, const double* t, int64_t t_ld, double sign,
                        uint64_t index_hi, void* stream) {
   if (!psi || !t || batch <= 0 || (coef_ld != 1 && coef_ld != batch) || (t_ld != 1 && t_ld != batch)) return B200SV_E_ARG;
-  if (int rc = check_terms(n_terms)) return rc;
+  if (int rc = check_terms(n_terms, n_single)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
   const long long bps = (N + 1023) / 1024;
   const long long grid = bps * batch;
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (dtype == B200SV_C128)
-    diag_evolve_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)psi, n, batch, terms, n_terms, coef, coef_ld, t, t_ld, sign, index_hi, bps);
+    diag_evolve_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, t, t_ld, sign, index_hi, bps);
   else if (dtype == B200SV_C64)
-    diag_evolve_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)psi, n, batch, terms, n_terms, coef, coef_ld, t, t_ld, sign, index_hi, bps);
+    diag_evolve_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, t, t_ld, sign, index_hi, bps);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;

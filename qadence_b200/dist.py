@@ -339,7 +339,7 @@ class QubitShardedSimulator:
         out = torch.zeros(1, dtype=torch.float64, device=dev)
         cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
         rc = cabi.load().b200sv_pauli_expectation(state.data_ptr(), engine._DT[state.dtype], self.n_local, 1, cps.terms(dev).data_ptr(),
-                                                  cps.n_terms, cf.data_ptr(), coef.shape[1], out.data_ptr(), self.index_hi, engine._stream_ptr(dev))
+                                                  cps.n_terms, cps.n_single, cf.data_ptr(), coef.shape[1], out.data_ptr(), self.index_hi, engine._stream_ptr(dev))
         cabi.check(rc, "pauli_expectation (sharded)")
         return out
 

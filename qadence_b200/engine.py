@@ -101,18 +101,25 @@ class CompiledPauliSum:
     consts: np.ndarray  # [T] complex
     names: list[tuple[str, ...]]
     diagonal: bool
+    n_single: int = 0
     _dev_terms: dict = field(default_factory=dict)
     _dev_const_coef: dict = field(default_factory=dict)
 
     @staticmethod
     def build(ps: PauliSum) -> "CompiledPauliSum":
         ps = ps.simplified()
-        if len(ps.terms) > 1024:
-            raise NotImplementedError("Pauli sums with more than 1024 distinct terms are not supported yet")
+        # single-Z strings first: the kernels evaluate them once per thread (see include/b200sv.h)
+        single = [t for t in ps.terms if len(t.paulis) == 1 and t.paulis[0][1] == "Z"]
+        rest = [t for t in ps.terms if not (len(t.paulis) == 1 and t.paulis[0][1] == "Z")]
+        ps = PauliSum(ps.n_qubits, single + rest)
+        if len(rest) > 1024:
+            raise NotImplementedError("Pauli sums with more than 1024 distinct non-trivial terms are not supported yet")
         terms = pack_pauli_terms([t.paulis for t in ps.terms], ps.n_qubits)
-        return CompiledPauliSum(
+        out = CompiledPauliSum(
             ps, terms, np.array([t.const for t in ps.terms], dtype=np.complex128), [t.names for t in ps.terms], ps.is_diagonal
         )
+        out.n_single = len(single)
+        return out
 
     @property
     def n_terms(self) -> int:
@@ -271,7 +278,7 @@ def pauli_apply(cps: CompiledPauliSum, coef: Tensor, psi: Tensor, out: Tensor | 
     cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
     rc = cabi.load().b200sv_pauli_apply(
         psi.data_ptr(), out.data_ptr(), 0 if acc is None else acc.data_ptr(), _DT[psi.dtype], n, B,
-        cps.terms(dev).data_ptr(), cps.n_terms, cf.data_ptr(), coef.shape[1],
+        cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), coef.shape[1],
         float(np.real(alpha)), float(np.imag(alpha)), float(np.real(beta)), float(np.imag(beta)), index_hi, _stream_ptr(dev),
     )
     cabi.check(rc, "pauli_apply")
@@ -286,7 +293,7 @@ def pauli_expectation(cps: CompiledPauliSum, coef: Tensor, psi: Tensor, index_hi
     out = torch.zeros(B, dtype=torch.float64, device=dev)
     cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
     rc = cabi.load().b200sv_pauli_expectation(
-        psi.data_ptr(), _DT[psi.dtype], n, B, cps.terms(dev).data_ptr(), cps.n_terms, cf.data_ptr(), coef.shape[1],
+        psi.data_ptr(), _DT[psi.dtype], n, B, cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), coef.shape[1],
         out.data_ptr(), index_hi, _stream_ptr(dev),
     )
     cabi.check(rc, "pauli_expectation")

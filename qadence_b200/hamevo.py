@@ -97,7 +97,7 @@ def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: 
         coef = compiled.coef(values, dev)
         cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
         rc = cabi.load().b200sv_diag_evolve(
-            psi.data_ptr(), E._DT[psi.dtype], n, B, compiled.terms(dev).data_ptr(), compiled.n_terms, cf.data_ptr(),
+            psi.data_ptr(), E._DT[psi.dtype], n, B, compiled.terms(dev).data_ptr(), compiled.n_terms, compiled.n_single, cf.data_ptr(),
             coef.shape[1], t.data_ptr(), B, sign, 0, E._stream_ptr(dev),
         )
         cabi.check(rc, "diag_evolve")

@@ -402,6 +402,9 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 #ifndef B200SV_MINB_FWD_D
 #define B200SV_MINB_FWD_D 4  // complex128 forward, r >= 3: CTAs per SM the register allocation targets
 #endif
+#ifndef B200SV_ADJ_D_MAXT
+#define B200SV_ADJ_D_MAXT 128  // threads per CTA of the complex128 adjoint kernel (r = 3)
+#endif
 #ifndef B200SV_MINB_FWD_D_R4
 #define B200SV_MINB_FWD_D_R4 2
 #endif
@@ -416,7 +419,7 @@ __device__ __forceinline__ int byte_of(unsigned long long w, int i) { return (in
 #endif
 // launch geometry per instantiation: (max threads per CTA, min CTAs per SM)
 template <typename real, int R, bool ADJ> struct SweepCfg {
-  static constexpr int MAXT = (ADJ && sizeof(real) == 8 && R >= 3) ? 128 : 256;
+  static constexpr int MAXT = (ADJ && sizeof(real) == 8 && R >= 3) ? B200SV_ADJ_D_MAXT : 256;
   static constexpr int MINB = (ADJ && sizeof(real) == 8) ? (R <= 2 ? B200SV_MINB_ADJ_D_R2 : B200SV_MINB_ADJ_D)
                               : ((sizeof(real) == 8 && R >= 4) ? B200SV_MINB_FWD_D_R4 : (sizeof(real) == 8 && R == 3) ? B200SV_MINB_FWD_D : ((sizeof(real) == 8 && R == 2) ? B200SV_MINB_FWD_D_R2 : (ADJ ? 2 : 3)));
 };

@@ -81,9 +81,11 @@ class TileConfig:
         if key in os.environ:  # tuning override: "m,r,low"
             m, r, low = (int(x) for x in os.environ[key].split(","))
             return TileConfig(m=m, r=r, low=low, fold=3 if dtype_is_c128 else 4)
+        # measured on B200 (profiles/r01_tile_geometry.md): 64-byte runs (low = 2 for 16-byte amplitudes) already
+        # stream at ~80 % of the HBM roofline, and every forced low bit costs a "hard" bit, i.e. more sweeps
         if dtype_is_c128:
-            return TileConfig(m=11, r=3, low=4, fold=3) if not adjoint else TileConfig(m=10, r=3, low=4, fold=3)
-        return TileConfig(m=12, r=4, low=5, fold=4) if not adjoint else TileConfig(m=11, r=3, low=5, fold=4)
+            return TileConfig(m=11, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3)
+        return TileConfig(m=12, r=4, low=2, fold=4) if not adjoint else TileConfig(m=11, r=3, low=2, fold=4)
 
 
 @dataclass

@@ -73,11 +73,13 @@ def test_hea_fuses_into_few_sweeps() -> None:
     n, depth = 20, 8
     prog = hea_program(n, depth)
     slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
-    plan = build_plan(prog.ops, n, slot_of, TileConfig.default(True, False))
+    cfg = TileConfig.default(True, False)
+    plan = build_plan(prog.ops, n, slot_of, cfg)
     assert len(prog.ops) == 632
-    assert plan.n_sweeps <= 40, plan.n_sweeps  # vs 632 state round trips gate by gate
+    assert plan.n_sweeps <= 16, plan.n_sweeps  # vs 632 state round trips gate by gate
+    assert int(plan.rounds["n_exec"].sum()) == 0  # no interpreter entries: merged 2x2 + folded CNOT permutations only
     for sw in plan.sweeps:
-        assert set(range(4)) <= set(int(x) for x in sw["tile_bits"][: sw["m"]])  # coalesced low bits
+        assert set(range(cfg.low)) <= set(int(x) for x in sw["tile_bits"][: sw["m"]])  # coalesced low bits
 
 
 def test_dagger_plan_inverts() -> None:

@@ -4,8 +4,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one full expectation+gradient evaluation of the whole batch: |0..0> init, 16 fused
-forward sweeps, <Z_tot>, λ = Oψ, 18 fused adjoint sweeps that also reduce all 480 gradients.
+One "step" = one full expectation+gradient evaluation of the whole batch: |0..0> init, fused
+forward sweeps, <Z_tot>, λ = Oψ, fused adjoint sweeps that also reduce all 480 gradients.
 Prints ONE JSON line (rank 0).  Multi-GPU (torchrun): every rank evaluates its own 256 parameter
 sets (parameter batches shard trivially: no data-path collective) → "scaling": "weak".
 """

@@ -59,7 +59,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
   static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
-  const int nbuf = persistent ? 2 : 1;
+  const int nbuf = persistent == 1 ? 2 : 1;  // 1: persistent + double buffer, 2: persistent, single buffer (table reuse only)
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
   auto kern = sweep_kernel<real, R, ADJ, GEN>;

@@ -246,3 +246,27 @@ def test_parametric_observable_only_in_ad_mode() -> None:
     bk = backend_factory("b200sv", diff_mode=DiffMode.ADJOINT)
     with pytest.raises(ValueError):
         bk.observable("w" * Z(0), 1)
+
+
+def test_qnn_training_step_through_the_plugin(oracle_device) -> None:
+    """configs[0] end to end at the ML layer: `QNN(hea(4, 2) + feature map, total_magnetization)` built by qadence's own
+    ml_tools on the b200sv backend, one Adam step on an MSE loss (ml_tools/models.py:107-475, optimize_step.py:44-54)."""
+    from qadence.ml_tools.models import QNN
+
+    torch.manual_seed(0)
+    circ = QuantumCircuit(4, feature_map(4), hea(4, 2))
+    model = QNN(circ, total_magnetization(4), backend="b200sv", diff_mode=DiffMode.ADJOINT)
+    x = torch.linspace(-0.9, 0.9, 16).reshape(-1, 1)
+    y = x**2
+    opt = torch.optim.Adam(model.parameters(), lr=0.05)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        out = model(x)
+        assert out.shape == (16, 1)
+        loss = torch.nn.functional.mse_loss(out, y.to(out.dtype))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    assert all(p.grad is not None for p in model.parameters() if p.requires_grad)

@@ -329,7 +329,8 @@ def main() -> None:
                     "h2d_bytes_per_step": n_slots * BATCH * 8, "d2h_bytes_per_step": BATCH * 8 + n_slots * BATCH * 8},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "sweep_kernel<double,3,true,false> (adjoint sweep: psi+lambda read+write, gradient moments reduced)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": 17.134e9, "traffic_source": "profiles/r01h_final_build.md: dram__bytes_read 8.592 GB + dram__bytes_write 8.541 GB for one adjoint sweep (ncu --set full)",
                          "peak_source": peak_src, "bytes_per_launch": 4 * S, "avg_launch_ms": adj_avg,
                          "forward_sweep": {"achieved": fwd_achieved, "frac": fwd_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": fwd_avg},
                          "light_sweep": {"what": "same kernel, one round of three merged 2x2 (6 gates) per sweep", "achieved": light_achieved,

@@ -488,7 +488,9 @@ class _AdjointExpectation(torch.autograd.Function):
                 cabi.check(rc, "adjoint_plan")
                 continue
             op = seg.op
-            if op.kind == OpKind.HAMEVO:
+            if op.kind == OpKind.HAMEVO and op.tsym:
+                psi, lam = hamevo.adjoint_time_dependent(op, seg.compiled, psi, lam, values, cp.n_qubits, grads, cp.slot_of)
+            elif op.kind == OpKind.HAMEVO:
                 if isinstance(op.param, str):
                     g_psi = hamevo.generator_apply(op, seg.compiled, psi, values, cp.n_qubits)
                     grads[cp.slot_of[op.param]] += 2.0 * dot(lam, g_psi).imag

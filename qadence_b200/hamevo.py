@@ -24,7 +24,7 @@ from torch import Tensor
 
 from . import cabi
 from . import engine as E
-from .program import Op, PauliSum, Program
+from .program import Op, PauliSum, Program, parse_td_expr
 
 KRYLOV_TOL = 1e-13
 KRYLOV_MAX_DIM = 64
@@ -87,7 +87,102 @@ def _norm_bound(op: Op, compiled: Any, values: Mapping[str, Tensor]) -> float | 
     return None
 
 
+_LAMBDA_CACHE: dict = {}
+
+
+def _td_coefficients(compiled: Any, tsym: str, t: Tensor, values: Mapping[str, Tensor], B: int, dev: torch.device, diff: str | None = None) -> Tensor:
+    """[T, B] complex128 coefficient table of a time-dependent generator at times t [B]; with `diff`, its partial
+    derivative w.r.t. that symbol.  The symbolic coefficients are evaluated on the host (T·B numbers per step); the
+    matrix-free evolution itself runs on the GPU."""
+    import sympy
+
+    def val(nm: str) -> np.ndarray:
+        v = torch.as_tensor(values[nm]).detach().cpu().reshape(-1)
+        v = (v.real if v.is_complex() else v).to(torch.float64).numpy()
+        return v if v.size == B else np.broadcast_to(v, (B,))
+
+    rows = []
+    tt = t.detach().cpu().numpy()
+    for const, names, term in zip(compiled.consts, compiled.names, compiled.ps.terms):
+        c = np.full(B, complex(const))
+        for nm in names:
+            c = c * val(nm)
+        key = (term.expr, diff)
+        if key not in _LAMBDA_CACHE:
+            e = parse_td_expr(term.expr)[0] if term.expr else sympy.Integer(1)
+            if diff is not None:
+                e = sympy.diff(e, sympy.Symbol(diff))
+            syms = sorted(str(s_) for s_ in e.free_symbols)
+            _LAMBDA_CACHE[key] = (syms, sympy.lambdify([sympy.Symbol(s_) for s_ in syms], e, modules="numpy"))
+        syms, fn = _LAMBDA_CACHE[key]
+        args = [tt if s_ == tsym else val(s_) for s_ in syms]
+        c = c * np.broadcast_to(np.asarray(fn(*args), dtype=np.float64), (B,))
+        rows.append(c)
+    return torch.as_tensor(np.stack(rows)).to(dev)
+
+
+def _td_step(compiled: Any, coef: Tensor, state: Tensor, dt: Tensor, sign: float, n: int) -> Tensor:
+    if compiled.diagonal:
+        cf = torch.view_as_real(coef.contiguous())
+        rc = cabi.load().b200sv_diag_evolve(state.data_ptr(), E._DT[state.dtype], n, state.shape[0], compiled.terms(state.device).data_ptr(),
+                                            compiled.n_terms, compiled.n_single, cf.data_ptr(), coef.shape[1], dt.data_ptr(), state.shape[0],
+                                            sign, 0, E._stream_ptr(state.device))
+        cabi.check(rc, "diag_evolve")
+        return state
+    return krylov_expm(lambda v: E.pauli_apply(compiled, coef, v), state, sign * dt)
+
+
+def evolve_time_dependent(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
+    """dψ/dt = −i H(t) ψ on [0, duration]: `op.steps` exponential-midpoint steps ψ ← exp(−i dt H(t_k + dt/2)) ψ, each one
+    a Krylov (or on-the-fly diagonal) exponential.  Second order in dt; unitary at any step count."""
+    dev = psi.device
+    B = psi.shape[0]
+    steps = max(1, op.steps)
+    dt = _time(op, values, B, dev) / steps
+    out = psi
+    for k in (range(steps - 1, -1, -1) if dagger else range(steps)):
+        coef = _td_coefficients(compiled, op.tsym, (k + 0.5) * dt, values, B, dev)
+        out = _td_step(compiled, coef, out, dt, -1.0 if dagger else 1.0, n)
+    return out
+
+
+def adjoint_time_dependent(op: Op, compiled: Any, psi: Tensor, lam: Tensor, values: Mapping[str, Tensor], n: int,
+                           grads: Tensor, slot_of: Mapping[str, int]) -> tuple[Tensor, Tensor]:
+    """Backward walk through a time-dependent HamEvo: un-applies the steps on ψ and λ and accumulates
+    ∂E/∂duration = 2 Im⟨λ|H(T)|ψ(T)⟩ and ∂E/∂s = ∫ 2 Im⟨λ(t)|∂H/∂s|ψ(t)⟩ dt (trapezoid over each step) for every free
+    symbol s of the coefficient expressions.  Both are the continuum derivatives, consistent with the discretised
+    forward pass to O(dt²)."""
+    from .program import time_dependent_symbols
+
+    dev = psi.device
+    B = psi.shape[0]
+    steps = max(1, op.steps)
+    dur = _time(op, values, B, dev)
+    dt = dur / steps
+    if isinstance(op.param, str):
+        coef_T = _td_coefficients(compiled, op.tsym, dur, values, B, dev)
+        grads[slot_of[op.param]] += 2.0 * E.dot(lam, E.pauli_apply(compiled, coef_T, psi)).imag
+    symbols = [s_ for s_ in time_dependent_symbols(compiled.ps, op.tsym) if s_ in slot_of]
+
+    def overlaps(tm: Tensor) -> list[Tensor]:
+        return [2.0 * E.dot(lam, E.pauli_apply(compiled, _td_coefficients(compiled, op.tsym, tm, values, B, dev, diff=s_), psi)).imag
+                for s_ in symbols]
+
+    for k in range(steps - 1, -1, -1):
+        tm = (k + 0.5) * dt
+        after = overlaps(tm)
+        coef = _td_coefficients(compiled, op.tsym, tm, values, B, dev)
+        psi = _td_step(compiled, coef, psi, dt, -1.0, n)
+        lam = _td_step(compiled, coef, lam, dt, -1.0, n)
+        before = overlaps(tm)
+        for s_, a, b in zip(symbols, after, before):
+            grads[slot_of[s_]] += 0.5 * dt * (a + b)
+    return psi, lam
+
+
 def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
+    if op.tsym:
+        return evolve_time_dependent(op, compiled, psi, values, n, dagger)
     dev = psi.device
     B = psi.shape[0]
     t = _time(op, values, B, dev)

@@ -51,13 +51,17 @@ class PauliTerm:
     const: complex
     names: tuple[str, ...]
     paulis: tuple[tuple[int, str], ...]  # sorted ((qubit, 'X'|'Y'|'Z'), ...)
+    expr: str = ""  # time-dependent generators only: symbolic factor of the term, "sin(0.7*t)*x|t,x" (see parse_td_expr)
 
     def to_json(self) -> dict:
-        return {
+        d = {
             "const": [float(np.real(self.const)), float(np.imag(self.const))],
             "names": list(self.names),
             "paulis": [[q, p] for q, p in self.paulis],
         }
+        if self.expr:
+            d["expr"] = self.expr
+        return d
 
     @staticmethod
     def from_json(d: dict) -> "PauliTerm":
@@ -65,6 +69,7 @@ class PauliTerm:
             complex(d["const"][0], d["const"][1]),
             tuple(d["names"]),
             tuple((int(q), str(p)) for q, p in d["paulis"]),
+            d.get("expr", ""),
         )
 
 
@@ -93,13 +98,17 @@ class PauliSum:
         acc: dict[tuple, complex] = {}
         order: list[tuple] = []
         for t in self.terms:
-            key = (tuple(sorted(t.names)), t.paulis)
+            key = (tuple(sorted(t.names)), t.paulis, t.expr)
             if key not in acc:
                 acc[key] = 0j
                 order.append(key)
             acc[key] += t.const
-        terms = [PauliTerm(acc[k], k[0], k[1]) for k in order if acc[k] != 0]
+        terms = [PauliTerm(acc[k], k[0], k[1], k[2]) for k in order if acc[k] != 0]
         return PauliSum(self.n_qubits, terms)
+
+    @property
+    def is_time_dependent(self) -> bool:
+        return any(t.expr for t in self.terms)
 
     def to_json(self) -> dict:
         return {"n_qubits": self.n_qubits, "terms": [t.to_json() for t in self.terms]}
@@ -119,11 +128,15 @@ class Op:
     subs: list["Program"] | None = None  # ADD
     generator: Any = None  # HAMEVO: PauliSum | Program | np.ndarray [2^k,2^k] | str (key of a matrix value)
     label: str = ""  # reference op name, for diagnostics only
+    tsym: str = ""  # HAMEVO with a time-dependent generator: name of the time symbol; `param` is then the DURATION
+    steps: int = 0  # ... and the number of integration steps (Configuration.n_steps_hevo)
 
     def to_json(self) -> dict:
         d: dict[str, Any] = {"kind": int(self.kind), "t": list(self.targets), "c": list(self.controls)}
         if self.label:
             d["label"] = self.label
+        if self.tsym:
+            d["tsym"], d["steps"] = self.tsym, self.steps
         if self.param is not None:
             if isinstance(self.param, str):
                 d["p"] = self.param
@@ -180,6 +193,8 @@ class Op:
             subs=[Program.from_json(s) for s in d["subs"]] if "subs" in d else None,
             generator=gen,
             label=d.get("label", ""),
+            tsym=d.get("tsym", ""),
+            steps=int(d.get("steps", 0)),
         )
 
 
@@ -215,6 +230,8 @@ class Program:
             if isinstance(op.generator, PauliSum):
                 for nm in op.generator.param_names:
                     add(nm)
+                for nm in time_dependent_symbols(op.generator, op.tsym):
+                    add(nm)
             elif isinstance(op.generator, str):
                 add(op.generator)
         return out
@@ -240,6 +257,36 @@ class Program:
     @staticmethod
     def loads(s: str) -> "Program":
         return Program.from_json(json.loads(s))
+
+
+def parse_td_expr(s: str):
+    """`PauliTerm.expr` is "<sympy expression>|<comma-separated symbol names>" (the explicit symbol list keeps names such
+    as `E`, `I`, `S`, `N` from being parsed as sympy singletons).  Returns (expression, [symbol names])."""
+    import sympy
+
+    body, _, names = s.partition("|")
+    syms = [nm for nm in names.split(",") if nm]
+    expr = sympy.sympify(body, locals={nm: sympy.Symbol(nm) for nm in syms})
+    return expr, sorted(str(x) for x in expr.free_symbols)
+
+
+def make_td_expr(expr: Any) -> str:
+    return f"{expr}|{','.join(sorted(str(x) for x in expr.free_symbols))}"
+
+
+def time_dependent_symbols(ps: "PauliSum", tsym: str) -> list[str]:
+    """Free symbols (other than the time symbol) of a time-dependent generator's coefficient expressions."""
+    out: list[str] = []
+    for t in ps.terms:
+        if t.expr:
+            for sname in parse_td_expr(t.expr)[1]:
+                if sname != tsym and sname not in out:
+                    out.append(sname)
+    return out
+
+
+def hamevo_td(self: "ProgramBuilder", generator: "PauliSum", duration: Param, tsym: str = "t", steps: int = 100) -> "ProgramBuilder":
+    return self._add(Op(OpKind.HAMEVO, (), (), param=duration, generator=generator, label="HamEvo(t)", tsym=tsym, steps=steps))
 
 
 # ---------------------------------------------------------------------------
@@ -388,3 +435,6 @@ def hea_program(n_qubits: int, depth: int, prefix: str = "theta") -> Program:
 def total_magnetization(n_qubits: int) -> PauliSum:
     """Σ_q Z_q — `qadence.constructors.total_magnetization` (constructors/hamiltonians.py)."""
     return PauliSum(n_qubits, [PauliTerm(1.0 + 0j, (), ((q, "Z"),)) for q in range(n_qubits)])
+
+
+ProgramBuilder.hamevo_td = hamevo_td  # type: ignore[attr-defined]

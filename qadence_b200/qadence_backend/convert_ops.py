@@ -86,7 +86,7 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
     if isinstance(block, TimeEvolutionBlock):
         gen = block.generator
         if getattr(gen, "is_time_dependent", False):
-            raise NotImplementedError("time-dependent HamEvo generators are not supported by b200sv yet")
+            return [_convert_time_dependent(block, n_qubits, config)]
         names = config.get_param_name(block)
         if isinstance(gen, sympy.Basic):  # symbolic matrix generator: looked up in param_values (convert_ops.py:231-232)
             generator: Any = names[1]
@@ -151,6 +151,46 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
     )
 
 
+def _convert_time_dependent(block: Any, n_qubits: int, config: Any) -> Op:
+    """HamEvo whose generator carries a TimeParameter: the reference switches to expression-level parameter names,
+    takes `duration` from the block and hands the generator to pyqtorch's ODE solvers with `n_steps_hevo` steps
+    (backends/pyqtorch/convert_ops.py:227-231,258-268).  Here the generator becomes a Pauli sum whose coefficients keep
+    their symbolic time dependence; the engine integrates it with `n_steps_hevo` exponential-midpoint steps."""
+    config._use_gate_params = False
+    times = {str(s_) for s_ in _scale_symbols(block.generator) if getattr(s_, "is_time", False)}
+    if len(times) != 1:
+        raise NotImplementedError(f"time-dependent HamEvo needs exactly one TimeParameter, found {sorted(times)}")
+    try:
+        ps = to_pauli_sum(block.generator, n_qubits, config, symbolic=True)
+    except NotPauliLike as e:
+        raise NotImplementedError(f"time-dependent HamEvo generator is not a sum of Pauli-like strings ({e})") from e
+    for t in ps.terms:
+        if abs(complex(t.const).imag) > 1e-12:
+            raise ValueError("HamEvo generator must be Hermitian")
+    duration = block.duration
+    if isinstance(duration, sympy.Basic) and duration.free_symbols:
+        dur: Any = config.get_param_name(block)[1]  # ("t", "duration", ...) — convert_ops.py:263
+    else:
+        dur = float(_numeric(duration))
+    return Op(OpKind.HAMEVO, tuple(block.qubit_support), (), param=dur, generator=ps, label="HamEvo(t)",
+              tsym=times.pop(), steps=int(config.n_steps_hevo))
+
+
+def _scale_symbols(block: Any) -> set:
+    from qadence.blocks import CompositeBlock, ScaleBlock
+
+    out: set = set()
+    if isinstance(block, ScaleBlock):
+        p = block.parameters.parameter
+        if isinstance(p, sympy.Basic):
+            out |= set(p.free_symbols)
+        out |= _scale_symbols(block.block)
+    elif isinstance(block, CompositeBlock):
+        for b in block.blocks:
+            out |= _scale_symbols(b)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # Pauli-sum extraction (observables, HamEvo generators)
 # ---------------------------------------------------------------------------------------------------
@@ -158,11 +198,27 @@ class NotPauliLike(Exception):
     pass
 
 
-def _terms(block: Any, config: Any) -> list[tuple[complex, tuple[str, ...], dict[int, np.ndarray]]]:
-    """Expand a block into Σ const·Π names · ⊗_q (2x2 matrix on q); raises NotPauliLike otherwise."""
+_EXPR = "\0expr:"  # marker of a symbolic (time-dependent) factor inside a term's `names` tuple
+
+
+def _terms(block: Any, config: Any, symbolic: bool = False) -> list[tuple[complex, tuple[str, ...], dict[int, np.ndarray]]]:
+    """Expand a block into Σ const·Π names · ⊗_q (2x2 matrix on q); raises NotPauliLike otherwise.
+    With `symbolic`, non-numeric scales are kept as sympy expressions (time-dependent generators)."""
     from qadence.blocks import AddBlock, ChainBlock, KronBlock, ParametricBlock, PrimitiveBlock, ScaleBlock
     from qadence.blocks.primitive import ProjectorBlock
 
+    if symbolic:
+        _t = lambda b: _terms(b, config, True)  # noqa: E731
+    else:
+        _t = lambda b: _terms(b, config)  # noqa: E731
+    if isinstance(block, ScaleBlock) and symbolic:
+        inner = _t(block.block)
+        p = block.parameters.parameter
+        if isinstance(p, sympy.Basic) and p.free_symbols:
+            key = str(len(_SYMS))
+            _SYMS[key] = p
+            return [(c, (*nm, _EXPR + key), f) for c, nm, f in inner]
+        return [(c * complex(_numeric(p)), nm, f) for c, nm, f in inner]
     if isinstance(block, ScaleBlock):
         inner = _terms(block.block, config)
         p = extract_parameter(block, config)
@@ -170,13 +226,13 @@ def _terms(block: Any, config: Any) -> list[tuple[complex, tuple[str, ...], dict
             return [(c, (*nm, p), f) for c, nm, f in inner]
         return [(c * complex(p), nm, f) for c, nm, f in inner]
     if isinstance(block, AddBlock):
-        return list(itertools.chain.from_iterable(_terms(b, config) for b in block.blocks))
+        return list(itertools.chain.from_iterable(_t(b) for b in block.blocks))
     if isinstance(block, (ChainBlock, KronBlock)):
         acc: list[tuple[complex, tuple[str, ...], dict[int, np.ndarray]]] = [(1.0 + 0j, (), {})]
         for b in block.blocks:  # later blocks act after earlier ones: factor_q <- new_q @ factor_q
             nxt = []
             for c1, n1, f1 in acc:
-                for c2, n2, f2 in _terms(b, config):
+                for c2, n2, f2 in _t(b):
                     f = dict(f1)
                     for q, mat in f2.items():
                         f[q] = mat @ f[q] if q in f else mat
@@ -199,10 +255,26 @@ def _terms(block: Any, config: Any) -> list[tuple[complex, tuple[str, ...], dict
     raise NotPauliLike(type(block).__name__)
 
 
-def to_pauli_sum(block: Any, n_qubits: int, config: Any) -> PauliSum:
+_SYMS: dict[str, Any] = {}  # id → sympy expression, filled while a symbolic expansion is in flight
+
+
+def to_pauli_sum(block: Any, n_qubits: int, config: Any, symbolic: bool = False) -> PauliSum:
     """Σ coef·(Pauli string) in the {I,X,Y,Z} basis; N, projectors, S, T, H ... are expanded."""
+    from ..program import make_td_expr
+
     out: list[PauliTerm] = []
-    for const, names, factors in _terms(block, config):
+    _SYMS.clear()
+    for const, names, factors in _terms(block, config, symbolic):
+        expr = ""
+        sym = [_SYMS[nm[len(_EXPR):]] for nm in names if nm.startswith(_EXPR)]
+        if sym:
+            prod = sympy.Integer(1)
+            for e_ in sym:
+                prod = prod * e_
+            num, rest = prod.as_coeff_Mul()
+            const = const * complex(num)
+            expr = make_td_expr(rest) if rest.free_symbols else ""
+            names = tuple(nm for nm in names if not nm.startswith(_EXPR))
         comps: list[list[tuple[str, complex]]] = []
         qubits = sorted(factors)
         for q in qubits:
@@ -223,7 +295,7 @@ def to_pauli_sum(block: Any, n_qubits: int, config: Any) -> PauliSum:
                 c *= cp
                 if p != "I":
                     paulis.append((q, p))
-            out.append(PauliTerm(c, tuple(names), tuple(paulis)))
+            out.append(PauliTerm(c, tuple(names), tuple(paulis), expr))
     return PauliSum(n_qubits, out).simplified()
 
 

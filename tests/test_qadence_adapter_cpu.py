@@ -270,3 +270,45 @@ def test_qnn_training_step_through_the_plugin(oracle_device) -> None:
         losses.append(loss.item())
     assert losses[-1] < losses[0]
     assert all(p.grad is not None for p in model.parameters() if p.requires_grad)
+
+
+def test_time_dependent_hamevo_conversion() -> None:
+    """The reference's own time-dependent generator (tests/conftest.py:261-266) becomes a symbolic-coefficient Pauli sum with
+    `duration` as the evolution parameter and `n_steps_hevo` steps (backends/pyqtorch/convert_ops.py:227-231,258-268)."""
+    import sympy
+    from qadence.parameters import Parameter, TimeParameter
+
+    from tests.test_time_dependent import FY, OMEGA, X as Xm, Y as Ym, I2, ode_solution
+
+    t, x = TimeParameter("t"), Parameter("x", trainable=False)
+    gen = OMEGA * (sympy.sin(FY * t) * qadence.X(0) + x * (t**2) * qadence.Y(1))
+    bk = backend_factory("b200sv", diff_mode=None, configuration={"n_steps_hevo": 500})
+    conv = bk.convert(QuantumCircuit(2, qadence.HamEvo(gen, "t")))
+    (op,) = conv.circuit.native.program.ops
+    assert (op.tsym, op.steps, op.param) == ("t", 500, "duration")
+    assert sorted(tm.expr for tm in op.generator.terms) == [f"sin({FY}*t)|t", "t**2*x|t,x"]
+    assert bk.config._use_gate_params is False
+    emb = conv.embedding_fn(conv.params, {"x": torch.tensor(2.0), "duration": torch.tensor(1.0)})
+    out = oracle.run(conv.circuit.native.program, emb)[0].numpy()
+    want = ode_solution(lambda s: OMEGA * (np.sin(FY * s) * np.kron(Xm, I2) + 2.0 * s**2 * np.kron(I2, Ym)), 4, 1.0)
+    assert np.abs(out - want).max() < 5e-6
+
+
+@pytest.mark.parametrize("duration", [0.5, 1.0])
+def test_time_dependent_hamevo_through_quantum_model(oracle_device, duration: float) -> None:
+    """Mirror of the reference's tests/backends/pyq/test_time_dependent_generator.py:25-62 with the ODE solution in
+    place of qutip (not installed here) and the reference's own acceptance (MIDDLE_ACCEPTANCE = 6e-2 → we ask 1e-5)."""
+    import sympy
+    from qadence.parameters import Parameter, TimeParameter
+
+    from tests.test_time_dependent import FY, OMEGA, X as Xm, Y as Ym, I2, ode_solution
+
+    t, x = TimeParameter("t"), Parameter("x", trainable=False)
+    hamevo = qadence.HamEvo(OMEGA * (sympy.sin(FY * t) * qadence.X(0) + x * (t**2) * qadence.Y(1)), "t")
+    values = {"x": torch.tensor(2.0), "duration": torch.tensor(duration)}
+    model = QuantumModel(QuantumCircuit(2, hamevo), backend="b200sv", diff_mode=DiffMode.AD, configuration={"n_steps_hevo": 500})
+    state = model.run(values=values)
+    want = ode_solution(lambda s: OMEGA * (np.sin(FY * s) * np.kron(Xm, I2) + 2.0 * s**2 * np.kron(I2, Ym)), 4, duration)
+    assert np.abs(state[0].numpy() - want).max() < 1e-5
+    state1 = qadence.run(hamevo, values=values, backend="b200sv", configuration={"n_steps_hevo": 500})
+    assert torch.allclose(state, state1)

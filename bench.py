@@ -26,6 +26,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 N_QUBITS, DEPTH, BATCH = 20, 8, 256
+FP64_PEAK_TFLOPS = 33.9  # measured on this pool's B200 with tools/ubench/dmma.cu (16 independent DFMA chains per thread)
 CPU_SAMPLE_BATCH = 4  # parameter sets per CPU step (≈ 10-20 s of host work)
 WORKLOAD = ("cfg2: hea(n_qubits=20, depth=8) expectation of total_magnetization + adjoint gradients of 480 parameters, "
             "batch 256 per GPU, complex128")
@@ -306,6 +307,13 @@ def main() -> None:
     achieved = 4 * S / (adj_avg * 1e-3) / 1e9
     fwd_achieved = 2 * S / (fwd_avg * 1e-3) / 1e9
 
+    # FP64 pipe view of the same step: every merged 2x2 costs 8 FP64 instructions per amplitude going forward and
+    # 24 going backward (un-apply on psi and lambda + the four gradient moments), see DESIGN.md §4.1
+    n_chain_f = int((fwd.plan.rounds["mslot"] >= 0).sum())
+    n_chain_a = int((adj.plan.rounds["mslot"] >= 0).sum())
+    fp64_instr = (8 * n_chain_f + 24 * n_chain_a) * float(BATCH) * float(1 << N_QUBITS)
+    fp64_tflops = 2 * fp64_instr / (ms_per_step * 1e-3) / 1e12
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -335,7 +343,11 @@ def main() -> None:
                          "forward_sweep": {"achieved": fwd_achieved, "frac": fwd_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": fwd_avg},
                          "light_sweep": {"what": "same kernel, one round of three merged 2x2 (6 gates) per sweep", "achieved": light_achieved,
                                          "frac": light_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": light_ms},
-                         "note": "complex128 sweeps with ~10 merged 2x2 per tile are FP64-issue bound on B200 (an FP64 instruction holds the issue port 2 cycles), see DESIGN.md §4.1"},
+                         "fp64_pipe": {"what": "whole step: FP64 instructions of the merged 2x2 applications and gradient moments (counted from the plan) vs the DFMA rate measured by tools/ubench/dmma.cu",
+                                       "merged_2x2_fwd": n_chain_f, "merged_2x2_adj": n_chain_a, "achieved": fp64_tflops, "peak": FP64_PEAK_TFLOPS,
+                                       "unit": "TFLOP/s", "frac": fp64_tflops / FP64_PEAK_TFLOPS,
+                                       "floor_ms_per_step": 2 * fp64_instr / (FP64_PEAK_TFLOPS * 1e12) * 1e3},
+                         "note": "complex128 sweeps with ~10 merged 2x2 per tile are FP64-pipe/issue bound on B200, not HBM bound (an FP64 instruction holds the issue port 2 cycles; DMMA runs at the same pipe rate), see DESIGN.md §4.1 and profiles/r01_fp64_microbench.md"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

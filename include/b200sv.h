@@ -253,6 +253,35 @@ int b200sv_bit_reverse(const void* in, void* out, int dtype, int n_qubits, int64
 int b200sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, int64_t batch,
                         const int32_t* perm, void* stream);
 
+/* Device-side parameter embedding (replaces the per-call host loop of qadence/blocks/embedding.py:118-167, which
+ * evaluates one sympytorch module per unique expression and builds a dict, and its autograd graph).
+ * Every slot of the gate-parameter table is a small expression DAG over root parameters, stored as `b200sv_enode`
+ * records in topological order (operands `a`, `b` are node indices relative to the slot's first node; the slot's value is
+ * its last node):
+ *     out[slot][e] = f_slot(var[0..], feat[0..][e])            forward
+ *     gloads[L][e] = gout[slot][e] * d f_slot / d(load L)      backward: one row per VAR / FEAT node (`load` = L)
+ * `var` holds the batch-independent (variational) roots, `feat` is [n_feat][batch] (feature inputs).  The function set is
+ * the reference's SYMPY_TO_PYQ_MAPPING (backends/pyqtorch/convert_ops.py:46-61).  Slots are limited to 32 nodes. */
+enum {
+  B200SV_EO_CONST = 0, /* arg = index into consts */
+  B200SV_EO_VAR = 1,   /* arg = index into var,  load = row of gloads */
+  B200SV_EO_FEAT = 2,  /* arg = row of feat,     load = row of gloads */
+  B200SV_EO_ADD = 3, B200SV_EO_MUL = 4, B200SV_EO_POW = 5,
+  B200SV_EO_SIN = 6, B200SV_EO_COS = 7, B200SV_EO_TAN = 8, B200SV_EO_TANH = 9, B200SV_EO_LOG = 10, B200SV_EO_EXP = 11,
+  B200SV_EO_ACOS = 12, B200SV_EO_ASIN = 13, B200SV_EO_ATAN = 14, B200SV_EO_ABS = 15,
+  B200SV_EO_HEAVISIDE = 16 /* 0 / 0.5 / 1, zero gradient (parameters.py:196-205) */
+};
+#define B200SV_EMBED_MAX_NODES 32
+typedef struct b200sv_enode {
+  int32_t op, a, b, arg, load, pad0, pad1, pad2;
+} b200sv_enode;
+
+int b200sv_embed_forward(const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts,
+                         const double* var, const double* feat, int64_t batch, double* out, void* stream);
+int b200sv_embed_backward(const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts,
+                          const double* var, const double* feat, int64_t batch, const double* gout,
+                          double* gloads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

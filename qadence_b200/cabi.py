@@ -37,6 +37,8 @@ EXPORTS = [
     "b200sv_sample",
     "b200sv_bit_reverse",
     "b200sv_permute_bits",
+    "b200sv_embed_forward",
+    "b200sv_embed_backward",
 ]
 
 
@@ -98,6 +100,8 @@ def load() -> C.CDLL:
         "b200sv_sample": [vp, i32, i32, i64, vp, vp, vp, i64, vp, vp],
         "b200sv_bit_reverse": [vp, vp, i32, i32, i64, vp],
         "b200sv_permute_bits": [vp, vp, i32, i32, i64, vp, vp],
+        "b200sv_embed_forward": [vp, vp, i32, vp, vp, vp, i64, vp, vp],
+        "b200sv_embed_backward": [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)

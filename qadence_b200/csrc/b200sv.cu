@@ -853,3 +853,105 @@ int b200sv_bit_reverse(const void* in, void* out, int dtype, int n, int64_t batc
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Device-side parameter embedding: one thread per (slot, batch element), slot uniform per CTA row
+// ------------------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(128) embed_kernel(const b200sv_enode* __restrict__ nodes, const int32_t* __restrict__ slot_off,
+                                                    const double* __restrict__ consts, const double* __restrict__ var,
+                                                    const double* __restrict__ feat, long long batch, const double* __restrict__ gout,
+                                                    double* __restrict__ out) {
+  const int slot = blockIdx.y;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch) return;
+  const int first = slot_off[slot], n = slot_off[slot + 1] - first;
+  const b200sv_enode* nd = nodes + first;
+  double val[B200SV_EMBED_MAX_NODES];
+  for (int i = 0; i < n; ++i) {
+    const b200sv_enode q = nd[i];
+    const double x = (q.op >= B200SV_EO_ADD) ? val[q.a] : 0.0;
+    double r;
+    switch (q.op) {
+      case B200SV_EO_CONST: r = consts[q.arg]; break;
+      case B200SV_EO_VAR: r = var[q.arg]; break;
+      case B200SV_EO_FEAT: r = feat[(long long)q.arg * batch + e]; break;
+      case B200SV_EO_ADD: r = x + val[q.b]; break;
+      case B200SV_EO_MUL: r = x * val[q.b]; break;
+      case B200SV_EO_POW: r = pow(x, val[q.b]); break;
+      case B200SV_EO_SIN: r = sin(x); break;
+      case B200SV_EO_COS: r = cos(x); break;
+      case B200SV_EO_TAN: r = tan(x); break;
+      case B200SV_EO_TANH: r = tanh(x); break;
+      case B200SV_EO_LOG: r = log(x); break;
+      case B200SV_EO_EXP: r = exp(x); break;
+      case B200SV_EO_ACOS: r = acos(x); break;
+      case B200SV_EO_ASIN: r = asin(x); break;
+      case B200SV_EO_ATAN: r = atan(x); break;
+      case B200SV_EO_ABS: r = fabs(x); break;
+      default: r = x > 0.0 ? 1.0 : (x < 0.0 ? 0.0 : 0.5); break;  // HEAVISIDE
+    }
+    val[i] = r;
+  }
+  if constexpr (!BWD) {
+    out[(long long)slot * batch + e] = n > 0 ? val[n - 1] : 0.0;
+  } else {
+  double adj[B200SV_EMBED_MAX_NODES];
+  for (int i = 0; i < n; ++i) adj[i] = 0.0;
+  if (n > 0) adj[n - 1] = gout[(long long)slot * batch + e];
+  for (int i = n - 1; i >= 0; --i) {
+    const b200sv_enode q = nd[i];
+    const double g = adj[i];
+    if (q.op == B200SV_EO_VAR || q.op == B200SV_EO_FEAT) {
+      out[(long long)q.load * batch + e] = g;
+      continue;
+    }
+    if (q.op < B200SV_EO_ADD) continue;
+    const double x = val[q.a];
+    switch (q.op) {
+      case B200SV_EO_ADD: adj[q.a] += g; adj[q.b] += g; break;
+      case B200SV_EO_MUL: adj[q.a] += g * val[q.b]; adj[q.b] += g * x; break;
+      case B200SV_EO_POW: {
+        const double y = val[q.b];
+        adj[q.a] += g * y * pow(x, y - 1.0);
+        if (nd[q.b].op != B200SV_EO_CONST) adj[q.b] += g * val[i] * log(x);
+        break;
+      }
+      case B200SV_EO_SIN: adj[q.a] += g * cos(x); break;
+      case B200SV_EO_COS: adj[q.a] -= g * sin(x); break;
+      case B200SV_EO_TAN: adj[q.a] += g * (1.0 + val[i] * val[i]); break;
+      case B200SV_EO_TANH: adj[q.a] += g * (1.0 - val[i] * val[i]); break;
+      case B200SV_EO_LOG: adj[q.a] += g / x; break;
+      case B200SV_EO_EXP: adj[q.a] += g * val[i]; break;
+      case B200SV_EO_ACOS: adj[q.a] -= g / sqrt(1.0 - x * x); break;
+      case B200SV_EO_ASIN: adj[q.a] += g / sqrt(1.0 - x * x); break;
+      case B200SV_EO_ATAN: adj[q.a] += g / (1.0 + x * x); break;
+      case B200SV_EO_ABS: adj[q.a] += x > 0.0 ? g : (x < 0.0 ? -g : 0.0); break;
+      default: break;  // HEAVISIDE: zero gradient
+    }
+  }
+  }
+}
+
+static int embed_launch(bool bwd, const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts, const double* var,
+                        const double* feat, int64_t batch, const double* gout, double* out, void* stream) {
+  if (!nodes || !slot_off || n_slots < 0 || n_slots > 65535 || batch <= 0 || !out || (bwd && !gout)) return B200SV_E_ARG;
+  if (n_slots == 0) return 0;
+  dim3 grid((unsigned)((batch + 127) / 128), (unsigned)n_slots);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bwd) embed_kernel<true><<<grid, 128, 0, st>>>(nodes, slot_off, consts, var, feat, batch, gout, out);
+  else embed_kernel<false><<<grid, 128, 0, st>>>(nodes, slot_off, consts, var, feat, batch, nullptr, out);
+  LAUNCH_CK();
+  return 0;
+}
+
+extern "C" {
+int b200sv_embed_forward(const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts, const double* var,
+                         const double* feat, int64_t batch, double* out, void* stream) {
+  return embed_launch(false, nodes, slot_off, n_slots, consts, var, feat, batch, nullptr, out, stream);
+}
+int b200sv_embed_backward(const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts, const double* var,
+                          const double* feat, int64_t batch, const double* gout, double* gloads, void* stream) {
+  return embed_launch(true, nodes, slot_off, n_slots, consts, var, feat, batch, gout, gloads, stream);
+}
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""Device-side parameter embedding.
+
+The reference maps user parameters to gate parameters on the host, once per call
+(`qadence/blocks/embedding.py:118-167`): one sympytorch module call per unique expression, a python dict with one
+entry per gate parameter, and an autograd graph with one node chain per entry (≈ 600 entries for a 16-qubit depth-12
+QNN: 12 ms forward + 10 ms packing + 27 ms backward on the host, more than the 30 ms the GPU needs for the circuit).
+Here the expressions are compiled ONCE into a table of small expression DAGs (`b200sv_enode`, include/b200sv.h) and
+evaluated by one kernel launch into the `[n_slots, batch]` gate-parameter table the sweep kernels read; the backward
+pass is one more launch plus two `index_add_`s.  The function set is the reference's `SYMPY_TO_PYQ_MAPPING`
+(`backends/pyqtorch/convert_ops.py:46-61`); anything else makes the caller keep the reference's host embedding.
+
+`ParamTable` is what the compiled embedding returns: a `dict` whose entries (rows of the device table) materialise
+lazily, so qadence code that only forwards `param_values` to the backend never touches per-gate tensors.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Iterable, Iterator, Mapping, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import cabi
+
+ENODE_DT = np.dtype([("op", "<i4"), ("a", "<i4"), ("b", "<i4"), ("arg", "<i4"), ("load", "<i4"), ("pad", "<i4", (3,))])
+MAX_NODES = 32
+(EO_CONST, EO_VAR, EO_FEAT, EO_ADD, EO_MUL, EO_POW, EO_SIN, EO_COS, EO_TAN, EO_TANH, EO_LOG, EO_EXP, EO_ACOS, EO_ASIN, EO_ATAN,
+ EO_ABS, EO_HEAVISIDE) = range(17)
+
+
+class UnsupportedExpression(Exception):
+    """The expression cannot be compiled for the device; the caller keeps the host embedding."""
+
+
+def _unary_ops() -> dict:
+    import sympy
+
+    return {sympy.sin: EO_SIN, sympy.cos: EO_COS, sympy.tan: EO_TAN, sympy.tanh: EO_TANH, sympy.log: EO_LOG, sympy.exp: EO_EXP,
+            sympy.acos: EO_ACOS, sympy.asin: EO_ASIN, sympy.atan: EO_ATAN, sympy.Abs: EO_ABS, sympy.Heaviside: EO_HEAVISIDE}
+
+
+class EmbedProgram:
+    """Expression DAGs of all table rows, host arrays + lazily uploaded device copies."""
+
+    def __init__(self, names: Sequence[str], var_names: Sequence[str], feat_names: Sequence[str], nodes: np.ndarray,
+                 slot_off: np.ndarray, consts: np.ndarray, var_load_root: np.ndarray, feat_load_root: np.ndarray):
+        self.names = list(names)
+        self.var_names = list(var_names)
+        self.feat_names = list(feat_names)
+        self.nodes, self.slot_off, self.consts = nodes, slot_off, consts
+        self.var_load_root, self.feat_load_root = var_load_root, feat_load_root  # load row -> root index
+        self._dev: dict = {}
+
+    @property
+    def n_slots(self) -> int:
+        return len(self.names)
+
+    @property
+    def n_loads(self) -> int:
+        return len(self.var_load_root) + len(self.feat_load_root)
+
+    def device_arrays(self, device: torch.device) -> dict:
+        if device not in self._dev:
+            def up(a: np.ndarray, dtype: torch.dtype | None = None) -> Tensor:
+                raw = np.ascontiguousarray(a)
+                if dtype is None:
+                    raw = raw.view(np.uint8).reshape(-1)
+                    if raw.size == 0:
+                        raw = np.zeros(32, dtype=np.uint8)
+                elif raw.size == 0:
+                    raw = np.zeros(1, dtype=raw.dtype)
+                return torch.from_numpy(raw.copy()).to(device)
+
+            self._dev[device] = {
+                "nodes": up(self.nodes), "slot_off": up(self.slot_off.astype(np.int32), torch.int32),
+                "consts": up(self.consts.astype(np.float64), torch.float64),
+                "var_load_root": torch.from_numpy(self.var_load_root.astype(np.int64)).to(device),
+                "feat_load_root": torch.from_numpy(self.feat_load_root.astype(np.int64)).to(device),
+            }
+        return self._dev[device]
+
+
+def compile_expressions(named_exprs: Sequence[tuple[str, Any]], is_feature: Callable[[str], bool]) -> EmbedProgram:
+    """`named_exprs`: (table row name, sympy expression or python number); `is_feature(symbol name)` splits the free
+    symbols into batch-dependent feature inputs and batch-independent (variational) parameters."""
+    import sympy
+
+    unary = _unary_ops()
+    var_names: list[str] = []
+    feat_names: list[str] = []
+    consts: list[float] = []
+    const_idx: dict[float, int] = {}
+    rows: list[tuple[int, int, int, int, int]] = []  # op, a, b, arg, load (load: provisional (kind, k) resolved below)
+    loads: list[tuple[int, int]] = []  # (0 var | 1 feat, root index)
+    slot_off = [0]
+
+    def const(v: float) -> int:
+        if v not in const_idx:
+            const_idx[v] = len(consts)
+            consts.append(v)
+        return const_idx[v]
+
+    for name, expr in named_exprs:
+        local: list[tuple[int, int, int, int, int]] = []
+        memo: dict = {}
+
+        def emit(e: Any) -> int:
+            if e in memo:
+                return memo[e]
+            if not isinstance(e, sympy.Basic):
+                e = sympy.sympify(e)
+            if e.is_Number or e.is_NumberSymbol:
+                c = complex(e)
+                if c.imag != 0:
+                    raise UnsupportedExpression(f"complex constant {e}")
+                node = (EO_CONST, 0, 0, const(c.real), 0)
+            elif e.is_Symbol:
+                nm = str(e.name if hasattr(e, "name") else e)
+                if is_feature(nm):
+                    if nm not in feat_names:
+                        feat_names.append(nm)
+                    loads.append((1, feat_names.index(nm)))
+                    node = (EO_FEAT, 0, 0, feat_names.index(nm), len(loads) - 1)
+                else:
+                    if nm not in var_names:
+                        var_names.append(nm)
+                    loads.append((0, var_names.index(nm)))
+                    node = (EO_VAR, 0, 0, var_names.index(nm), len(loads) - 1)
+            elif e.func in (sympy.Add, sympy.Mul):
+                op = EO_ADD if e.func is sympy.Add else EO_MUL
+                acc = emit(e.args[0])
+                for arg in e.args[1:-1]:
+                    rhs = emit(arg)
+                    local.append((op, acc, rhs, 0, 0))
+                    acc = len(local) - 1
+                node = (op, acc, emit(e.args[-1]), 0, 0)
+            elif e.func is sympy.Pow:
+                node = (EO_POW, emit(e.args[0]), emit(e.args[1]), 0, 0)
+            elif e.func in unary:
+                node = (unary[e.func], emit(e.args[0]), 0, 0, 0)
+            else:
+                raise UnsupportedExpression(f"{e.func} in {expr}")
+            local.append(node)
+            memo[e] = len(local) - 1
+            return memo[e]
+
+        emit(expr)
+        if len(local) > MAX_NODES:
+            raise UnsupportedExpression(f"expression for '{name}' has {len(local)} nodes (max {MAX_NODES})")
+        rows.extend(local)
+        slot_off.append(len(rows))
+
+    # loads: variational rows first, feature rows after (the backward pass reduces the two groups separately)
+    order = [i for i, (k, _) in enumerate(loads) if k == 0] + [i for i, (k, _) in enumerate(loads) if k == 1]
+    new_row = {old: new for new, old in enumerate(order)}
+    nodes = np.zeros(len(rows), dtype=ENODE_DT)
+    for i, (op, a, b, arg, load) in enumerate(rows):
+        nodes[i] = (op, a, b, arg, new_row[load] if op in (EO_VAR, EO_FEAT) else 0, (0, 0, 0))
+    var_load_root = np.array([loads[i][1] for i in order if loads[i][0] == 0], dtype=np.int64)
+    feat_load_root = np.array([loads[i][1] for i in order if loads[i][0] == 1], dtype=np.int64)
+    return EmbedProgram([nm for nm, _ in named_exprs], var_names, feat_names, nodes, np.array(slot_off, dtype=np.int32),
+                        np.array(consts, dtype=np.float64), var_load_root, feat_load_root)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device evaluation
+# ---------------------------------------------------------------------------------------------------
+def _stream(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _forward_device(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int) -> Tensor:
+    dev = var.device
+    d = prog.device_arrays(dev)
+    out = torch.empty(prog.n_slots, batch, dtype=torch.float64, device=dev)
+    rc = cabi.load().b200sv_embed_forward(d["nodes"].data_ptr(), d["slot_off"].data_ptr(), prog.n_slots, d["consts"].data_ptr(),
+                                          var.data_ptr(), feat.data_ptr(), batch, out.data_ptr(), _stream(dev))
+    cabi.check(rc, "embed_forward")
+    return out
+
+
+def _backward_device(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int, gout: Tensor) -> Tensor:
+    dev = var.device
+    d = prog.device_arrays(dev)
+    gloads = torch.empty(max(1, prog.n_loads), batch, dtype=torch.float64, device=dev)
+    rc = cabi.load().b200sv_embed_backward(d["nodes"].data_ptr(), d["slot_off"].data_ptr(), prog.n_slots, d["consts"].data_ptr(),
+                                           var.data_ptr(), feat.data_ptr(), batch, gout.data_ptr(), gloads.data_ptr(), _stream(dev))
+    cabi.check(rc, "embed_backward")
+    return gloads
+
+
+class _Embed(torch.autograd.Function):
+    """table[slot, e] = f_slot(var, feat[:, e]); the product never evaluates expressions on the host."""
+
+    @staticmethod
+    def forward(ctx, var: Tensor, feat: Tensor, prog: EmbedProgram, batch: int) -> Tensor:  # type: ignore[override]
+        ctx.prog, ctx.batch = prog, batch
+        ctx.save_for_backward(var, feat)
+        return _forward_device(prog, var, feat, batch)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):  # type: ignore[override]
+        var, feat = ctx.saved_tensors
+        prog: EmbedProgram = ctx.prog
+        gl = _backward_device(prog, var, feat, ctx.batch, gout.contiguous())
+        d = prog.device_arrays(var.device)
+        nv = len(prog.var_load_root)
+        gvar = gfeat = None
+        if ctx.needs_input_grad[0]:
+            gvar = torch.zeros_like(var).index_add_(0, d["var_load_root"], gl[:nv].sum(dim=1))
+        if ctx.needs_input_grad[1]:
+            gfeat = torch.zeros_like(feat).index_add_(0, d["feat_load_root"], gl[nv : nv + len(prog.feat_load_root)])
+        return gvar, gfeat, None, None
+
+
+def evaluate(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int) -> Tensor:
+    """`[n_slots, batch]` float64 gate-parameter table on the device of `var`; differentiable w.r.t. var and feat."""
+    return _Embed.apply(var.contiguous(), feat.contiguous(), prog, batch)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the lazily materialised parameter dict
+# ---------------------------------------------------------------------------------------------------
+class ParamTable(dict):
+    """`param_values` backed by one `[n_slots, batch]` device table.  Behaves like the reference's embedded dict
+    (`name -> tensor[batch]`) for anyone who looks inside; `engine` takes the table itself."""
+
+    def __init__(self, names: Sequence[str], table: Tensor, extras: Mapping[str, Any] | None = None,
+                 input_device: torch.device | None = None):
+        super().__init__()
+        self.names = list(names)
+        self.slot = {nm: i for i, nm in enumerate(self.names)}
+        self.table = table
+        self.extras = dict(extras or {})
+        self.input_device = input_device
+        self.clean = True  # False once somebody assigned an entry: the table is then no longer authoritative
+        self._index: dict = {}
+
+    @property
+    def batch(self) -> int:
+        return int(self.table.shape[1])
+
+    # -- mapping protocol ----------------------------------------------------------------------------
+    def __missing__(self, key: str) -> Any:
+        if key in self.slot:
+            v = self.table[self.slot[key]]
+        elif key in self.extras:
+            v = self.extras[key]
+        else:
+            raise KeyError(key)
+        dict.__setitem__(self, key, v)
+        return v
+
+    def __setitem__(self, key: str, value: Any) -> None:
+        self.clean = False
+        dict.__setitem__(self, key, value)
+
+    def __contains__(self, key: object) -> bool:
+        return key in self.slot or key in self.extras or dict.__contains__(self, key)
+
+    def _all_keys(self) -> list[str]:
+        seen = dict.fromkeys(self.names)
+        seen.update(dict.fromkeys(self.extras))
+        seen.update(dict.fromkeys(dict.keys(self)))
+        return list(seen)
+
+    def keys(self):  # type: ignore[override]
+        return self._all_keys()
+
+    def __iter__(self) -> Iterator[str]:
+        return iter(self._all_keys())
+
+    def __len__(self) -> int:
+        return len(self._all_keys())
+
+    def values(self):  # type: ignore[override]
+        return [self[k] for k in self._all_keys()]
+
+    def items(self):  # type: ignore[override]
+        return [(k, self[k]) for k in self._all_keys()]
+
+    def get(self, key: str, default: Any = None) -> Any:
+        return self[key] if key in self else default
+
+    def copy(self) -> dict:  # type: ignore[override]
+        return dict(self.items())
+
+    # -- what the engine uses ------------------------------------------------------------------------
+    def rows(self, names: Sequence[str]) -> Tensor | None:
+        """Table restricted to `names` in that order, or None if a name is not a table row."""
+        names = list(names)
+        if names == self.names:
+            return self.table
+        key = tuple(names)
+        if key not in self._index:
+            if any(nm not in self.slot for nm in names):
+                self._index[key] = None
+            else:
+                self._index[key] = torch.tensor([self.slot[nm] for nm in names], dtype=torch.int64, device=self.table.device)
+        idx = self._index[key]
+        return None if idx is None else self.table.index_select(0, idx)
+
+    def detach(self) -> "ParamTable":
+        out = ParamTable(self.names, self.table.detach(), {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in self.extras.items()},
+                         self.input_device)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# the embedding function handed to qadence (`Converted.embedding_fn`)
+# ---------------------------------------------------------------------------------------------------
+def _resolve_device(device: torch.device | str | None) -> torch.device:
+    cabi.require_device()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, stock_fn: Callable[[dict, dict], dict],
+                      passthrough: bool) -> Callable[[dict, dict], dict]:
+    """embedding_fn(params, inputs) with the signature of qadence/blocks/embedding.py:118; `stock_fn` (the reference's
+    host embedding) is kept for calls this table cannot serve (separate circuit/observable dicts, a variational
+    parameter overridden through `inputs`, multi-element parameters)."""
+    def fn(params: Mapping[str, Any], inputs: Mapping[str, Any]) -> dict:
+        if "circuit" in inputs or "observables" in inputs:
+            return stock_fn(params, inputs)
+        dev = _resolve_device(device)
+        var_rows, feat_rows = [], []
+        for nm in prog.var_names:
+            if nm in inputs or nm not in params:
+                return stock_fn(params, inputs)
+            v = params[nm]
+            if not isinstance(v, Tensor) or v.numel() != 1 or v.is_complex():
+                return stock_fn(params, inputs)
+            var_rows.append(v.reshape(1))
+        batch = 1
+        for nm in prog.feat_names:
+            if nm not in inputs:
+                return stock_fn(params, inputs)
+            v = torch.as_tensor(inputs[nm])
+            if v.is_complex() or v.dim() > 1 and v.numel() != v.shape[0]:
+                return stock_fn(params, inputs)
+            feat_rows.append(v.reshape(-1))
+            batch = max(batch, feat_rows[-1].numel())
+        for nm, v in inputs.items():  # inputs that feed no expression may still set the batch size (qadence/backends/utils.py:169-184)
+            if isinstance(v, Tensor) and v.dim() == 1:
+                batch = max(batch, v.shape[0])
+        if any(r.numel() not in (1, batch) for r in feat_rows):
+            return stock_fn(params, inputs)
+        src = [t for t in (*var_rows, *feat_rows)]
+        input_device = src[0].device if src else torch.device("cpu")
+        var = torch.cat(var_rows).to(device=dev, dtype=torch.float64) if var_rows else torch.zeros(1, dtype=torch.float64, device=dev)
+        if feat_rows:
+            feat = torch.stack([r.expand(batch) for r in feat_rows]).to(device=dev, dtype=torch.float64)
+        else:
+            feat = torch.zeros(1, batch, dtype=torch.float64, device=dev)
+        table = evaluate(prog, var, feat, batch)
+        extras: dict = {}
+        if passthrough:  # expression-level dicts also carry the raw inputs and parameters (embedding.py:155-166)
+            for k, v in {**params, **inputs}.items():
+                t = torch.as_tensor(v)
+                extras[k] = t[None] if t.ndim == 0 else v
+        return ParamTable(prog.names, table, extras, input_device)
+
+    return fn

@@ -20,6 +20,7 @@ import torch
 from torch import Tensor
 
 from . import cabi
+from .embedding import ParamTable
 from .plan import SweepPlan, TileConfig, build_plan, pack_pauli_terms
 from .program import Op, OpKind, PauliSum, Program
 
@@ -213,6 +214,8 @@ class CompiledProgram:
 # ---------------------------------------------------------------------------------------------------
 def infer_batch(values: Mapping[str, Any] | None) -> int:
     """Max leading length of the tensor values (`qadence/backends/utils.py:169-184`)."""
+    if isinstance(values, ParamTable) and values.clean:
+        return values.batch
     b = 1
     for v in (values or {}).values():
         if isinstance(v, Tensor) and v.dim() in (1, 3):  # [B] scalars or [B, k, k] generator matrices; a bare [k, k] matrix is not a batch
@@ -224,6 +227,10 @@ def pack_params(names: Sequence[str], values: Mapping[str, Tensor], batch: int, 
     """[n_slots, batch] float64 device table of gate parameters, differentiable w.r.t. `values`."""
     if not names:
         return torch.zeros(1, batch, dtype=torch.float64, device=device)
+    if isinstance(values, ParamTable) and values.clean and values.table.device == device:
+        tab = values.rows(names)  # device-side embedding: the table is already there
+        if tab is not None and tab.shape[1] in (1, batch):
+            return tab if tab.shape[1] == batch else tab.expand(-1, batch).contiguous()
     rows = []
     for nm in names:
         if nm not in values:
@@ -438,7 +445,8 @@ class _AdjointExpectation(torch.autograd.Function):
         st = prepare_state(cp.n_qubits, batch, state, dtype, device)
         psi = _run_segments(cp, st, ptable, values)
         cols = [o.expectation(psi, values) for o in cobs]
-        ctx.cp, ctx.cobs, ctx.values, ctx.batch = cp, cobs, {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}, batch
+        detached = values.detach() if isinstance(values, ParamTable) else {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}
+        ctx.cp, ctx.cobs, ctx.values, ctx.batch = cp, cobs, detached, batch
         ctx.psi = psi
         ctx.save_for_backward(ptable)
         return torch.stack(cols, dim=1)
@@ -512,7 +520,7 @@ def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], 
     """`[B, n_obs]` real expectation values, differentiable (adjoint method) w.r.t. every tensor in `values`
     that feeds a gate parameter or an observable coefficient."""
     dev = _dev(device)
-    values = dict(values or {})
+    values = values if isinstance(values, ParamTable) else dict(values or {})
     B = infer_batch(values)
     if state is not None:
         B = max(B, state.shape[0])

@@ -14,6 +14,7 @@ from dataclasses import dataclass, field
 from logging import getLogger
 from typing import Any
 
+import sympy
 import torch
 from torch import Tensor
 
@@ -29,6 +30,7 @@ from qadence.transpile import flatten, scale_primitive_blocks_only, transpile
 from qadence.types import BackendName, Endianness, Engine, ParamDictType
 
 from .. import engine
+from ..embedding import ParamTable, UnsupportedExpression, compile_expressions, make_embedding_fn
 from ..program import Program
 from .config import Configuration, default_passes
 from .convert_ops import convert_block, convert_observable
@@ -98,11 +100,55 @@ def _result_device(cfg: Configuration, *dicts: Any) -> torch.device | None:
     for d in dicts:
         if isinstance(d, Tensor):
             devs.add(d.device)
+        elif isinstance(d, ParamTable):
+            if d.input_device is not None:
+                devs.add(d.input_device)
         elif isinstance(d, dict):
             devs |= {v.device for v in d.values() if isinstance(v, Tensor)}
     if any(dv.type == "cuda" for dv in devs):
         return None
     return torch.device("cpu")
+
+
+def _device_embedding_fn(conv: Converted, config: Configuration) -> Any:
+    """Compile the expressions behind every gate / observable parameter of `conv` for the device
+    (replaces the per-call host loop of qadence/blocks/embedding.py:118-167; see qadence_b200/embedding.py)."""
+    from qadence.blocks.utils import expressions, parameters, uuid_to_expression
+    from qadence.parameters import stringify
+
+    blocks = [conv.circuit.abstract.block] + [o.abstract for o in (conv.observable or [])]
+    needed: list[str] = list(conv.circuit.native.program.param_names)
+    for o in conv.observable or []:
+        for nm in o.native.compiled.names:
+            if nm not in needed:
+                needed.append(nm)
+    symbols: dict[str, Any] = {}
+    by_name: dict[str, Any] = {}
+    for blk in blocks:
+        for p in parameters(blk):
+            if isinstance(p, sympy.Array):
+                continue
+            for sym in (p.free_symbols if isinstance(p, sympy.Basic) else ()):
+                symbols[sym.name] = sym
+        if config._use_gate_params:
+            by_name.update(uuid_to_expression(blk))
+        else:
+            for e in expressions(blk):
+                if not isinstance(e, sympy.Array):
+                    by_name[stringify(e)] = e
+    if not config._use_gate_params:
+        for nm, sym in symbols.items():
+            by_name.setdefault(nm, sym)
+    if any(getattr(sym, "is_time", False) for sym in symbols.values()):
+        raise UnsupportedExpression("time-dependent generator")
+    named = []
+    for nm in needed:
+        e = by_name.get(nm)
+        if e is None or isinstance(e, sympy.Array):
+            raise UnsupportedExpression(f"no scalar expression behind parameter '{nm}'")
+        named.append((nm, e))
+    prog = compile_expressions(named, is_feature=lambda nm: not getattr(symbols.get(nm), "trainable", False))
+    return make_embedding_fn(prog, config.device, conv.embedding_fn, passthrough=not config._use_gate_params)
 
 
 @dataclass(frozen=True, eq=True)
@@ -127,7 +173,13 @@ class Backend(BackendInterface):
         `self.engine` names the differentiation engine `backend_factory` imports
         (qadence/backends/api.py:52), while `embedding()` needs the array library (torch)."""
         proxy = dataclasses.replace(self, engine=Engine.TORCH)
-        return BackendInterface.convert(proxy, circuit, observable)
+        conv = BackendInterface.convert(proxy, circuit, observable)
+        if self.config.device_embedding:
+            try:
+                conv = Converted(conv.circuit, conv.observable, _device_embedding_fn(conv, self.config), conv.params)
+            except UnsupportedExpression as e:
+                logger.debug(f"b200sv: keeping the host parameter embedding ({e})")
+        return conv
 
     def circuit(self, circuit: QuantumCircuit) -> ConvertedCircuit:
         passes = self.config.transpilation_passes
@@ -190,7 +242,7 @@ class Backend(BackendInterface):
         n = circuit.abstract.n_qubits
         nat: NativeCircuit = circuit.native
         observable = observable if isinstance(observable, list) else [observable]
-        values = dict(pc)
+        values = pc if isinstance(pc, ParamTable) and po is pc else dict(pc)
         if po is not pc:
             values.update(po)
         out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, self._state_in(state, n),

@@ -46,6 +46,10 @@ class Configuration(BackendConfiguration):
     """CUDA device of the simulation (default: current device)."""
     dtype: str = "complex128"
     """State precision: "complex128" (default, qadence/__init__.py:13-15) or "complex64"."""
+    device_embedding: bool = True
+    """Evaluate the parameter expressions (feature maps, scaled / shared parameters) on the GPU with one kernel launch
+    per call instead of the host loop of qadence/blocks/embedding.py; falls back to the host embedding for
+    expressions outside the reference's SYMPY_TO_PYQ_MAPPING function set."""
     results_on_input_device: bool = True
     """Return wavefunctions / expectations on the device of the parameter tensors (CPU for a default
     `QuantumModel`), so the backend is a drop-in even though it always computes on the GPU."""

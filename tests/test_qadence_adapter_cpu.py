@@ -96,6 +96,9 @@ def test_no_cpu_fallback() -> None:
     conv = bk.convert(QuantumCircuit(2, X(0)))
     with pytest.raises(cabi.B200svError):
         bk.run(conv.circuit, {})
+    conv = bk.convert(QuantumCircuit(2, RX(0, "x")))  # the device-side parameter embedding has no host fallback either
+    with pytest.raises(cabi.B200svError):
+        conv.embedding_fn(conv.params, {"x": torch.tensor([0.1])})
 
 
 # ------------------------------------------------------------------------------------------ conversion
@@ -312,3 +315,104 @@ def test_time_dependent_hamevo_through_quantum_model(oracle_device, duration: fl
     assert np.abs(state[0].numpy() - want).max() < 1e-5
     state1 = qadence.run(hamevo, values=values, backend="b200sv", configuration={"n_steps_hevo": 500})
     assert torch.allclose(state, state1)
+
+
+# ------------------------------------------------------------------------------------------ device-side embedding
+@pytest.fixture(autouse=True)
+def oracle_embedding_device(request: pytest.FixtureRequest, monkeypatch: pytest.MonkeyPatch) -> None:
+    """Run the compiled embedding through its CPU restatement (test double for the CUDA kernels)."""
+    from oracle import embedding as oemb
+    from qadence_b200 import embedding as emb
+
+    if request.node.name == "test_no_cpu_fallback":
+        return
+
+    monkeypatch.setattr(emb, "evaluate", oemb.evaluate)
+    monkeypatch.setattr(emb, "_resolve_device", lambda device: torch.device("cpu"))
+
+
+def _embedding_circuits():
+    from qadence import BasisSet, ReuploadScaling, feature_map
+    from qadence.parameters import FeatureParameter, VariationalParameter
+
+    n = 3
+    xs, w = FeatureParameter("x"), VariationalParameter("w")
+    return [
+        chain(feature_map(n, param="x", fm_type=BasisSet.CHEBYSHEV, reupload_scaling=ReuploadScaling.TOWER), hea(n, 2)),
+        chain(feature_map(n, param="x", fm_type=BasisSet.FOURIER), feature_map(n, param="y", fm_type=BasisSet.CHEBYSHEV), hea(n, 1)),
+        chain(qadence.RX(0, 2 * w * xs), qadence.RY(1, w), qadence.CRZ(0, 2, sympy_expr_sin(xs) + w**2), qadence.RX(2, 0.3) * (w + 1.5)),
+    ]
+
+
+def sympy_expr_sin(p):
+    import sympy
+
+    return sympy.sin(p)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+@pytest.mark.parametrize("gate_level", [True, False])
+def test_device_embedding_equals_reference_embedding(oracle_embedding_device, idx: int, gate_level: bool) -> None:
+    """Same keys the program needs, same values, same gradients as qadence/blocks/embedding.py:118-167 — in
+    expression-level (AD) and gate-level (ADJOINT) naming."""
+    from qadence_b200.embedding import ParamTable
+
+    block = _embedding_circuits()[idx]
+    circ = QuantumCircuit(3, block)
+    obs = [qadence.total_magnetization(3), 0.5 * qadence.VariationalParameter("ow") * qadence.Z(1)]
+    on = backend_factory("b200sv", diff_mode=DiffMode.ADJOINT)
+    off = backend_factory("b200sv", diff_mode=DiffMode.ADJOINT, configuration={"device_embedding": False})
+    on.backend.config._use_gate_params = off.backend.config._use_gate_params = gate_level
+    conv, ref = on.convert(circ, obs), off.convert(circ, obs)
+    assert list(conv.params) == list(ref.params)
+    rng = np.random.default_rng(idx)
+    inputs = {"x": torch.tensor(rng.uniform(0.1, 0.9, size=5), requires_grad=True), "y": torch.tensor(rng.uniform(0.1, 0.9, size=5))}
+    pa = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in conv.params.items()}
+    pb = {k: pa[k].detach().clone().requires_grad_(v.requires_grad) for k, v in ref.params.items()}  # (qadence re-draws observable parameters per convert)
+    xa = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in inputs.items()}
+    xb = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in inputs.items()}
+    got, want = conv.embedding_fn(pa, xa), ref.embedding_fn(pb, xb)
+    assert isinstance(got, ParamTable) and not isinstance(want, ParamTable)
+    needed = list(conv.circuit.native.program.param_names) + [nm for o in conv.observable for nm in o.native.compiled.names]
+    needed_ref = list(ref.circuit.native.program.param_names) + [nm for o in ref.observable for nm in o.native.compiled.names]
+    assert needed and set(needed) <= set(got.names) and len(needed) == len(needed_ref)  # gate-level names are fresh uuids per convert
+    loss_a = loss_b = 0.0
+    for k, (nm, nm_ref) in enumerate(zip(needed, needed_ref)):
+        a, b = got[nm], want[nm_ref]
+        assert torch.allclose(a.expand(5) if a.numel() == 1 else a, (b.expand(5) if b.numel() == 1 else b).to(torch.float64), atol=1e-13, rtol=0), nm
+        loss_a = loss_a + (k + 1) * a.sum()
+        loss_b = loss_b + (k + 1) * (b.expand(5) if b.numel() == 1 else b).sum()
+    loss_a.backward()
+    loss_b.backward()
+    for k in pa:
+        if pa[k].requires_grad:
+            ga = pa[k].grad if pa[k].grad is not None else torch.zeros_like(pa[k])
+            gb = pb[k].grad if pb[k].grad is not None else torch.zeros_like(pb[k])
+            assert torch.allclose(ga, gb, atol=1e-11), k
+    assert torch.allclose(xa["x"].grad, xb["x"].grad, atol=1e-11)
+    if not gate_level:  # expression-level dicts also pass the raw inputs and parameters through (embedding.py:155-166)
+        assert torch.equal(got["x"], xa["x"]) and set(want) <= set(got.keys())
+
+
+def test_device_embedding_through_quantum_model(oracle_device, oracle_embedding_device) -> None:
+    from qadence import BasisSet, feature_map
+
+    n = 3
+    circ = QuantumCircuit(n, chain(feature_map(n, param="x", fm_type=BasisSet.CHEBYSHEV), hea(n, 2)))
+    obs = qadence.total_magnetization(n)
+    torch.manual_seed(0)
+    m_on = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.ADJOINT)
+    m_off = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.ADJOINT, configuration={"device_embedding": False})
+    m_off.load_state_dict(m_on.state_dict())
+    x = torch.linspace(0.1, 0.9, 4, dtype=torch.float64)
+    e_on, e_off = m_on.expectation({"x": x}), m_off.expectation({"x": x})
+    assert torch.allclose(e_on, e_off, atol=1e-12)
+    e_on.sum().backward()
+    e_off.sum().backward()
+    n_checked = 0
+    for (ka, a), (kb, b) in zip(m_on.named_parameters(), m_off.named_parameters()):
+        if a.requires_grad:
+            assert ka == kb and torch.allclose(a.grad, b.grad, atol=1e-10), ka
+            n_checked += 1
+    assert n_checked == 18
+    assert torch.allclose(m_on.run({"x": x}), m_off.run({"x": x}), atol=1e-12)

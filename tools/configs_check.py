@@ -119,4 +119,61 @@ def cfg4():
 ms4 = timeit(cfg4, reps=5, warm=2)
 out["cfg4"] = {"n": n, "batch_per_gpu": B, "gates": len(prog4.ops), "ms_per_training_step": ms4, "samples_per_s_per_gpu": B / (ms4 * 1e-3),
                "sweeps_fwd": cp4.n_sweeps(), "sweeps_adj": cp4.n_sweeps(adjoint=True)}
+
+# ---- cfg4 as the qadence plugin drives it: CPU nn.Parameters (one per gate), Chebyshev-tower feature map (q+1)*acos(x),
+#      (a) host embedding: one small torch expression per gate parameter, dict -> pack -> H2D (what blocks/embedding.py does)
+#      (b) device embedding: one torch.cat + one H2D + one kernel (qadence_b200/embedding.py)
+import sympy
+
+from qadence_b200 import embedding as E
+
+b = ProgramBuilder(n)
+for q in range(n):
+    b.RX(q, f"fm{q}")
+prog5 = b.build()
+prog5.ops += hea_program(n, 12).ops
+cp5 = engine.CompiledProgram(prog5)
+tnames = [nm for nm in prog5.param_names if not nm.startswith("fm")]
+theta_h = {nm: torch.rand(1, dtype=torch.float64).requires_grad_(True) for nm in tnames}
+x_h = torch.rand(B, dtype=torch.float64) * 1.98 - 0.99
+opt_h = torch.optim.Adam(theta_h.values(), lr=0.01)
+xs = sympy.Symbol("x")
+eprog = E.compile_expressions([(f"fm{q}", (q + 1) * sympy.acos(xs)) for q in range(n)] + [(nm, sympy.Symbol(nm)) for nm in tnames],
+                              lambda nm: nm == "x")
+
+
+def step_host():
+    opt_h.zero_grad()
+    vals = {f"fm{q}": (q + 1) * torch.acos(x_h) for q in range(n)}
+    vals.update(theta_h)
+    e = engine.expectation(cp5, [cob4], vals, device=dev)
+    loss = ((e[:, 0].cpu() - x_h**2) ** 2).mean()
+    loss.backward()
+    opt_h.step()
+
+
+def step_device():
+    opt_h.zero_grad()
+    var = torch.cat([theta_h[nm] for nm in eprog.var_names]).to(dev)
+    feat = x_h.reshape(1, B).to(dev)
+    pt = E.ParamTable(eprog.names, E.evaluate(eprog, var, feat, B), {}, torch.device("cpu"))
+    e = engine.expectation(cp5, [cob4], pt, device=dev)
+    loss = ((e[:, 0].cpu() - x_h**2) ** 2).mean()
+    loss.backward()
+    opt_h.step()
+
+
+def wall(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+out["cfg4_plugin_like"] = {"what": "same circuit, CPU-resident per-gate nn.Parameters + Adam, wall-clock ms per training step",
+                           "host_embedding_ms": wall(step_host), "device_embedding_ms": wall(step_device), "slots": eprog.n_slots}
 print(json.dumps(out, indent=1))

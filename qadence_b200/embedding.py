@@ -201,10 +201,18 @@ class _Embed(torch.autograd.Function):
         return _forward_device(prog, var, feat, batch)
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, gout: Tensor):  # type: ignore[override]
         var, feat = ctx.saved_tensors
         prog: EmbedProgram = ctx.prog
+        if torch.is_grad_enabled() and (gout.requires_grad or var.requires_grad or feat.requires_grad):
+            # create_graph=True (derivatives w.r.t. features inside the loss): differentiate a torch-op evaluation of the
+            # same DAGs on the device, which autograd can differentiate to any order
+            with torch.enable_grad():
+                v = var if var.requires_grad else var.detach().requires_grad_(True)
+                f = feat if feat.requires_grad else feat.detach().requires_grad_(True)
+                out = _evaluate_torch(prog, v, f, ctx.batch)
+                gv, gf = torch.autograd.grad(out, (v, f), gout, create_graph=True, allow_unused=True)
+            return (gv if ctx.needs_input_grad[0] else None), (gf if ctx.needs_input_grad[1] else None), None, None
         gl = _backward_device(prog, var, feat, ctx.batch, gout.contiguous())
         d = prog.device_arrays(var.device)
         nv = len(prog.var_load_root)
@@ -214,6 +222,39 @@ class _Embed(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gfeat = torch.zeros_like(feat).index_add_(0, d["feat_load_root"], gl[nv : nv + len(prog.feat_load_root)])
         return gvar, gfeat, None, None
+
+
+_TORCH_UNARY = {EO_SIN: torch.sin, EO_COS: torch.cos, EO_TAN: torch.tan, EO_TANH: torch.tanh, EO_LOG: torch.log, EO_EXP: torch.exp,
+                EO_ACOS: torch.acos, EO_ASIN: torch.asin, EO_ATAN: torch.atan, EO_ABS: torch.abs}
+
+
+def _evaluate_torch(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int) -> Tensor:
+    """The same DAGs with torch ops on the device — used only under `create_graph=True` (higher-order derivatives)."""
+    rows = []
+    dev = var.device
+    for s in range(prog.n_slots):
+        val: list[Tensor] = []
+        for q in prog.nodes[int(prog.slot_off[s]) : int(prog.slot_off[s + 1])]:
+            op, a, b, arg = int(q["op"]), int(q["a"]), int(q["b"]), int(q["arg"])
+            if op == EO_CONST:
+                r = torch.full((batch,), float(prog.consts[arg]), dtype=torch.float64, device=dev)
+            elif op == EO_VAR:
+                r = var[arg].expand(batch)
+            elif op == EO_FEAT:
+                r = feat[arg]
+            elif op == EO_ADD:
+                r = val[a] + val[b]
+            elif op == EO_MUL:
+                r = val[a] * val[b]
+            elif op == EO_POW:
+                r = torch.pow(val[a], val[b])
+            elif op == EO_HEAVISIDE:
+                r = torch.heaviside(val[a].detach(), torch.tensor(0.5, dtype=torch.float64, device=dev))
+            else:
+                r = _TORCH_UNARY[op](val[a])
+            val.append(r)
+        rows.append(val[-1] if val else torch.zeros(batch, dtype=torch.float64, device=dev))
+    return torch.stack(rows)
 
 
 def evaluate(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int) -> Tensor:

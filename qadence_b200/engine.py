@@ -174,6 +174,7 @@ class CompiledProgram:
         self.names: list[str] = program.param_names
         self.slot_of = {nm: i for i, nm in enumerate(self.names)}
         self.segments: list[Segment] = []
+        self._shift_rules: list[int | None] | None = None
         run: list[Op] = []
         for op in program.ops:
             if op.kind < OpKind.MATK:
@@ -205,6 +206,43 @@ class CompiledProgram:
             tc = cfg or TileConfig.default(dtype == torch.complex128, adjoint)
             seg._plans[key] = DevicePlan(build_plan(seg.gates, self.n_qubits, self.slot_of, tc), device)
         return seg._plans[key]
+
+    def shift_rule(self, slot: int) -> int | None:
+        """Number of terms (2 or 4) of the exact parameter-shift rule of this slot, or None when it has none: the slot
+        must feed exactly one RX / RY / RZ / PHASE gate (possibly controlled) of the top-level circuit."""
+        if self._shift_rules is None:
+            uses: dict[str, list] = {}
+
+            def walk(ops: Sequence[Op], nested: bool) -> None:
+                for op in ops:
+                    if isinstance(op.param, str):
+                        uses.setdefault(op.param, []).append((op.kind, bool(op.controls), nested or bool(op.tsym)))
+                    for sub in op.subs or []:
+                        walk(sub.ops, True)
+                    if isinstance(op.generator, Program):
+                        walk(op.generator.ops, True)
+                    elif isinstance(op.generator, PauliSum):
+                        from .program import time_dependent_symbols
+
+                        for nm in [*op.generator.param_names, *time_dependent_symbols(op.generator, op.tsym)]:
+                            uses.setdefault(nm, []).append((None, False, True))
+                    elif isinstance(op.generator, str):
+                        uses.setdefault(op.generator, []).append((None, False, True))
+
+            walk(self.program.ops, False)
+            rules: list[int | None] = []
+            for nm in self.names:
+                u = uses.get(nm, [])
+                rule = None
+                if len(u) == 1 and not u[0][2]:
+                    kind, controlled, _ = u[0]
+                    if kind == OpKind.PHASE:
+                        rule = 2
+                    elif kind in (OpKind.RX, OpKind.RY, OpKind.RZ):
+                        rule = 4 if controlled else 2
+                rules.append(rule)
+            self._shift_rules = rules
+        return self._shift_rules[slot]
 
     def n_sweeps(self, dtype: torch.dtype = torch.complex128, adjoint: bool = False) -> int:
         tc = TileConfig.default(dtype == torch.complex128, adjoint)
@@ -447,21 +485,31 @@ class _AdjointExpectation(torch.autograd.Function):
         cols = [o.expectation(psi, values) for o in cobs]
         detached = values.detach() if isinstance(values, ParamTable) else {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}
         ctx.cp, ctx.cobs, ctx.values, ctx.batch = cp, cobs, detached, batch
+        ctx.state, ctx.dtype = state, dtype
         ctx.psi = psi
         ctx.save_for_backward(ptable)
         return torch.stack(cols, dim=1)
 
     @staticmethod
     def backward(ctx, grad_out: Tensor):
-        from . import hamevo
-
         (ptable,) = ctx.saved_tensors
-        cp: CompiledProgram = ctx.cp
-        psi: Tensor = ctx.psi
-        values = ctx.values
-        dev = psi.device
-        B = ctx.batch
-        lib = cabi.load()
+        if torch.is_grad_enabled() and (ptable.requires_grad or grad_out.requires_grad):
+            # create_graph=True: hand out a gradient that can itself be differentiated (DQC-style losses)
+            grads = _AdjointGradient.apply(ctx.cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ctx.batch, ptable, grad_out)
+        else:
+            grads = _adjoint_gradient(ctx.cp, ctx.cobs, ctx.values, ctx.batch, ptable, grad_out, ctx.psi)
+        return None, None, None, None, None, None, None, grads
+
+
+def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], values: Mapping[str, Any], B: int, ptable: Tensor,
+                      grad_out: Tensor, psi: Tensor) -> Tensor:
+    """`[n_slots, B]` vector-Jacobian product Σ_o ḡ[b,o]·∂E[b,o]/∂θ[slot,b] by the adjoint method: λ = Σ_o ḡ·O_o ψ, then
+    one backward walk that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps."""
+    from . import hamevo
+
+    dev = psi.device
+    lib = cabi.load()
+    with torch.no_grad():
         if not cp.invertible:
             raise NotImplementedError(
                 "adjoint differentiation needs an invertible circuit (unitary gates, Scale, HamEvo); "
@@ -470,7 +518,7 @@ class _AdjointExpectation(torch.autograd.Function):
         # λ = Σ_o ḡ[:,o] · O_o ψ
         lam = None
         go = grad_out.to(torch.float64)
-        for o, cob in enumerate(ctx.cobs):
+        for o, cob in enumerate(cobs):
             w = go[:, o].to(torch.complex128)
             if cob.pauli is not None:
                 coef = cob.pauli.coef(values, dev)
@@ -511,7 +559,63 @@ class _AdjointExpectation(torch.autograd.Function):
                 lam = apply_dense(lam, md, bits)
             else:
                 raise NotImplementedError(op.kind)
-        return None, None, None, None, None, None, None, grads
+    return grads
+
+
+# parameter-shift rules used ONLY to differentiate the adjoint gradient once more (second order):
+#   two eigenvalues, gap 1 (RX, RY, RZ, PHASE, controlled PHASE):  f' = [f(θ+π/2) − f(θ−π/2)] / 2
+#   controlled rotations (eigenvalues 0, ±1/2: gaps 1/2 and 1):      f' = d₊[f(θ+π/2) − f(θ−π/2)] − d₋[f(θ+3π/2) − f(θ−3π/2)]
+_SQ2 = 2.0 ** 0.5
+SHIFT_RULES = {
+    2: [(np.pi / 2, 0.5), (-np.pi / 2, -0.5)],
+    4: [(np.pi / 2, (_SQ2 + 1) / (4 * _SQ2)), (-np.pi / 2, -(_SQ2 + 1) / (4 * _SQ2)),
+        (3 * np.pi / 2, -(_SQ2 - 1) / (4 * _SQ2)), (-3 * np.pi / 2, (_SQ2 - 1) / (4 * _SQ2))],
+}
+
+
+class _AdjointGradient(torch.autograd.Function):
+    """g = Jᵀḡ as a differentiable function of (θ, ḡ): second and higher derivatives of expectation values.
+
+    Its own backward (cotangent w of g) needs J·w for ḡ and Σ_k w_k ∂_k(Jᵀḡ) for θ.  Both come from exact parameter
+    shifts of the slots k on which w is non-zero — for a DQC loss these are the feature-map gates only — each shifted
+    evaluation being one more forward + adjoint pass on the GPU (and itself differentiable, so third order works too).
+    The reference reaches higher orders by torch autograd through pyqtorch's dense ops (`ml_tools/models.py:27-35`,
+    `create_graph=True`); its own higher-order adjoint is untested (tests/backends/test_adjoint.py:127-248, skipped)."""
+
+    @staticmethod
+    def forward(ctx, cp: CompiledProgram, cobs: list, values: Any, state: Tensor | None, dtype: torch.dtype, batch: int,
+                ptable: Tensor, grad_out: Tensor) -> Tensor:
+        dev = ptable.device
+        st = prepare_state(cp.n_qubits, batch, state, dtype, dev)
+        psi = _run_segments(cp, st, ptable, values)
+        ctx.cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ctx.batch = cp, cobs, values, state, dtype, batch
+        ctx.save_for_backward(ptable, grad_out)
+        return _adjoint_gradient(cp, cobs, values, batch, ptable, grad_out, psi)
+
+    @staticmethod
+    def backward(ctx, w: Tensor):
+        ptable, grad_out = ctx.saved_tensors
+        cp: CompiledProgram = ctx.cp
+        active = torch.nonzero(w.detach().abs().amax(dim=1) > 0).reshape(-1).tolist()
+        d_theta = torch.zeros_like(ptable) if ctx.needs_input_grad[6] else None
+        d_gout = torch.zeros_like(grad_out) if ctx.needs_input_grad[7] else None
+        for k in active:
+            rule = cp.shift_rule(k)
+            if rule is None:
+                raise NotImplementedError(
+                    f"second-order differentiation w.r.t. parameter '{cp.names[k]}' is not supported: it must feed exactly one "
+                    "rotation / phase gate (use gate-level parameter names, or diff_mode='gpsr')")
+            unit = torch.zeros_like(ptable)
+            unit[k] = 1.0
+            for shift, coef in SHIFT_RULES[rule]:
+                theta_s = ptable + shift * unit
+                if d_gout is not None:  # (J w)[b,o] += coef · w[k,b] · E[b,o](θ + s e_k)
+                    e_s = _AdjointExpectation.apply(cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ptable.device, ctx.batch, theta_s)
+                    d_gout = d_gout + coef * w[k][:, None] * e_s.to(d_gout.dtype)
+                if d_theta is not None:  # Σ_k w_k ∂_k g += coef · w[k,b] · g(θ + s e_k)
+                    g_s = _AdjointGradient.apply(cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ctx.batch, theta_s, grad_out)
+                    d_theta = d_theta + coef * w[k][None, :] * g_s
+        return None, None, None, None, None, None, d_theta, d_gout
 
 
 def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], values: Mapping[str, Tensor] | None = None,

@@ -176,4 +176,22 @@ def wall(fn, reps=5, warm=2):
 
 out["cfg4_plugin_like"] = {"what": "same circuit, CPU-resident per-gate nn.Parameters + Adam, wall-clock ms per training step",
                            "host_embedding_ms": wall(step_host), "device_embedding_ms": wall(step_device), "slots": eprog.n_slots}
+
+
+# ---- cfg4, DQC variant: the loss contains dE/dx (create_graph=True), so the optimiser step needs second derivatives:
+#      the adjoint gradient is differentiated by exact shifts of the 16 feature-map gates (2 x 16 more forward+adjoint passes)
+def step_dqc():
+    opt_h.zero_grad()
+    var = torch.cat([theta_h[nm] for nm in eprog.var_names]).to(dev)
+    feat = x_h.reshape(1, B).to(dev).requires_grad_(True)
+    pt = E.ParamTable(eprog.names, E.evaluate(eprog, var, feat, B), {}, torch.device("cpu"))
+    e = engine.expectation(cp5, [cob4], pt, device=dev)[:, 0]
+    (dedx,) = torch.autograd.grad(e.sum(), feat, create_graph=True)
+    loss = ((dedx[0] - feat[0].detach()) ** 2).mean() + (e[0] - 0.5) ** 2
+    loss.backward()
+    opt_h.step()
+
+
+out["cfg4_dqc"] = {"what": "training step whose loss contains dE/dx (second-order differentiation), batch 512, wall-clock ms",
+                   "ms_per_training_step": wall(step_dqc, reps=3, warm=1)}
 print(json.dumps(out, indent=1))

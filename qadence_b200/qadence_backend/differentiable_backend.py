@@ -12,6 +12,9 @@ from __future__ import annotations
 from functools import partial
 from typing import Any
 
+import torch
+from torch import Tensor
+
 from qadence.backend import Backend as QuantumBackend
 from qadence.backend import ConvertedCircuit, ConvertedObservable
 from qadence.backends.parameter_shift_rules import general_psr
@@ -39,6 +42,25 @@ class DifferentiableBackend(DifferentiableBackendInterface):
         endianness: Endianness = Endianness.BIG,
     ) -> Any:
         observable = observable if isinstance(observable, list) else [observable]
+        if measurement is not None:
+            # shot-based protocols (tomography / shadows, qadence/measurements/): qadence's own estimators, drawing their
+            # samples from THIS backend (`Backend.circuit` + `Backend.sample`).  The stock engine forgets to hand the
+            # backend to the estimator in its psr() branch (engines/torch/differentiable_expectation.py:181-190), which
+            # silently falls back to pyqtorch there.
+            measured = partial(
+                measurement.get_measurement_fn(), circuit=circuit.original, observables=[o.original for o in observable],
+                options=measurement.options, state=state, backend=self.backend, noise=noise, endianness=endianness,
+            )
+            if self.diff_mode != DiffMode.GPSR:  # mirrors DifferentiableExpectation.ad(): a plain (non-differentiable) estimate
+                from qadence.ml_tools import promote_to_tensor
+
+                out = measured(param_values=param_values)
+                return promote_to_tensor(out if isinstance(out, Tensor) else torch.tensor(out))
+            from qadence.engines.torch.differentiable_expectation import DifferentiableExpectation, PSRExpectation
+
+            rules = DifferentiableExpectation.construct_rules(circuit.abstract, [o.abstract for o in observable], general_psr, **self.psr_args)
+            shifted = {k: param_values[k] for k in rules.keys()}
+            return PSRExpectation.apply(measured, rules.values(), shifted.keys(), *shifted.values())
         if self.diff_mode == DiffMode.GPSR:
             # qadence's own PSR machinery; torch and its pyqtorch import are only needed lazily here
             from qadence.engines.torch.differentiable_expectation import DifferentiableExpectation
@@ -48,8 +70,6 @@ class DifferentiableBackend(DifferentiableBackendInterface):
                 measurement=measurement, noise=noise, mitigation=mitigation, endianness=endianness,
             )
             return partial(de.psr, psr_fn=general_psr, **self.psr_args)()
-        if measurement is not None:
-            raise NotImplementedError("shot-based measurement protocols are not supported by b200sv (exact expectation only)")
         # AD and ADJOINT: the backend's expectation is itself differentiable (adjoint method)
         return self.backend.expectation(
             circuit=circuit, observable=observable, param_values=param_values, state=state, noise=noise,

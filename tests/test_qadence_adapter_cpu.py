@@ -416,3 +416,47 @@ def test_device_embedding_through_quantum_model(oracle_device, oracle_embedding_
             n_checked += 1
     assert n_checked == 18
     assert torch.allclose(m_on.run({"x": x}), m_off.run({"x": x}), atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ shot-based measurements
+@pytest.mark.parametrize("mode", [DiffMode.AD, DiffMode.GPSR])
+def test_tomography_measurement_samples_from_this_backend(oracle_device, mode) -> None:
+    """`measurement=Measurements("tomography")`: qadence's estimator (measurements/tomography.py:17-70) rotates the circuit
+    into each Pauli basis and calls `backend.circuit` + `backend.sample` of THIS backend; the estimate converges to the
+    exact expectation and, in GPSR mode, stays differentiable through the shift rules."""
+    from qadence import Measurements
+
+    circ = QuantumCircuit(2, chain(RX(0, "x"), RY(1, "t0"), CNOT(0, 1), RX(1, "t1")))
+    obs = qadence.add(Z(0), 0.5 * kron(X(0), Z(1)))
+    torch.manual_seed(3)
+    shots = QuantumModel(circ, obs, backend="b200sv", diff_mode=mode, measurement=Measurements(protocol="tomography", options={"n_shots": 200000}))
+    exact = QuantumModel(circ, obs, backend="b200sv", diff_mode=mode)
+    exact.load_state_dict(shots.state_dict())
+    v = {"x": torch.tensor([0.3, 0.9])}
+    e_s, e_x = shots.expectation(v), exact.expectation(v)
+    assert e_s.shape == e_x.shape == (2, 1)
+    assert (e_s.detach() - e_x.detach()).abs().max() < 0.02  # ~ 4 sigma of two 200k-shot estimates
+    if mode == DiffMode.GPSR:
+        e_s.sum().backward()
+        e_x.sum().backward()
+        n_checked = 0
+        for (ka, a), (kb, b) in zip(shots.named_parameters(), exact.named_parameters()):
+            if a.requires_grad and b.grad is not None:
+                assert a.grad is not None and (a.grad - b.grad).abs().max() < 0.03, ka
+                n_checked += 1
+        assert n_checked == 2
+
+
+def test_classical_shadow_measurement(oracle_device) -> None:
+    """`Measurements("shadow")` (measurements/shadow.py:124-175): one-shot samples of randomly rotated copies of the circuit,
+    all converted and sampled by this backend."""
+    from qadence import Measurements
+
+    np.random.seed(0)
+    circ = QuantumCircuit(2, chain(RX(0, "x"), RY(1, 0.4), CNOT(0, 1)))
+    obs = qadence.add(Z(0), 0.5 * kron(X(0), X(1)))
+    opts = {"accuracy": 0.3, "confidence": 0.1}
+    shots = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.AD, measurement=Measurements(protocol="shadow", options=opts))
+    exact = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.AD)
+    v = {"x": torch.tensor([0.7])}
+    assert (shots.expectation(v).detach() - exact.expectation(v).detach()).abs().max() < 0.45

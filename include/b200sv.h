@@ -253,6 +253,24 @@ int b200sv_bit_reverse(const void* in, void* out, int dtype, int n_qubits, int64
 int b200sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, int64_t batch,
                         const int32_t* perm, void* stream);
 
+/* One register sharded over several GPUs of a box by its highest-order qubits, WITHOUT exchange passes: forward sweeps
+ * [first_sweep, last_sweep) of a plan built for all `n_total` qubits, where `peer_states[r]` is the shard of rank r
+ * (2^(n_total - log2 n_peers) amplitudes; peer_states[rank] is this GPU's own buffer, the others are NVLink peer
+ * mappings opened with b200sv_ipc_open).  Index bits >= n_local select the buffer, so a gate on a "global" qubit is a
+ * sweep whose tiles straddle shards: the exchange that the reference design would do as a separate all-to-all
+ *  is fused into the sweep's own tile loads / stores.  This GPU processes the rank-th slice of the
+ * sweep's tiles; every tile is read and written by exactly one CTA on one GPU.  The CALLER puts a cross-GPU barrier on
+ * the stream between two sweeps.  Tile geometry r must be 3 or 4. */
+int b200sv_apply_plan_peers(void* const* peer_states, int n_peers, int rank, int dtype, int n_total, const double* params,
+                            const b200sv_plan* plan, int first_sweep, int last_sweep, void* workspace, void* stream);
+
+/* Device memory that other processes of the box can map (cudaMalloc + CUDA IPC); `handle64` is 64 opaque bytes to ship to
+ * the peers, who call b200sv_ipc_open (enables peer access lazily) and b200sv_ipc_close. */
+int b200sv_ipc_alloc(int64_t bytes, void** ptr, void* handle64);
+int b200sv_ipc_open(const void* handle64, void** ptr);
+int b200sv_ipc_close(void* ptr);
+int b200sv_ipc_free(void* ptr);
+
 /* Device-side parameter embedding (replaces the per-call host loop of qadence/blocks/embedding.py:118-167, which
  * evaluates one sympytorch module per unique expression and builds a dict, and its autograd graph).
  * Every slot of the gate-parameter table is a small expression DAG over root parameters, stored as `b200sv_enode`

@@ -37,6 +37,11 @@ EXPORTS = [
     "b200sv_sample",
     "b200sv_bit_reverse",
     "b200sv_permute_bits",
+    "b200sv_apply_plan_peers",
+    "b200sv_ipc_alloc",
+    "b200sv_ipc_open",
+    "b200sv_ipc_close",
+    "b200sv_ipc_free",
     "b200sv_embed_forward",
     "b200sv_embed_backward",
 ]
@@ -100,6 +105,11 @@ def load() -> C.CDLL:
         "b200sv_sample": [vp, i32, i32, i64, vp, vp, vp, i64, vp, vp],
         "b200sv_bit_reverse": [vp, vp, i32, i32, i64, vp],
         "b200sv_permute_bits": [vp, vp, i32, i32, i64, vp, vp],
+        "b200sv_apply_plan_peers": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
+        "b200sv_ipc_alloc": [i64, vp, vp],
+        "b200sv_ipc_open": [vp, vp],
+        "b200sv_ipc_close": [vp],
+        "b200sv_ipc_free": [vp],
         "b200sv_embed_forward": [vp, vp, i32, vp, vp, vp, i64, vp, vp],
         "b200sv_embed_backward": [vp, vp, i32, vp, vp, vp, i64, vp, vp, vp],
     }

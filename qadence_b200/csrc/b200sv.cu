@@ -53,16 +53,17 @@ size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool adjoint) {
   return bytes + 256;
 }
 
-template <typename real, int R, bool ADJ, bool GEN>
+template <typename real, int R, bool ADJ, bool GEN, bool PEER = false>
 int launch_sweep(void* psi, void* lam, const double* params, double* grads, const b200sv_plan* plan,
-                 const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st) {
+                 const Workspace<real>& ws, int s, int n, int64_t batch, uint64_t index_hi, int dir, cudaStream_t st,
+                 const PeerTable* peers = nullptr) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
   static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
   const int nbuf = persistent == 1 ? 2 : 1;  // 1: persistent + double buffer, 2: persistent, single buffer (table reuse only)
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
-  auto kern = sweep_kernel<real, R, ADJ, GEN>;
+  auto kern = sweep_kernel<real, R, ADJ, GEN, PEER>;
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -70,8 +71,8 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   }
   const int nt = 1 << (sw.m - R);
   if (nt > SweepCfg<real, R, ADJ>::MAXT) return B200SV_E_ARG;
-  const long long total = ((long long)batch) << sw.n_outer;
-  if (total <= 0) return B200SV_E_ARG;
+  const long long total = PEER ? peers->n_tiles : (((long long)batch) << sw.n_outer);
+  if (total <= 0) return PEER ? 0 : B200SV_E_ARG;  // a rank may have no tile of a very small sweep
   static int resident = 0;  // persistent grid: CTAs that fit on the device at once
   if (resident == 0) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -86,8 +87,52 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   if (grid > 2147483647ll) return B200SV_E_ARG;
   kern<<<(unsigned)grid, nt, smem, st>>>((c2*)psi, (c2*)lam, params, grads, plan->sweeps, plan->rounds,
                                          plan->gates, plan->consts, ws.xtab, ws.mom, s, n, (long long)batch,
-                                         (unsigned long long)index_hi, (dir < 0 ? 0x100 : 0) | dbg_flags, per_cta, nbuf);
+                                         (unsigned long long)index_hi, (dir < 0 ? 0x100 : 0) | dbg_flags, per_cta, nbuf,
+                                         peers ? *peers : PeerTable{});
   LAUNCH_CK();
+  return 0;
+}
+
+// forward sweeps [first, last) of a plan over the FULL index space of a register sharded over `n_peers` GPUs
+// (peer-memory addressing, see PeerTable in sweep.cuh); the caller separates sweeps by a cross-GPU barrier
+template <typename real>
+int run_plan_peers(void* const* peer_states, int n_peers, int rank, int n_total, const double* params, const b200sv_plan* plan,
+                   int first, int last, void* workspace, cudaStream_t st) {
+  if (first >= last) return 0;
+  int g = 0;
+  while ((1 << g) < n_peers) ++g;
+  if ((1 << g) != n_peers || n_peers > 16 || rank < 0 || rank >= n_peers) return B200SV_E_ARG;
+  const Workspace<real> ws = carve_workspace<real>(workspace, plan, 1);
+  const int x_first = plan->sweeps_host[first].first_exec;
+  const int x_count = plan->sweeps_host[last - 1].first_exec + plan->sweeps_host[last - 1].n_exec - x_first;
+  if (x_count > 0) {
+    resolve_kernel<real><<<(unsigned)((x_count + 127) / 128), 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab,
+                                                                          x_first, x_count, 1ll, +1, 0);
+    LAUNCH_CK();
+  }
+  for (int s = first; s < last; ++s) {
+    const b200sv_sweep& sw = plan->sweeps_host[s];
+    if (sw.m < sw.r || sw.m - sw.r > 8 || sw.m > 12 || sw.n_outer != n_total - sw.m) return B200SV_E_ARG;
+    PeerTable pt{};
+    for (int i = 0; i < n_peers; ++i) pt.p[i] = peer_states[i];
+    pt.n_local = n_total - g;
+    const long long tiles = 1ll << sw.n_outer;
+    const long long per_rank = (tiles + n_peers - 1) / n_peers;
+    pt.tile_offset = per_rank * rank;
+    pt.n_tiles = pt.tile_offset >= tiles ? 0 : (pt.tile_offset + per_rank > tiles ? tiles - pt.tile_offset : per_rank);
+    const bool gen = sw.n_gen > 0;
+    int rc = B200SV_E_ARG;
+#define B200SV_LAUNCH_PEER(RR)                                                                                                           \
+  rc = gen ? launch_sweep<real, RR, false, true, true>(peer_states[rank], nullptr, params, nullptr, plan, ws, s, n_total, 1, 0, +1, st, &pt) \
+           : launch_sweep<real, RR, false, false, true>(peer_states[rank], nullptr, params, nullptr, plan, ws, s, n_total, 1, 0, +1, st, &pt)
+    switch (sw.r) {
+      case 3: B200SV_LAUNCH_PEER(3); break;
+      case 4: B200SV_LAUNCH_PEER(4); break;
+      default: return B200SV_E_ARG;  // peer sweeps are built with the large-state tile geometry only
+    }
+#undef B200SV_LAUNCH_PEER
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -946,6 +991,40 @@ static int embed_launch(bool bwd, const b200sv_enode* nodes, const int32_t* slot
 }
 
 extern "C" {
+int b200sv_apply_plan_peers(void* const* peer_states, int n_peers, int rank, int dtype, int n_total, const double* params,
+                            const b200sv_plan* plan, int first_sweep, int last_sweep, void* workspace, void* stream) {
+  if (!peer_states || !plan || n_total < 1 || n_total > 48 || first_sweep < 0 || last_sweep > plan->n_sweeps) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200SV_C128) return run_plan_peers<double>(peer_states, n_peers, rank, n_total, params, plan, first_sweep, last_sweep, workspace, st);
+  if (dtype == B200SV_C64) return run_plan_peers<float>(peer_states, n_peers, rank, n_total, params, plan, first_sweep, last_sweep, workspace, st);
+  return B200SV_E_ARG;
+}
+
+int b200sv_ipc_alloc(int64_t bytes, void** ptr, void* handle64) {
+  if (bytes <= 0 || !ptr || !handle64) return B200SV_E_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaMalloc(ptr, (size_t)bytes));
+  CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
+  return 0;
+}
+int b200sv_ipc_open(const void* handle64, void** ptr) {
+  if (!handle64 || !ptr) return B200SV_E_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int b200sv_ipc_close(void* ptr) {
+  if (!ptr) return B200SV_E_ARG;
+  CK(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+int b200sv_ipc_free(void* ptr) {
+  if (!ptr) return B200SV_E_ARG;
+  CK(cudaFree(ptr));
+  return 0;
+}
+
 int b200sv_embed_forward(const b200sv_enode* nodes, const int32_t* slot_off, int n_slots, const double* consts, const double* var,
                          const double* feat, int64_t batch, double* out, void* stream) {
   return embed_launch(false, nodes, slot_off, n_slots, consts, var, feat, batch, nullptr, out, stream);

@@ -439,14 +439,29 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // cp.async loads of tile k+1 are in flight while tile k is processed.
 // GEN = false: the sweep has no generic-phase entries (pure merged-2x2 + permutation rounds, e.g.
 // every sweep of an HEA): the interpreter is compiled out, which shrinks registers and code.
-template <typename real, int R, bool ADJ, bool GEN>
+// PEER = true: the register is sharded over several GPUs by its highest-order qubits and this kernel addresses ALL
+// shards directly: amplitude index bits >= peers.n_local select the owning GPU's buffer (NVLink peer memory, mapped
+// with CUDA IPC), the rest is the offset inside it.  A gate on a "global" qubit is then just a sweep whose tiles
+// straddle shards — the exchange is fused into the sweep's own tile loads and stores (no separate all-to-all pass,
+// no staging buffer).  Every tile is read and written by exactly one CTA of one GPU, so there is no intra-sweep
+// hazard; sweeps are separated by a cross-GPU barrier on the stream.
+struct PeerTable {
+  void* p[16];            // state buffers of ranks 0..n_peers-1 (p[rank] is the local one)
+  int n_local;            // index bits below this are the offset inside a shard
+  long long tile_offset;  // this GPU processes tiles [tile_offset, tile_offset + n_tiles) of the sweep
+  long long n_tiles;
+};
+
+template <typename real, int R, bool ADJ, bool GEN, bool PEER = false>
 __global__ void __launch_bounds__(SweepCfg<real, R, ADJ>::MAXT, SweepCfg<real, R, ADJ>::MINB)
 sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::type* __restrict__ lam_g,
              const double* __restrict__ params, double* __restrict__ grads,
              const b200sv_sweep* __restrict__ sweeps, const b200sv_round* __restrict__ rounds,
              const b200sv_gate* __restrict__ gates, const double* __restrict__ consts,
              const ExecGate<real>* __restrict__ xtab, double* __restrict__ mom_g, int sweep_idx,
-             int n, long long batch, unsigned long long index_hi, int dir_dbg, long long tiles_per_cta, int nbuf) {
+             int n, long long batch, unsigned long long index_hi, int dir_dbg, long long tiles_per_cta, int nbuf,
+             const PeerTable peers) {
+  static_assert(!(PEER && ADJ), "peer-memory sweeps are forward only");
   constexpr int dir = ADJ ? -1 : +1;  // the adjoint kernel always walks backwards, the plain one forwards
   const int dbg = dir_dbg & 0xff;  // timing experiments only (B200SV_DBG): 1 = skip math, 2 = skip rounds
   using c2 = typename C2<real>::type;
@@ -476,7 +491,13 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   unsigned* rtab = reinterpret_cast<unsigned*>(gsum + (ADJ ? 4 * n_exec * nwarps : 0));
 
   const long long tiles_per_state = 1ll << sw.n_outer;
-  const long long total_tiles = batch << sw.n_outer;
+  const long long total_tiles = PEER ? peers.n_tiles : (batch << sw.n_outer);
+  const long long tile_off = PEER ? peers.tile_offset : 0;
+  const unsigned long long local_mask = PEER ? ((1ull << peers.n_local) - 1ull) : ~0ull;
+  auto gaddr = [&](c2* base_ptr, unsigned long long idx) -> c2* {  // basis index -> address (through the peer table)
+    if constexpr (PEER) return reinterpret_cast<c2*>(peers.p[idx >> peers.n_local]) + (idx & local_mask);
+    else return base_ptr + idx;
+  };
   const long long tile_first = (long long)blockIdx.x * tiles_per_cta;
   long long tile_end = tile_first + tiles_per_cta;
   if (tile_end > total_tiles) tile_end = total_tiles;
@@ -518,7 +539,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   __syncthreads();
 
   auto tile_base = [&](long long t) -> unsigned long long {  // CTA-index bits of tile t deposited into the basis index
-    const unsigned long long c = (unsigned long long)(t % tiles_per_state);
+    const unsigned long long c = (unsigned long long)((t + tile_off) % tiles_per_state);
     unsigned long long base = 0;
     if (sw.n_seg >= 0) {  // runs of consecutive outer bits: a few shifts instead of a bit loop
       for (int k = 0; k < sw.n_seg; ++k)
@@ -535,7 +556,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     for (int i = 0; i < NV; ++i) {
       const int e = i * nt + tid;
       const long long g = off + (long long)(t_lo[e & 63] + t_hi[e >> 6]);
-      cp_async<sizeof(c2)>(dst + swz<real>(e), psi_g + g);
+      cp_async<sizeof(c2)>(dst + swz<real>(e), gaddr(psi_g, (unsigned long long)g));
       if constexpr (ADJ) cp_async<sizeof(c2)>(dst + tile + swz<real>(e), lam_g + g);
     }
     cp_async_commit();
@@ -757,7 +778,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = i * nt + tid;
-      psi_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])] = tile_psi[swz<real>(e)];
+      *gaddr(psi_g, (unsigned long long)(state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6]))) = tile_psi[swz<real>(e)];
     }
     if (ADJ) {
 #pragma unroll

@@ -350,3 +350,164 @@ class QubitShardedSimulator:
         if self.world > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Global-qubit sharding WITHOUT exchange passes: sweeps address every GPU's shard through NVLink peer memory
+# ---------------------------------------------------------------------------------------------------
+class _RawDeviceArray:
+    """Lets torch view device memory that was not allocated by its caching allocator."""
+
+    def __init__(self, ptr: int, n_float64: int):
+        self.__cuda_array_interface__ = {"shape": (n_float64,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class PeerShards:
+    """This rank's shard of a `2^n`-amplitude register plus NVLink mappings of every other rank's shard (CUDA IPC).
+
+    `b200sv_ipc_alloc` (cudaMalloc + cudaIpcGetMemHandle) → 64-byte handles all-gathered over the process group →
+    `b200sv_ipc_open` on every peer.  `ptrs` is the table `b200sv_apply_plan_peers` takes (own buffer at [rank])."""
+
+    def __init__(self, n_local: int, dtype: torch.dtype, rank: int, world: int, device: torch.device, group=None):
+        from . import cabi
+
+        lib = cabi.load()
+        self.rank, self.world, self.device, self.dtype = rank, world, device, dtype
+        elem = 16 if dtype == torch.complex128 else 8
+        self.nbytes = (1 << n_local) * elem
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            cabi.check(lib.b200sv_ipc_alloc(self.nbytes, C.byref(ptr), handle), "ipc_alloc")
+        self.local_ptr = int(ptr.value)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(gathered, mine, group=group)
+        else:
+            gathered = [mine]
+        self._opened: list[int] = []
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(self.local_ptr)
+                continue
+            hb = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
+            p = C.c_void_p()
+            with torch.cuda.device(device):
+                cabi.check(lib.b200sv_ipc_open(hb, C.byref(p)), "ipc_open")
+            self._opened.append(int(p.value))
+            ptrs.append(int(p.value))
+        self.ptrs = (C.c_void_p * world)(*ptrs)
+        real = torch.as_tensor(_RawDeviceArray(self.local_ptr, self.nbytes // 8), device=device)
+        pair = real.view(-1, 2) if dtype == torch.complex128 else real.view(torch.float32).view(-1, 2)
+        self.state = torch.view_as_complex(pair).reshape(1, -1)  # [1, 2^n_local] view of the local shard
+
+    def close(self) -> None:
+        from . import cabi
+
+        lib = cabi.load()
+        if self.local_ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.b200sv_ipc_close(p)
+            if self.world > 1:
+                dist.barrier()
+            lib.b200sv_ipc_free(self.local_ptr)
+        self.local_ptr, self.state, self._opened = None, None, []
+
+
+def peer_traffic(plan, n: int, g: int, elem_bytes: int = 16) -> dict:
+    """NVLink bytes one rank moves per direction over all sweeps of a peer-memory plan: a sweep whose tile contains k of
+    the g rank bits keeps 2^-k of every tile it processes in its own HBM and reads (then writes back) the rest remotely."""
+    shard = (1 << (n - g)) * elem_bytes
+    remote = 0.0
+    ks = []
+    for sw in plan.sweeps:
+        k = sum(1 for b in list(sw["tile_bits"])[: int(sw["m"])] if int(b) >= n - g)
+        ks.append(k)
+        remote += shard * (1.0 - 2.0 ** -k)
+    return {"global_bits_per_sweep": ks, "nvlink_bytes_per_rank_per_direction": int(remote), "hbm_bytes_per_rank": 2 * shard * len(ks)}
+
+
+class PeerShardedSimulator:
+    """`QubitShardedSimulator` with the exchanges fused into the sweeps.
+
+    The plan is the ordinary single-device plan of the whole `n`-qubit program; each rank runs its slice of every
+    sweep's tiles with `b200sv_apply_plan_peers`, which reads and writes the amplitudes wherever they live (own HBM
+    or a peer's over NVLink).  The state never leaves the standard layout (rank = top index bits), there is no
+    staging buffer and no all-to-all; the only collective is the barrier that separates two sweeps."""
+
+    def __init__(self, program: Program, rank: int, world: int, device: torch.device | str | None = None, group=None,
+                 dtype: torch.dtype = torch.complex128):
+        from . import engine
+        from .engine import DevicePlan
+        from .plan import TileConfig, build_plan
+
+        if world & (world - 1) or world > 16:
+            raise ValueError("world size must be a power of two (<= 16)")
+        self.program = program
+        self.n = program.n_qubits
+        self.g = world.bit_length() - 1
+        self.n_local = self.n - self.g
+        self.rank, self.world, self.group, self.dtype = rank, world, group, dtype
+        self.device = engine._dev(device)
+        self.names = program.param_names
+        self.slot_of = {nm: i for i, nm in enumerate(self.names)}
+        cfg = TileConfig.default(dtype == torch.complex128, False)
+        self.plan = DevicePlan(build_plan(list(program.ops), self.n, self.slot_of, cfg), self.device)
+        self.shards = PeerShards(self.n_local, dtype, rank, world, self.device, group)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.time_sweeps = False  # diagnostics: per-sweep CUDA-event times (incl. the barrier) in `sweep_ms`
+        self.sweep_ms: list[float] = []
+        self.stats = {"exchanges": 0, "sweeps": self.plan.n_sweeps, **peer_traffic(self.plan.plan, self.n, self.g, 16 if dtype == torch.complex128 else 8)}
+
+    def n_sweeps(self) -> int:
+        return self.plan.n_sweeps
+
+    def _barrier(self) -> None:
+        """Cross-GPU barrier ON THE STREAM: a 1-element NCCL all-reduce (no host synchronisation)."""
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def run(self, values: Mapping[str, Tensor] | None = None) -> Tensor:
+        """Returns the `[1, 2^n_local]` local shard (a view of the IPC buffer, standard layout) of U|0…0>."""
+        from . import cabi, engine
+
+        lib = cabi.load()
+        st = self.shards.state
+        cabi.check(lib.b200sv_init_zero_state(st.data_ptr(), engine._DT[self.dtype], self.n_local, 1, engine._stream_ptr(self.device)), "init")
+        if self.rank != 0:
+            st[0, 0] = 0
+        ptable = engine.pack_params(self.names, values or {}, 1, self.device)
+        ws = self.plan.workspace(self.dtype, 1, False).data_ptr()
+        self._barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(self.plan.n_sweeps + 1)] if self.time_sweeps else None
+        if ev:
+            ev[0].record()
+        for s in range(self.plan.n_sweeps):
+            rc = lib.b200sv_apply_plan_peers(self.shards.ptrs, self.world, self.rank, engine._DT[self.dtype], self.n, ptable.data_ptr(),
+                                             C.byref(self.plan.struct), s, s + 1, ws, engine._stream_ptr(self.device))
+            cabi.check(rc, "apply_plan_peers")
+            self._barrier()
+            if ev:
+                ev[s + 1].record()
+        if ev:
+            torch.cuda.synchronize(self.device)
+            self.sweep_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(self.plan.n_sweeps)]
+        return st
+
+    def norm2(self, state: Tensor) -> Tensor:
+        from . import engine
+
+        out = engine.dot(state, state).real.clone()
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def close(self) -> None:
+        self.shards.close()

@@ -1,0 +1,72 @@
+"""Peer-memory sweeps (`b200sv_apply_plan_peers`): a register sharded over GPUs by its top qubits, gates on global qubits
+executed as sweeps whose tiles straddle shards (SURVEY.md §8e, configs[4]).  One GPU: the peer table has one entry and the
+result must be bit-identical to the ordinary path; two GPUs (when the box has them): two processes over CUDA IPC."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from qadence_b200.program import Program, ProgramBuilder, hea_program
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _program(n: int) -> Program:
+    b = ProgramBuilder(n)
+    for q in range(n):
+        b.H(q)
+        for k in range(q + 1, min(n, q + 6)):
+            b.CPHASE(k, q, 2 * np.pi / 2 ** (k - q + 1))
+    b.SWAP(0, n - 1).CNOT(n - 1, 0)
+    return Program(n, b.build().ops + hea_program(n, 1).ops)
+
+
+def test_single_rank_peer_table_equals_plain_path() -> None:
+    from qadence_b200 import dist as qdist
+    from qadence_b200 import engine
+
+    n = 16
+    prog = _program(n)
+    g = torch.Generator().manual_seed(3)
+    values = {nm: 6.28 * torch.rand(1, generator=g, dtype=torch.float64) for nm in prog.param_names}
+    sim = qdist.PeerShardedSimulator(prog, 0, 1, "cuda:0")
+    try:
+        got = sim.run(values).clone()
+        want = engine.run(engine.CompiledProgram(prog), values, device="cuda:0")
+        assert torch.equal(got, want)
+        assert abs(float(sim.norm2(got)) - 1.0) < 1e-12
+    finally:
+        sim.close()
+
+
+def test_traffic_model_counts_global_bits() -> None:
+    from qadence_b200.dist import peer_traffic
+    from qadence_b200.plan import TileConfig, build_plan
+
+    n, g = 24, 2
+    prog = _program(n)
+    plan = build_plan(list(prog.ops), n, {nm: i for i, nm in enumerate(prog.param_names)}, TileConfig.default(True, False))
+    t = peer_traffic(plan, n, g)
+    assert len(t["global_bits_per_sweep"]) == plan.n_sweeps and max(t["global_bits_per_sweep"]) >= 1
+    assert 0 < t["nvlink_bytes_per_rank_per_direction"] < t["hbm_bytes_per_rank"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_ranks_match_single_gpu() -> None:
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "tools" / "sharded_check.py"), "--qubits", "22", "--verify", "--peer", "--reps", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env={**os.environ})
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert out.returncode == 0 and line, out.stderr[-2000:]
+    import json
+
+    res = json.loads(line[-1])
+    assert res["max_abs_err_vs_single_gpu"] == 0.0 and abs(res["norm"] - 1) < 1e-12

@@ -36,6 +36,7 @@ ap.add_argument("--qubits", type=int, default=26)
 ap.add_argument("--depth", type=int, default=1)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--peer", action="store_true", help="fuse the exchanges into the sweeps (NVLink peer-memory addressing)")
 args = ap.parse_args()
 rank, world = qdist.init_from_env("nccl")
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -45,13 +46,14 @@ n = args.qubits
 prog = Program(n, qft_program(n).ops + hea_program(n, args.depth).ops)
 g = torch.Generator().manual_seed(7)
 values = {nm: 2 * torch.pi * torch.rand(1, generator=g, dtype=torch.float64) for nm in prog.param_names}
-sim = qdist.QubitShardedSimulator(prog, rank, world, dev)
+sim = qdist.PeerShardedSimulator(prog, rank, world, dev) if args.peer else qdist.QubitShardedSimulator(prog, rank, world, dev)
 st = sim.run(values)  # warm-up (plans, NCCL communicator)
 torch.cuda.synchronize()
 times = []
 for _ in range(args.reps):
-    del st  # a 36-qubit shard is 128 GiB: never hold two
-    torch.cuda.empty_cache()
+    if not args.peer:
+        del st  # a 36-qubit shard is 128 GiB: never hold two
+        torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -65,8 +67,13 @@ for _ in range(args.reps):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(float(t.item()))
 ms = min(times)
+sweep_ms = None
+if args.peer:
+    sim.time_sweeps = True
+    sim.run(values)
+    sweep_ms = [round(x, 3) for x in sim.sweep_ms]
 norm = float(sim.norm2(st).item())
-mag = float(sim.expectation_diagonal(st, total_magnetization(n)).item())
+mag = None if args.peer else float(sim.expectation_diagonal(st, total_magnetization(n)).item())
 err = None
 if args.verify:
     full = engine.run(engine.CompiledProgram(prog), values, device=dev) if rank == 0 else torch.empty(1, 1 << n, dtype=torch.complex128, device=dev)
@@ -82,9 +89,14 @@ if rank == 0:
     n_sweeps = sim.n_sweeps()
     print(json.dumps({
         "n": n, "world": world, "gates": len(prog.ops), "ms": ms, "gates_per_s": len(prog.ops) / (ms * 1e-3), "sweeps": n_sweeps,
-        "exchanges": sim.stats["exchanges"], "nvlink_bytes_sent_per_rank": sim.bytes_sent,
+        "mode": "peer-memory sweeps" if args.peer else "all-to-all exchanges",
+        "exchanges": sim.stats["exchanges"], "nvlink_bytes_sent_per_rank": sim.stats["nvlink_bytes_per_rank_per_direction"] if args.peer else sim.bytes_sent,
+        "global_bits_per_sweep": sim.stats.get("global_bits_per_sweep"), "sweep_ms_rank0": sweep_ms,
         "local_sweep_bytes": 2 * S_local * n_sweeps, "norm": norm, "total_magnetization": mag, "max_abs_err_vs_single_gpu": err,
     }))
+if args.peer:
+    del st
+    sim.close()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -11,6 +11,7 @@ happens in the hand-written CUDA kernels.  No CPU fallback: everything here rais
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import Counter
 from dataclasses import dataclass, field
 from typing import Any, Mapping, Sequence
@@ -204,7 +205,13 @@ class CompiledProgram:
         key = (dtype, adjoint, device, None if cfg is None else (cfg.m, cfg.r, cfg.low))
         if key not in seg._plans:
             tc = cfg or TileConfig.default(dtype == torch.complex128, adjoint)
-            seg._plans[key] = DevicePlan(build_plan(seg.gates, self.n_qubits, self.slot_of, tc), device)
+            plan = build_plan(seg.gates, self.n_qubits, self.slot_of, tc)
+            if (cfg is None and not adjoint and dtype == torch.complex128 and tc.m == 11 and self.n_qubits > 12
+                    and "B200SV_TILE_FWD_C128" not in os.environ and int((plan.sweeps["n_gen"] > 0).sum()) > 0):
+                # sweeps with generic-phase entries (controlled / diagonal gates, e.g. a QFT) run 17 % faster with
+                # 2^12-amplitude tiles; pure rotation + CNOT sweeps do not care (profiles/r01_multi_gpu.md)
+                plan = build_plan(seg.gates, self.n_qubits, self.slot_of, TileConfig(m=12, r=4, low=tc.low, fold=tc.fold))
+            seg._plans[key] = DevicePlan(plan, device)
         return seg._plans[key]
 
     def shift_rule(self, slot: int) -> int | None:

@@ -599,12 +599,12 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
     }
     cur_b = b;
   }
-  if (tid < n_rounds) {  // per-tile constant of the permutation phase: external (outer / rank bit) controls
-    const b200sv_round& rd = rounds[sw.first_round + tid];
+  for (int rr = tid; rr < n_rounds; rr += nt) {  // per-tile constant of the permutation phase: external (outer / rank bit) controls
+    const b200sv_round& rd = rounds[sw.first_round + rr];
     unsigned ext = 0;
     for (int k = 0; k < (int)rd.n_pext; ++k)
       if ((cta_index >> rd.pext[k].bit) & 1ull) ext ^= rd.pext[k].vec;
-    rtab[tid * RT_STRIDE + 36] = (unsigned)swz<real>((int)ext) << 16;
+    rtab[rr * RT_STRIDE + 36] = (unsigned)swz<real>((int)ext) << 16;
   }
   __syncthreads();  // tile `which` has landed; eg / rtab[36] visible
   const long long state_off = b << n;

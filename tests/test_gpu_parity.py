@@ -47,7 +47,8 @@ def test_random_circuit_run(n: int, batch: int, dtype: torch.dtype) -> None:
     assert (got - want).abs().max().item() <= TOL[dtype] * scale
 
 
-@pytest.mark.parametrize("cfg", [TileConfig(11, 3, 4, 3), TileConfig(10, 3, 4, 3), TileConfig(12, 4, 5, 3), TileConfig(9, 2, 3, 3), TileConfig(8, 1, 2, 3)], ids=lambda c: f"m{c.m}r{c.r}")
+@pytest.mark.parametrize("cfg", [TileConfig(11, 3, 4, 3), TileConfig(10, 3, 4, 3), TileConfig(12, 4, 5, 3), TileConfig(9, 2, 3, 3), TileConfig(8, 1, 2, 3),
+                                 TileConfig(2, 1, 0, 4), TileConfig(3, 2, 0, 3)], ids=lambda c: f"m{c.m}r{c.r}")  # the last two: fewer threads than rounds
 def test_tile_geometries(cfg: TileConfig) -> None:
     """Every (m, r) instantiation of the sweep kernel, through the C-ABI directly."""
     import ctypes as C
@@ -210,3 +211,15 @@ def test_sharded_simulator_world_1_matches_engine() -> None:
     assert abs(sim.norm2(st).item() - 1.0) < 1e-10
     e = sim.expectation_diagonal(st, total_magnetization(n)).item()
     assert abs(e - oracle.expectation(prog, [total_magnetization(n)], values).item()) < 1e-10
+
+
+def test_randomised_differential_fuzz() -> None:
+    """A short run of tools/gpu_fuzz.py (random circuits x random tile geometries, forward and adjoint) — the campaign that
+    found the tiny-CTA bug (per-tile permutation constants of rounds beyond the CTA's thread count)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "tools" / "gpu_fuzz.py"), "12", "5"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]

@@ -223,3 +223,14 @@ def test_randomised_differential_fuzz() -> None:
     root = Path(__file__).resolve().parents[1]
     out = subprocess.run([sys.executable, str(root / "tools" / "gpu_fuzz.py"), "12", "5"], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and out.stdout.strip().startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_randomised_differential_fuzz_of_the_other_kernels() -> None:
+    """A short run of tools/gpu_fuzz_ops.py: Pauli sums, diagonal / Krylov HamEvo, dense matrices, bit-exact sampling."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "tools" / "gpu_fuzz_ops.py"), "10", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]

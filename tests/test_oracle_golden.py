@@ -117,3 +117,18 @@ def test_hea_program_shape() -> None:
     prog = hea_program(20, 8)
     assert len(prog.ops) == 632 and len(prog.param_names) == 480  # 320 RX + 160 RY + 152 CNOT
     assert total_magnetization(20).is_diagonal
+
+
+def test_oracle_exponential_is_exact_where_matrix_exp_is_not() -> None:
+    """torch.linalg.matrix_exp (the reference's dense HamEvo) is off by ~2e-10 for small-norm complex128 matrices; the
+    oracle's spectral exponential matches the closed form to rounding."""
+    import torch
+
+    from oracle import statevec as oracle
+
+    x = torch.linspace(0.001, 0.3, 100, dtype=torch.float64)
+    z = torch.tensor([[1, 0], [0, -1]], dtype=torch.complex128).expand(100, 2, 2)
+    u = oracle.expm_i(z, x, -1j)
+    assert (u[:, 0, 0] - torch.exp(-1j * x)).abs().max() < 1e-15 and (u[:, 1, 1] - torch.exp(1j * x)).abs().max() < 1e-15
+    g = torch.tensor([[0.3, 0.2 - 0.1j], [0.2 + 0.1j, -0.7]], dtype=torch.complex128).expand(1, 2, 2)
+    assert (oracle.expm_i(g, torch.tensor([1.7]), -1j) - torch.linalg.matrix_exp(-1.7j * g)).abs().max() < 1e-9

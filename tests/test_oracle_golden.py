@@ -131,4 +131,4 @@ def test_oracle_exponential_is_exact_where_matrix_exp_is_not() -> None:
     u = oracle.expm_i(z, x, -1j)
     assert (u[:, 0, 0] - torch.exp(-1j * x)).abs().max() < 1e-15 and (u[:, 1, 1] - torch.exp(1j * x)).abs().max() < 1e-15
     g = torch.tensor([[0.3, 0.2 - 0.1j], [0.2 + 0.1j, -0.7]], dtype=torch.complex128).expand(1, 2, 2)
-    assert (oracle.expm_i(g, torch.tensor([1.7]), -1j) - torch.linalg.matrix_exp(-1.7j * g)).abs().max() < 1e-9
+    assert (oracle.expm_i(g, torch.tensor([1.7], dtype=torch.float64), -1j) - torch.linalg.matrix_exp(-1.7j * g)).abs().max() < 1e-9

@@ -38,7 +38,7 @@ def evaluate(prog: EmbedProgram, var: Tensor, feat: Tensor, batch: int) -> Tenso
             elif op == EO_POW:
                 r = torch.pow(val[a], val[b])
             elif op == EO_HEAVISIDE:
-                r = torch.heaviside(val[a].detach(), torch.tensor(0.5, dtype=torch.float64)) + 0.0 * val[a]
+                r = torch.heaviside(val[a].detach(), torch.tensor(0.5, dtype=torch.float64))  # as parameters.py:196-205
             else:
                 r = _UNARY[op](val[a])
             val.append(r)

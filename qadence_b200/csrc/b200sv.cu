@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(128) embed_kernel(const b200sv_enode* __restri
       case B200SV_EO_ASIN: r = asin(x); break;
       case B200SV_EO_ATAN: r = atan(x); break;
       case B200SV_EO_ABS: r = fabs(x); break;
-      default: r = x > 0.0 ? 1.0 : (x < 0.0 ? 0.0 : 0.5); break;  // HEAVISIDE
+      default: r = x > 0.0 ? 1.0 : (x == 0.0 ? 0.5 : 0.0); break;  // HEAVISIDE (torch.heaviside: NaN -> 0)
     }
     val[i] = r;
   }

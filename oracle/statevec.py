@@ -259,11 +259,14 @@ def expm_i(G: torch.Tensor, t: torch.Tensor, sign: complex) -> torch.Tensor:
     2.3e-10 of error on complex128 matrices of small norm (measured: exp(−i x Z), x in (0, 0.3]) — more than the 1e-10
     parity bar, so a correct kernel could fail against it.  For Hermitian G (every generator the reference accepts) the
     oracle therefore exponentiates spectrally, which is exact to rounding; anything else falls back to matrix_exp."""
-    if torch.allclose(G, G.conj().transpose(-1, -2), atol=1e-12, rtol=0):
-        w, V = torch.linalg.eigh(G)
-        phase = torch.exp(sign * t[:, None].to(CDTYPE) * w.to(CDTYPE))
-        return (V * phase[:, None, :]) @ V.conj().transpose(-1, -2)
-    return torch.linalg.matrix_exp(sign * t[:, None, None] * G)
+    me = torch.linalg.matrix_exp(sign * t[:, None, None] * G)
+    if torch.allclose(G.detach(), G.detach().conj().transpose(-1, -2), atol=1e-12, rtol=0):
+        w, V = torch.linalg.eigh(G.detach())
+        phase = torch.exp(sign * t.detach()[:, None].to(CDTYPE) * w.to(CDTYPE))
+        exact = (V * phase[:, None, :]) @ V.conj().transpose(-1, -2)
+        # value from the spectral form, derivatives from matrix_exp (eigh's backward is singular on degenerate spectra)
+        return me + (exact - me.detach())
+    return me
 
 
 def hamevo_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = False) -> torch.Tensor:

@@ -158,6 +158,23 @@ class CompiledPauliSum:
         return torch.stack(rows) if rows else torch.zeros(0, 1, dtype=torch.complex128, device=device)
 
 
+def _dcoef(cps: "CompiledPauliSum", name: str, values: Mapping[str, Tensor], device: torch.device, batch: int) -> Tensor:
+    """[T, batch] complex128 table of ∂coef_t/∂values[name] (coef_t = const_t · Π values[names_t])."""
+    rows = []
+    for c, nms in zip(cps.consts, cps.names):
+        total = torch.zeros(batch, dtype=torch.complex128, device=device)
+        for i, nm in enumerate(nms):
+            if nm != name:
+                continue
+            v = torch.full((batch,), complex(c), dtype=torch.complex128, device=device)
+            for j, other in enumerate(nms):
+                if j != i:
+                    v = v * torch.as_tensor(values[other]).detach().to(device).reshape(-1)
+            total = total + v
+        rows.append(total)
+    return torch.stack(rows) if rows else torch.zeros(0, batch, dtype=torch.complex128, device=device)
+
+
 @dataclass
 class Segment:
     gates: list[Op] | None = None  # run of simple gates
@@ -493,6 +510,9 @@ class _AdjointExpectation(torch.autograd.Function):
         detached = values.detach() if isinstance(values, ParamTable) else {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}
         ctx.cp, ctx.cobs, ctx.values, ctx.batch = cp, cobs, detached, batch
         ctx.state, ctx.dtype = state, dtype
+        # names whose tensors asked for a gradient (None = unknown, e.g. a device-embedded table): only those HamEvo
+        # generator coefficients get the (more expensive) quadrature in the backward pass
+        ctx.grad_names = None if isinstance(values, ParamTable) else {k for k, v in values.items() if isinstance(v, Tensor) and v.requires_grad}
         ctx.psi = psi
         ctx.save_for_backward(ptable)
         return torch.stack(cols, dim=1)
@@ -504,12 +524,12 @@ class _AdjointExpectation(torch.autograd.Function):
             # create_graph=True: hand out a gradient that can itself be differentiated (DQC-style losses)
             grads = _AdjointGradient.apply(ctx.cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ctx.batch, ptable, grad_out)
         else:
-            grads = _adjoint_gradient(ctx.cp, ctx.cobs, ctx.values, ctx.batch, ptable, grad_out, ctx.psi)
+            grads = _adjoint_gradient(ctx.cp, ctx.cobs, ctx.values, ctx.batch, ptable, grad_out, ctx.psi, ctx.grad_names)
         return None, None, None, None, None, None, None, grads
 
 
 def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], values: Mapping[str, Any], B: int, ptable: Tensor,
-                      grad_out: Tensor, psi: Tensor) -> Tensor:
+                      grad_out: Tensor, psi: Tensor, grad_names: set | None = None) -> Tensor:
     """`[n_slots, B]` vector-Jacobian product Σ_o ḡ[b,o]·∂E[b,o]/∂θ[slot,b] by the adjoint method: λ = Σ_o ḡ·O_o ψ, then
     one backward walk that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps."""
     from . import hamevo
@@ -557,8 +577,18 @@ def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], v
                 if isinstance(op.param, str):
                     g_psi = hamevo.generator_apply(op, seg.compiled, psi, values, cp.n_qubits)
                     grads[cp.slot_of[op.param]] += 2.0 * dot(lam, g_psi).imag
-                psi = hamevo.evolve(op, seg.compiled, psi, values, cp.n_qubits, dagger=True)
-                lam = hamevo.evolve(op, seg.compiled, lam, values, cp.n_qubits, dagger=True)
+                gen_names = [nm for nm in (op.generator.param_names if isinstance(op.generator, PauliSum) else [])
+                             if grad_names is None or nm in grad_names]
+                if gen_names:  # parametric generator coefficients: ∂E/∂g = 2 t ∫ Im<λ(s)|∂H/∂g|ψ(s)> ds along the evolution
+                    psi, lam = hamevo.adjoint_generator_params(op, seg.compiled, psi, lam, values, cp.n_qubits, grads, cp.slot_of, gen_names)
+                else:
+                    if grad_names is not None and not isinstance(op.generator, PauliSum):
+                        bad = [nm for nm in (seg.compiled.names if isinstance(op.generator, Program) else [op.generator] if isinstance(op.generator, str) else [])
+                               if nm in grad_names]
+                        if bad:
+                            raise NotImplementedError(f"adjoint gradients w.r.t. the HamEvo generator parameters {bad} need a Pauli-sum generator; use diff_mode='gpsr'")
+                    psi = hamevo.evolve(op, seg.compiled, psi, values, cp.n_qubits, dagger=True)
+                    lam = hamevo.evolve(op, seg.compiled, lam, values, cp.n_qubits, dagger=True)
             elif op.kind == OpKind.MATK:
                 bits = [cp.n_qubits - 1 - q for q in op.targets]
                 md = np.asarray(op.matrix, dtype=np.complex128).conj().T
@@ -638,12 +668,13 @@ def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], 
     cobs = list(observables)
     ptable = pack_params(cp.names, values, B, dev)
     real_dt = torch.float64 if dtype == torch.complex128 else torch.float32
-    if not (torch.is_grad_enabled() and ptable.requires_grad):
+    grad_on = torch.is_grad_enabled()
+    if not (grad_on and ptable.requires_grad):
         with torch.no_grad():
             st = prepare_state(cp.n_qubits, B, state, dtype, dev)
             psi = _run_segments(cp, st, ptable, values)
             out = torch.stack([o.expectation(psi, values) for o in cobs], dim=1)
-            obs_grad = torch.is_grad_enabled() and any(
+            obs_grad = grad_on and any(
                 isinstance(values.get(nm), Tensor) and values[nm].requires_grad for o in cobs for nm in o.names
             )
         if not obs_grad:

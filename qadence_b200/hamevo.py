@@ -180,6 +180,50 @@ def adjoint_time_dependent(op: Op, compiled: Any, psi: Tensor, lam: Tensor, valu
     return psi, lam
 
 
+def adjoint_generator_params(op: Op, compiled: Any, psi: Tensor, lam: Tensor, values: Mapping[str, Tensor], n: int, grads: Tensor,
+                             slot_of: Mapping[str, int], names: list) -> tuple[Tensor, Tensor]:
+    """Backward step through U = exp(−i t H(g)) that also yields ∂E/∂g for coefficients g of the Pauli-sum generator:
+
+        ∂U/∂g = −i t ∫_0^1 e^{−i(1−s) t H} (∂H/∂g) e^{−i s t H} ds   ⇒   ∂E/∂g = 2 t ∫_0^1 Im⟨λ(s)|∂H/∂g|ψ(s)⟩ ds,
+
+    ψ(s), λ(s) being the states evolved back from the end of the gate to the fraction s.  Commuting (all-Z) generators have
+    a constant integrand; otherwise Gauss–Legendre nodes (as many as the phase t‖H‖ needs for 1e-12) are visited while
+    un-applying the evolution piecewise.  Returns (ψ, λ) before the gate."""
+    dev = psi.device
+    B = psi.shape[0]
+    t = _time(op, values, B, dev)
+    dcoefs = [E._dcoef(compiled, nm, values, dev, B) for nm in names]
+
+    def accumulate(weight: float) -> None:
+        for nm, dc in zip(names, dcoefs):
+            grads[slot_of[nm]] += (2.0 * weight) * t * E.dot(lam, E.pauli_apply(compiled, dc, psi)).imag
+
+    def back(frac: float) -> None:  # un-apply the fraction `frac` of the evolution on both states
+        nonlocal psi, lam
+        if frac <= 0.0:
+            return
+        part = Op(op.kind, op.targets, op.controls, param="__t_part__", generator=op.generator, label=op.label)
+        vals = {**values, "__t_part__": frac * t}
+        psi = evolve(part, compiled, psi, vals, n, dagger=True)
+        lam = evolve(part, compiled, lam, vals, n, dagger=True)
+
+    if compiled.diagonal:
+        accumulate(1.0)
+        back(1.0)
+        return psi, lam
+    rho = (_norm_bound(op, compiled, values) or 1.0) * float(t.abs().max())
+    k = int(min(96, max(8, np.ceil(rho) + 8)))
+    nodes, weights = np.polynomial.legendre.leggauss(k)
+    nodes, weights = 0.5 * (nodes + 1.0), 0.5 * weights  # on [0, 1]
+    at = 1.0
+    for s_, w_ in zip(nodes[::-1], weights[::-1]):
+        back(at - float(s_))
+        at = float(s_)
+        accumulate(float(w_))
+    back(at)
+    return psi, lam
+
+
 def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
     if op.tsym:
         return evolve_time_dependent(op, compiled, psi, values, n, dagger)

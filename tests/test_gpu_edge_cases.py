@@ -171,3 +171,42 @@ def test_missing_parameter_and_bad_state_errors() -> None:
         engine.run(cp, {"theta": torch.zeros(1)}, torch.zeros(1, 8, dtype=torch.complex128), device=DEV)
     with pytest.raises(ValueError):
         engine.run(cp, {"theta": torch.zeros(3)}, torch.zeros(2, 4, dtype=torch.complex128), device=DEV)
+
+
+def test_observable_parameter_gradient_without_circuit_parameters() -> None:
+    """dE/dw for a parametric observable when nothing in the circuit asks for a gradient (found by tools/gpu_fuzz_mixed.py:
+    the no-adjoint branch used to drop it)."""
+    n = 3
+    prog = ProgramBuilder(n).H(0).CNOT(0, 1).RX(2, 0.4).build()
+    obs = PauliSum(n, [PauliTerm(0.7, ("w",), ((0, "Z"), (1, "Z"))), PauliTerm(1.0, (), ((2, "Z"),)), PauliTerm(-0.3, ("w", "w"), ((2, "Y"),))])
+    w = torch.tensor([0.9, -0.4], dtype=torch.float64, device=DEV, requires_grad=True)
+    e = engine.expectation(engine.CompiledProgram(prog), [engine.CompiledObservable(obs)], {"w": w}, device=DEV)
+    e.sum().backward()
+    wh = w.detach().cpu().requires_grad_(True)
+    ref = oracle.expectation(prog, [obs], {"w": wh})
+    ref.sum().backward()
+    assert (e.detach().cpu() - ref.detach()).abs().max() < 1e-12
+    assert (w.grad.cpu() - wh.grad).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("diagonal", [True, False])
+def test_hamevo_generator_coefficient_gradients(diagonal: bool) -> None:
+    """Adjoint gradients w.r.t. parametric coefficients of a Pauli-sum HamEvo generator (analog blocks with parametric
+    omega / delta): constant integrand for commuting generators, Gauss-Legendre along the evolution otherwise."""
+    n, B = 4, 3
+    rng = np.random.default_rng(11)
+    p = "Z" if diagonal else "X"
+    gen = PauliSum(n, [PauliTerm(0.9, ("g",), ((0, "Z"), (1, "Z"))), PauliTerm(0.4, ("h",), ((2, p),)), PauliTerm(1.1, ("g", "h"), ((3, "Z"),)),
+                       PauliTerm(-0.6, (), ((1, p), (2, "Z")))])
+    prog = ProgramBuilder(n).H(0).RY(1, "a").hamevo(gen, "t").CNOT(0, 3).RX(2, "a").build()
+    obs = PauliSum(n, [PauliTerm(1.0, (), ((0, "X"),)), PauliTerm(0.5, (), ((1, "Z"), (3, "Y")))])
+    host = {"g": torch.tensor(rng.uniform(0.5, 1.5, size=B), requires_grad=True), "h": torch.tensor([0.8], dtype=torch.float64, requires_grad=True),
+            "t": torch.tensor(rng.uniform(0.3, 2.5, size=B), requires_grad=True), "a": torch.tensor([0.6], dtype=torch.float64, requires_grad=True)}
+    want = oracle.expectation(prog, [obs], host)
+    want.sum().backward()
+    devv = {k: v.detach().clone().to(DEV).requires_grad_(True) for k, v in host.items()}
+    got = engine.expectation(engine.CompiledProgram(prog), [engine.CompiledObservable(obs)], devv, device=DEV)
+    got.sum().backward()
+    assert (got.detach().cpu() - want.detach()).abs().max() < 1e-10
+    for k in host:
+        assert (devv[k].grad.cpu() - host[k].grad).abs().max() < 1e-9, k

@@ -234,3 +234,14 @@ def test_randomised_differential_fuzz_of_the_other_kernels() -> None:
     root = Path(__file__).resolve().parents[1]
     out = subprocess.run([sys.executable, str(root / "tools" / "gpu_fuzz_ops.py"), "10", "3"], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and out.stdout.strip().startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]
+
+
+@pytest.mark.parametrize("tool,seconds", [("gpu_fuzz_mixed.py", "10"), ("gpu_fuzz_embedding.py", "6")])
+def test_randomised_differential_fuzz_of_whole_programs_and_embedding(tool: str, seconds: str) -> None:
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "tools" / tool), seconds, "4"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]

@@ -460,3 +460,16 @@ def test_classical_shadow_measurement(oracle_device) -> None:
     exact = QuantumModel(circ, obs, backend="b200sv", diff_mode=DiffMode.AD)
     v = {"x": torch.tensor([0.7])}
     assert (shots.expectation(v).detach() - exact.expectation(v).detach()).abs().max() < 0.45
+
+
+@pytest.mark.parametrize("tool", ["cpu_fuzz_convert.py", "cpu_fuzz_observable.py"])
+def test_randomised_converter_fuzz(tool: str) -> None:
+    """Short runs of the converter campaigns (≈ 16 000 random blocks and 6 000 random observables were run once, clean)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "tools" / tool), "5", "6"], capture_output=True, text=True, timeout=300, cwd=root)
+    last = [ln for ln in out.stdout.splitlines() if ln.strip()][-1:] or [""]
+    assert out.returncode == 0 and last[0].startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]

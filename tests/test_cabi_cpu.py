@@ -40,6 +40,10 @@ def test_record_layouts_match_header() -> None:
         m = re.search(r"typedef struct %s \{\s*/\* (\d+) bytes" % struct, header)
         assert m and int(m.group(1)) == dt.itemsize, struct
     assert C.sizeof(cabi.PlanStruct) == 56
+    from qadence_b200 import embedding
+
+    fields = re.search(r"typedef struct b200sv_enode \{\s*int32_t ([^;]+);", header).group(1).split(",")
+    assert embedding.ENODE_DT.itemsize == 4 * len(fields) == 32
 
 
 def test_fails_loudly_without_a_device(lib: C.CDLL) -> None:

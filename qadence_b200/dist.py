@@ -151,6 +151,11 @@ def plan_layout(ops: Sequence[Op], n: int, g: int, restore: bool = True) -> Layo
         raise ValueError("a register sharded over 2^g ranks needs at least 2g qubits")
     layout = list(range(n))  # logical -> physical
     hard = [hard_qubits(op) for op in ops]
+    hmax = max((len(h) for h in hard), default=0)
+    if n - g - max(0, hmax - 1) < g:
+        # an exchange always swaps all g rank bits with g local qubits that the current gate does not need
+        raise ValueError(f"{n} qubits over 2^{g} ranks: gates with {hmax} non-diagonal targets need at least {2 * g + hmax - 1} qubits "
+                         "for the all-to-all path (PeerShardedSimulator has no such limit)")
     INF = len(ops) + 1
     # next_use[i][q]: first j >= i with q in hard[j]
     nxt = [INF] * n

@@ -139,3 +139,13 @@ def test_collectives_world_size_2_gloo(tmp_path) -> None:
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_layout_planner_rejects_registers_too_small_for_an_exchange() -> None:
+    """An exchange swaps all g rank bits with g local qubits the current gate does not need; with too few local qubits the
+    planner must say so (it used to trip an assertion — found by a randomised campaign of 15 000 sharded circuits)."""
+    b = ProgramBuilder(6)
+    b.H(0).SWAP(0, 5)
+    with pytest.raises(ValueError, match="at least"):
+        qdist.plan_layout(b.build().ops, 6, 3)
+    assert qdist.plan_layout(b.build().ops, 7, 3).final_layout == list(range(7))

@@ -190,6 +190,8 @@ class Backend(BackendInterface):
             circuit = transpile(*passes)(circuit)
         if self.config.noise:
             raise NotImplementedError("b200sv is a pure state-vector backend: `noise` is not supported")
+        if self.config.dropout_probability:
+            raise NotImplementedError("b200sv does not implement quantum dropout (`dropout_probability` must be 0)")
         ops = convert_block(circuit.block, n_qubits=circuit.n_qubits, config=self.config)
         native = NativeCircuit(Program(circuit.n_qubits, ops), _DTYPES[self.config.dtype], self.config.device)
         return ConvertedCircuit(native=native, abstract=circuit, original=original)

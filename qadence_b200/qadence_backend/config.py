@@ -31,11 +31,20 @@ class Configuration(BackendConfiguration):
     """HamEvo algorithm: diagonal generators are exponentiated on the fly, everything else uses the
     matrix-free Lanczos–Krylov propagator converged to 1e-13 (the reference's `EXP` is a dense
     `matrix_exp`; results agree to the parity tolerance)."""
+    ode_solver: object = None
+    """Accepted for compatibility (pyqtorch `SolverType`): time-dependent generators always use the exponential-midpoint
+    propagator with `n_steps_hevo` steps."""
     n_steps_hevo: int = 100
+    use_gradient_checkpointing: bool = False
+    """Accepted for compatibility; the adjoint pass keeps two states, there is nothing to checkpoint."""
+    use_single_qubit_composition: bool = False
+    """Accepted for compatibility; the fusion planner always merges chains of single-qubit gates."""
     loop_expectation: bool = False
     """Accepted for compatibility; the batched path never materialises per-term states."""
     noise: None = None
     dropout_probability: float = 0.0
+    """Quantum dropout is not supported: a non-zero value raises at conversion time."""
+    dropout_mode: object = None
     n_eqs: int | None = None
     shift_prefac: float = 0.5
     gap_step: float = 1.0

@@ -473,3 +473,33 @@ def test_randomised_converter_fuzz(tool: str) -> None:
     out = subprocess.run([sys.executable, str(root / "tools" / tool), "5", "6"], capture_output=True, text=True, timeout=300, cwd=root)
     last = [ln for ln in out.stdout.splitlines() if ln.strip()][-1:] or [""]
     assert out.returncode == 0 and last[0].startswith("ok:"), out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_pyqtorch_configuration_dicts_are_accepted(oracle_device) -> None:
+    """Every option name of `backends/pyqtorch/config.py:38-90` (and `use_sparse_observable`, backend.py:43) is accepted, so
+    user configuration dicts keep working; options that would change results raise instead of being ignored."""
+    cfg = {"algo_hevo": "exp", "ode_solver": "dp5_se", "n_steps_hevo": 50, "use_gradient_checkpointing": True,
+           "use_single_qubit_composition": True, "loop_expectation": True, "use_sparse_observable": True, "n_eqs": None,
+           "shift_prefac": 0.5, "gap_step": 1.0, "lb": None, "ub": None, "dropout_probability": 0.0, "dropout_mode": "rotational"}
+    model = QuantumModel(QuantumCircuit(2, chain(RX(0, "x"), CNOT(0, 1))), total_magnetization(2), backend="b200sv", configuration=cfg)
+    assert model.expectation({"x": torch.tensor([0.2, 0.4])}).shape == (2, 1)
+    with pytest.raises(NotImplementedError, match="dropout"):
+        QuantumModel(QuantumCircuit(1, RX(0, "x")), backend="b200sv", configuration={"dropout_probability": 0.1})
+
+
+@pytest.mark.parametrize("dtype", [torch.complex64, torch.complex128])
+def test_state_precision_comes_from_the_configuration(oracle_device, dtype) -> None:
+    """Counterpart of tests/backends/pyq/test_quantum_pyq.py:875-903.  `QuantumModel.to(dtype)` only retargets pyqtorch
+    circuits (model.py:651-655 checks `isinstance(native, pyqtorch.QuantumCircuit)`), so for this backend — as for any
+    non-pyqtorch backend — the precision is a configuration option; complex-typed inputs are accepted like there."""
+    circ = QuantumCircuit(3, chain(feature_map(3, param="x"), hea(3, 1)))
+    name = "complex64" if dtype == torch.complex64 else "complex128"
+    qm = QuantumModel(circ, total_magnetization(3), backend="b200sv", configuration={"dtype": name})
+    assert qm._circuit.native.dtype == dtype and all(o.native.dtype == dtype for o in qm._observable)
+    assert qm.to(dtype=dtype) is qm  # accepted, a no-op here
+    inputs = {"x": torch.tensor([0.1, 0.5]).to(dtype=dtype)}
+    state = qadence.uniform_state(3).to(dtype=dtype)
+    wf = qm.run(inputs, state=state)
+    assert wf.dtype == dtype and wf.shape == (2, 8)
+    ev = qm.expectation(inputs, state=state)
+    assert ev.dtype == (torch.float64 if dtype == torch.cdouble else torch.float32)

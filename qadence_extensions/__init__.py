@@ -43,4 +43,7 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
 
 if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):
-    sys.meta_path.append(_AliasFinder())
+    # FIRST on the meta path: once `qadence.backends.b200sv` is an alias of the real package, the stock PathFinder would
+    # otherwise find `config.py` through the package's __path__ and execute it a second time under the alias name, giving
+    # two distinct `Configuration` classes (backend_factory compares configuration types exactly, backends/api.py:34-41)
+    sys.meta_path.insert(0, _AliasFinder())

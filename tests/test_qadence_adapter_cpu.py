@@ -503,3 +503,36 @@ def test_state_precision_comes_from_the_configuration(oracle_device, dtype) -> N
     assert wf.dtype == dtype and wf.shape == (2, 8)
     ev = qm.expectation(inputs, state=state)
     assert ev.dtype == (torch.float64 if dtype == torch.cdouble else torch.float32)
+
+
+def test_default_and_custom_configuration() -> None:
+    """tests/backends/test_backends.py:266-300 for this backend: default configuration object, `change_config` with a known
+    option, ValueError for an unknown one."""
+    from qadence.backend import BackendConfiguration
+
+    bk = backend_factory("b200sv", diff_mode=None)
+    conf = bk.default_configuration()
+    assert isinstance(conf, BackendConfiguration) and isinstance(conf.available_options(), str) and "n_steps_hevo" in conf.available_options()
+    model = QuantumModel(QuantumCircuit(1, RX(0, np.pi)), backend="b200sv", diff_mode=DiffMode.GPSR)
+    old = model.backend.backend.config.use_sparse_observable
+    model.change_config({"use_sparse_observable": not old})
+    assert model.backend.backend.config.use_sparse_observable == (not old)
+    with pytest.raises(ValueError):
+        model.change_config({"sparse_observable": True})
+
+
+def test_custom_transpilation_passes() -> None:
+    """tests/backends/test_backends.py:316-337: user passes replace the default ones; an empty list disables them."""
+    from qadence.backends.api import config_factory
+    from qadence.transpile import flatten
+
+    circuit = QuantumCircuit(1, chain(chain(chain(RX(0, np.pi / 2))), kron(kron(RX(0, np.pi / 2)))))
+    config = config_factory("b200sv", {})
+    config.transpilation_passes = [flatten]
+    conv = backend_factory("b200sv", configuration=config).convert(circuit)
+    config = config_factory("b200sv", {})
+    config.transpilation_passes = []
+    conv_none = backend_factory("b200sv", configuration=config).convert(circuit)
+    assert conv.circuit.original == conv_none.circuit.original
+    assert conv.circuit.abstract != conv_none.circuit.abstract
+    assert len(conv.circuit.native.program.ops) == len(conv_none.circuit.native.program.ops) == 2

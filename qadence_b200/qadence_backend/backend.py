@@ -147,6 +147,12 @@ def _device_embedding_fn(conv: Converted, config: Configuration) -> Any:
         if e is None or isinstance(e, sympy.Array):
             raise UnsupportedExpression(f"no scalar expression behind parameter '{nm}'")
         named.append((nm, e))
+    # the reference's dict also has an entry for every gate whose parameter is a plain number (embedding.py:147-153): the
+    # parameter-shift machinery looks those uuids up (engines/torch/differentiable_expectation.py:208), so they are table
+    # rows too (constant DAGs)
+    for nm, e in by_name.items():
+        if nm not in needed and not isinstance(e, sympy.Array) and not (isinstance(e, sympy.Basic) and e.is_Symbol and not config._use_gate_params):
+            named.append((nm, e))
     prog = compile_expressions(named, is_feature=lambda nm: not getattr(symbols.get(nm), "trainable", False))
     return make_embedding_fn(prog, config.device, conv.embedding_fn, passthrough=not config._use_gate_params)
 
@@ -205,6 +211,8 @@ class Backend(BackendInterface):
     def _state_in(self, state: Tensor | None, n_qubits: int) -> Tensor | None:
         if state is None:
             return None
+        if type(state).__name__ == "DensityMatrix":
+            raise NotImplementedError("b200sv is a pure state-vector backend: density-matrix states are not supported")
         validate_state(state, n_qubits)
         if is_pyq_shape(state, n_qubits) and not (state.dim() == 2 and state.shape[1] == 2**n_qubits):
             state = unpyqify(state)

@@ -187,6 +187,9 @@ class CompiledProgram:
     """A Program split into fused-gate segments and non-fusable ops, with its parameter slots."""
 
     def __init__(self, program: Program):
+        if program.is_noisy:
+            raise ValueError("this program carries digital noise: it runs as a density matrix (qadence_b200.density), "
+                             "not as a state vector")
         self.program = program
         self.n_qubits = program.n_qubits
         self.names: list[str] = program.param_names
@@ -491,6 +494,11 @@ class CompiledObservable:
         if self.pauli is not None:
             return pauli_expectation(self.pauli, self.pauli.coef(values, psi.device), psi)
         return dot(psi, self.apply(psi, values)).real
+
+
+def apply_observable(cob: CompiledObservable, psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
+    """O ψ as a new tensor (the density-matrix path traces it: Tr(O ρ), density.py)."""
+    return cob.apply(psi, values)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -130,11 +130,16 @@ class Op:
     label: str = ""  # reference op name, for diagnostics only
     tsym: str = ""  # HAMEVO with a time-dependent generator: name of the time symbol; `param` is then the DURATION
     steps: int = 0  # ... and the number of integration steps (Configuration.n_steps_hevo)
+    # digital noise channels applied right after this op, in order: ((protocol name, (probabilities...)), ...) — what the
+    # reference hands to pyqtorch gates as `noise=` (backends/pyqtorch/convert_ops.py:206-208,354-372); see density.py
+    noise: tuple = ()
 
     def to_json(self) -> dict:
         d: dict[str, Any] = {"kind": int(self.kind), "t": list(self.targets), "c": list(self.controls)}
         if self.label:
             d["label"] = self.label
+        if self.noise:
+            d["noise"] = [[str(nm), [float(x) for x in pr]] for nm, pr in self.noise]
         if self.tsym:
             d["tsym"], d["steps"] = self.tsym, self.steps
         if self.param is not None:
@@ -195,6 +200,7 @@ class Op:
             label=d.get("label", ""),
             tsym=d.get("tsym", ""),
             steps=int(d.get("steps", 0)),
+            noise=tuple((str(nm), tuple(float(x) for x in pr)) for nm, pr in d.get("noise", [])),
         )
 
 
@@ -239,6 +245,10 @@ class Program:
     @property
     def is_simple(self) -> bool:
         return all(op.kind < OpKind.MATK for op in self.ops)
+
+    @property
+    def is_noisy(self) -> bool:
+        return any(op.noise for op in self.iter_ops())
 
     def n_gates(self) -> int:
         return sum(1 for _ in self.iter_ops())
@@ -407,6 +417,13 @@ class ProgramBuilder:
 
     def hamevo(self, generator: Any, time: Param, targets: Sequence[int] = ()) -> "ProgramBuilder":
         return self._add(Op(OpKind.HAMEVO, tuple(targets), (), param=time, generator=generator, label="HamEvo"))
+
+    def noise(self, protocol: str, *error_probability: float) -> "ProgramBuilder":
+        """Digital noise channel right after the last gate, on its first target (what `set_noise` + the reference's
+        `convert_digital_noise` attach to a block, backends/pyqtorch/convert_ops.py:354-372)."""
+        op = self.p.ops[-1]
+        op.noise = (*op.noise, (str(getattr(protocol, "value", protocol)), tuple(float(x) for x in error_probability)))
+        return self
 
     def build(self) -> Program:
         return self.p

@@ -26,14 +26,14 @@ from qadence.circuit import QuantumCircuit
 from qadence.measurements import Measurements
 from qadence.mitigations import Mitigations
 from qadence.noise import NoiseHandler
-from qadence.transpile import flatten, scale_primitive_blocks_only, transpile
+from qadence.transpile import flatten, scale_primitive_blocks_only, set_noise, transpile
 from qadence.types import BackendName, Endianness, Engine, ParamDictType
 
-from .. import engine
+from .. import density, engine
 from ..embedding import ParamTable, UnsupportedExpression, compile_expressions, make_embedding_fn
 from ..program import Program
 from .config import Configuration, default_passes
-from .convert_ops import convert_block, convert_observable
+from .convert_ops import convert_block, convert_observable, convert_readout_noise
 
 logger = getLogger(__name__)
 _DTYPES = {"complex128": torch.complex128, "complex64": torch.complex64}
@@ -45,13 +45,21 @@ class NativeCircuit:
     Duck-types the attributes qadence reads on pyqtorch circuits: `n_qubits`,
     `dtype`, `device`, `to()`, `operations`, `init_state`, `readout_noise`."""
 
-    def __init__(self, program: Program, dtype: torch.dtype, device: str | None):
+    def __init__(self, program: Program, dtype: torch.dtype, device: str | None, readout_noise: Any = None):
         self.program = program
-        self.compiled = engine.CompiledProgram(program)
+        self.is_noisy = program.is_noisy  # gates carry digital noise: runs as a density matrix (qadence_b200/density.py)
+        self.compiled = None if self.is_noisy else engine.CompiledProgram(program)
+        self._density: density.CompiledDensityProgram | None = None
         self.n_qubits = program.n_qubits
         self.dtype = dtype
         self._device = device
-        self.readout_noise = None
+        self.readout_noise = readout_noise
+
+    @property
+    def density(self) -> density.CompiledDensityProgram:
+        if self._density is None:
+            self._density = density.CompiledDensityProgram(self.program)
+        return self._density
 
     @property
     def operations(self) -> list:
@@ -78,6 +86,14 @@ class NativeObservable:
         self.compiled = engine.CompiledObservable(obs)
         self.obs = obs
         self.dtype = dtype
+        self._lifted: engine.CompiledObservable | None = None
+
+    @property
+    def lifted(self) -> engine.CompiledObservable:
+        """O ⊗ 1 on the doubled register of a vectorised density matrix."""
+        if self._lifted is None:
+            self._lifted = engine.CompiledObservable(density.lift_observable(self.obs, self.obs.n_qubits))
+        return self._lifted
 
     def to(self, *args: Any, **kwargs: Any) -> "NativeObservable":
         for a in list(args) + list(kwargs.values()):
@@ -91,6 +107,18 @@ def _split(param_values: ParamDictType) -> tuple[dict, dict]:
     pc = param_values["circuit"] if "circuit" in param_values else param_values
     po = param_values["observables"] if "observables" in param_values else param_values
     return pc, po
+
+
+def _is_density(state: Any) -> bool:
+    return isinstance(state, Tensor) and (isinstance(state, density.DensityMatrix) or type(state).__name__ == "DensityMatrix")
+
+
+def _reverse_density(rho: Tensor) -> Tensor:
+    """Little-endian view of `[B, N, N]` density matrices: the qubit order of the row AND the column index is reversed."""
+    B, N, _ = rho.shape
+    r = engine.bit_reverse(rho.as_subclass(Tensor).reshape(B * N, N).contiguous()).reshape(B, N, N).transpose(1, 2).contiguous()
+    r = engine.bit_reverse(r.reshape(B * N, N)).reshape(B, N, N).transpose(1, 2).contiguous()
+    return r.as_subclass(density.DensityMatrix)
 
 
 def _result_device(cfg: Configuration, *dicts: Any) -> torch.device | None:
@@ -194,13 +222,26 @@ class Backend(BackendInterface):
         original = circuit
         if len(passes) > 0:
             circuit = transpile(*passes)(circuit)
-        if self.config.noise:
-            raise NotImplementedError("b200sv is a pure state-vector backend: `noise` is not supported")
+        if self.config.noise:  # noise set in the configuration (pyqtorch/backend.py:118-127)
+            set_noise(circuit, self.config.noise)
         if self.config.dropout_probability:
             raise NotImplementedError("b200sv does not implement quantum dropout (`dropout_probability` must be 0)")
         ops = convert_block(circuit.block, n_qubits=circuit.n_qubits, config=self.config)
-        native = NativeCircuit(Program(circuit.n_qubits, ops), _DTYPES[self.config.dtype], self.config.device)
+        readout = convert_readout_noise(circuit.n_qubits, self.config.noise) if self.config.noise else None
+        native = NativeCircuit(Program(circuit.n_qubits, ops), _DTYPES[self.config.dtype], self.config.device, readout)
         return ConvertedCircuit(native=native, abstract=circuit, original=original)
+
+    def _set_block_and_readout_noises(self, circuit: ConvertedCircuit, noise: NoiseHandler | None) -> None:
+        """`noise` handed to expectation / sample: set it on the abstract blocks, re-convert the native circuit IN PLACE and
+        set the readout error — sticky, like the reference (pyqtorch/backend.py:42-79; pinned by
+        tests/qadence/test_noise/test_digital_noise.py:118-127)."""
+        if not noise:
+            return
+        set_noise(circuit, noise)
+        old: NativeCircuit = circuit.native
+        ops = convert_block(circuit.abstract.block, n_qubits=old.n_qubits, config=self.config)
+        readout = convert_readout_noise(circuit.abstract.n_qubits, noise) or old.readout_noise
+        circuit.native = NativeCircuit(Program(old.n_qubits, ops), old.dtype, old._device, readout)
 
     def observable(self, observable: AbstractBlock, n_qubits: int) -> ConvertedObservable:
         block = transpile(flatten, scale_primitive_blocks_only)(observable)  # type: ignore[call-overload]
@@ -211,8 +252,11 @@ class Backend(BackendInterface):
     def _state_in(self, state: Tensor | None, n_qubits: int) -> Tensor | None:
         if state is None:
             return None
-        if type(state).__name__ == "DensityMatrix":
-            raise NotImplementedError("b200sv is a pure state-vector backend: density-matrix states are not supported")
+        if _is_density(state):
+            if state.dim() != 3 or state.shape[1] != 2**n_qubits or state.shape[2] != 2**n_qubits:
+                raise ValueError("The initial state must be composed of tensors/arrays of size "
+                                 f"(batch_size, 2**n_qubits, 2**n_qubits). Found: {state.shape = }.")  # backends/utils.py:119-129
+            return state
         validate_state(state, n_qubits)
         if is_pyq_shape(state, n_qubits) and not (state.dim() == 2 and state.shape[1] == 2**n_qubits):
             state = unpyqify(state)
@@ -229,9 +273,15 @@ class Backend(BackendInterface):
     ) -> Tensor:
         n = circuit.abstract.n_qubits
         nat: NativeCircuit = circuit.native
-        out = engine.run(nat.compiled, param_values, self._state_in(state, n), dtype=nat.dtype, device=nat._device)
-        if endianness != self.native_endianness:
-            out = engine.bit_reverse(out)
+        state = self._state_in(state, n)
+        if nat.is_noisy or _is_density(state):  # mixed state: `[B, 2^n, 2^n]` DensityMatrix (backends/utils.py:140-147)
+            out = density.run(nat.density, param_values, state, dtype=nat.dtype, device=nat._device)
+            if endianness != self.native_endianness:
+                out = _reverse_density(out)
+        else:
+            out = engine.run(nat.compiled, param_values, state, dtype=nat.dtype, device=nat._device)
+            if endianness != self.native_endianness:
+                out = engine.bit_reverse(out)
         dev = _result_device(self.config, param_values, state)
         return out if dev is None else out.to(dev)
 
@@ -246,8 +296,7 @@ class Backend(BackendInterface):
         mitigation: Mitigations | None = None,
         endianness: Endianness = Endianness.BIG,
     ) -> Tensor:
-        if noise is not None and measurement is None:
-            logger.warning(f"Errors of type {noise} are not implemented for exact expectation yet. This is ignored for now.")
+        self._set_block_and_readout_noises(circuit, noise)  # pyqtorch/backend.py:191
         pc, po = _split(param_values)
         n = circuit.abstract.n_qubits
         nat: NativeCircuit = circuit.native
@@ -255,8 +304,14 @@ class Backend(BackendInterface):
         values = pc if isinstance(pc, ParamTable) and po is pc else dict(pc)
         if po is not pc:
             values.update(po)
-        out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, self._state_in(state, n),
-                                 dtype=nat.dtype, device=nat._device)
+        state = self._state_in(state, n)
+        if nat.is_noisy or _is_density(state):  # Tr(O ρ); differentiate with diff_mode="gpsr"
+            if endianness != self.native_endianness and state is not None:
+                raise NotImplementedError("little-endian initial density matrices are not supported")
+            out = density.expectation(nat.density, [o.native.lifted for o in observable], values, state, dtype=nat.dtype, device=nat._device)
+        else:
+            out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, state,
+                                     dtype=nat.dtype, device=nat._device)
         dev = _result_device(self.config, pc, po, state)
         return out if dev is None else out.to(dev)
 
@@ -271,12 +326,29 @@ class Backend(BackendInterface):
         endianness: Endianness = Endianness.BIG,
         pyqify_state: bool = True,
     ) -> list[Counter]:
-        if noise is not None or mitigation is not None:
-            raise NotImplementedError("b200sv is a pure state-vector backend: readout noise / mitigation are not supported")
+        self._set_block_and_readout_noises(circuit, noise)  # pyqtorch/backend.py:298
         n = circuit.abstract.n_qubits
         nat: NativeCircuit = circuit.native
-        return engine.sample(nat.compiled, param_values, n_shots, self._state_in(state, n), dtype=nat.dtype,
-                             device=nat._device, little_endian=endianness != Endianness.BIG)
+        state = self._state_in(state, n)
+        little = endianness != Endianness.BIG
+        if nat.is_noisy or nat.readout_noise is not None or _is_density(state):
+            # outcome probabilities of ρ (or ψ), corrupted by the readout confusion map, then the same inverse-CDF sampler
+            if nat.is_noisy or _is_density(state):
+                probs = density.probabilities(density.run(nat.density, param_values, state, dtype=nat.dtype, device=nat._device))
+            else:
+                probs = density.probabilities(engine.run(nat.compiled, param_values, state, dtype=nat.dtype, device=nat._device))
+            if nat.readout_noise is not None:
+                probs = nat.readout_noise.apply(probs, device=nat._device)
+            samples = density.sample_probabilities(probs, n_shots, little_endian=little)
+        else:
+            samples = engine.sample(nat.compiled, param_values, n_shots, state, dtype=nat.dtype, device=nat._device, little_endian=little)
+        if mitigation is not None:
+            from qadence.mitigations.protocols import apply_mitigation
+
+            logger.warning("Mitigation protocol is deprecated. Use qadence-protocols instead.")
+            assert noise
+            samples = apply_mitigation(noise=noise, mitigation=mitigation, samples=samples)
+        return samples
 
     def assign_parameters(self, circuit: ConvertedCircuit, param_values: ParamDictType) -> Any:
         raise NotImplementedError

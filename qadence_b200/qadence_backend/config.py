@@ -1,7 +1,7 @@
 """`Configuration` of the b200sv backend — mirrors
 `/root/reference/qadence/backends/pyqtorch/config.py:21-90` (same option names so that user
 configuration dicts keep working; options that only make sense for pyqtorch are accepted and
-ignored, those that would need density matrices raise at convert time)."""
+ignored)."""
 
 from __future__ import annotations
 
@@ -41,7 +41,9 @@ class Configuration(BackendConfiguration):
     """Accepted for compatibility; the fusion planner always merges chains of single-qubit gates."""
     loop_expectation: bool = False
     """Accepted for compatibility; the batched path never materialises per-term states."""
-    noise: None = None
+    noise: object = None
+    """`NoiseHandler` applied at conversion time (pyqtorch/config.py:62): digital noise on every primitive block — the
+    circuit then runs as a density matrix (qadence_b200/density.py) — and/or readout noise for `sample`."""
     dropout_probability: float = 0.0
     """Quantum dropout is not supported: a non-zero value raises at conversion time."""
     dropout_mode: object = None

@@ -54,6 +54,45 @@ def _projector_matrix(ket: str, bra: str) -> np.ndarray:
     return m
 
 
+def convert_digital_noise(noise: Any) -> tuple:
+    """`NoiseHandler` → ((protocol name, (error probabilities...)), ...) of its DIGITAL part — the information the reference
+    packs into `pyq.noise.DigitalNoiseProtocol` (backends/pyqtorch/convert_ops.py:354-372)."""
+    from qadence.types import NoiseProtocol
+
+    digital = noise.filter(NoiseProtocol.DIGITAL)
+    if digital is None:
+        return ()
+    out = []
+    for proto, option in zip(digital.protocol, digital.options):
+        p = option.get("error_probability")
+        probs = tuple(float(x) for x in torch.as_tensor(p, dtype=torch.float64).reshape(-1).tolist())
+        out.append((str(getattr(proto, "value", proto)), probs))
+    return tuple(out)
+
+
+def convert_readout_noise(n_qubits: int, noise: Any) -> Any:
+    """READOUT part of a `NoiseHandler` → `density.ReadoutNoise` (backends/pyqtorch/convert_ops.py:375-393)."""
+    from qadence.types import NoiseProtocol
+
+    from ..density import ReadoutNoise
+
+    readout = noise.filter(NoiseProtocol.READOUT)
+    if readout is None:
+        return None
+    options = dict(readout.options[0])
+    if readout.protocol[0] == NoiseProtocol.READOUT.INDEPENDENT:
+        options.pop("confusion_matrix", None)
+    elif options.get("confusion_matrix") is None:
+        raise ValueError("correlated readout noise needs a `confusion_matrix` option")
+    return ReadoutNoise(n_qubits, **options)
+
+
+def _with_noise(ops: list[Op], noise: tuple) -> list[Op]:
+    if noise:
+        ops[-1].noise = noise
+    return ops
+
+
 def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -> list[Op]:
     """Block tree → ordered list of ops (an `AddBlock` becomes one ADD op holding sub-programs)."""
     from qadence.blocks import (
@@ -77,8 +116,9 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
     qs = block.qubit_support
     if n_qubits is None:
         n_qubits = max(qs) + 1
-    if getattr(block, "noise", None):
-        raise NotImplementedError("b200sv is a pure state-vector backend: digital noise on blocks is not supported")
+    # digital noise set on a primitive block (`set_noise`) travels on the op and is applied by the density-matrix path
+    # (qadence_b200/density.py); like the reference, Scale / HamEvo / composite blocks do not take it (convert_ops.py:206-269)
+    noise = convert_digital_noise(block.noise) if getattr(block, "noise", None) else ()
 
     if isinstance(block, ScaleBlock):
         return [*convert_block(block.block, n_qubits, config), Op(OpKind.SCALE, param=extract_parameter(block, config), label="Scale")]
@@ -87,6 +127,8 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
         gen = block.generator
         if getattr(gen, "is_time_dependent", False):
             return [_convert_time_dependent(block, n_qubits, config)]
+        if len(getattr(block, "noise_operators", None) or []) > 0:
+            raise NotImplementedError("b200sv: Lindblad `noise_operators` of HamEvo (analog noise) are not supported")
         names = config.get_param_name(block)
         if isinstance(gen, sympy.Basic):  # symbolic matrix generator: looked up in param_values (convert_ops.py:231-232)
             generator: Any = names[1]
@@ -104,7 +146,7 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
         m = block.matrix.detach().to(torch.complex128).numpy()
         m = m.reshape(m.shape[-2], m.shape[-1])
         kind = OpKind.MAT1 if len(qs) == 1 else OpKind.MATK
-        return [Op(kind, tuple(qs), (), matrix=m, label="MatrixBlock")]
+        return _with_noise([Op(kind, tuple(qs), (), matrix=m, label="MatrixBlock")], noise)
 
     if isinstance(block, CompositeBlock):
         if isinstance(block, AddBlock):
@@ -114,9 +156,9 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
     if isinstance(block, tuple(non_unitary_gateset)):
         if isinstance(block, ProjectorBlock):
             if block.name == "N":  # N(t, state="0") keeps name "N": |1><1| like the reference (convert_ops.py:284-285)
-                return [Op(OpKind.MAT1, (q,), (), matrix=CONST_MATS["N"].copy(), label="N") for q in qs]
+                return _with_noise([Op(OpKind.MAT1, (q,), (), matrix=CONST_MATS["N"].copy(), label="N") for q in qs], noise)
             m = _projector_matrix(block.ket, block.bra)
-            return [Op(OpKind.MAT1 if len(qs) == 1 else OpKind.MATK, tuple(qs), (), matrix=m, label="Projector")]
+            return _with_noise([Op(OpKind.MAT1 if len(qs) == 1 else OpKind.MATK, tuple(qs), (), matrix=m, label="Projector")], noise)
         return [Op(OpKind.MAT1, (qs[0],), (), matrix=CONST_MATS["Zero"].copy(), label="Zero")]
 
     if isinstance(block, tuple(single_qubit_gateset)):
@@ -126,23 +168,23 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
                     config.get_param_name(block) if block.is_parametric else [_numeric(p) for p in block.parameters.expressions()]
                 )
                 t = qs[0]
-                return [Op(OpKind.RZ, (t,), (), param=phi, label="U.phi"), Op(OpKind.RY, (t,), (), param=theta, label="U.theta"),
-                        Op(OpKind.RZ, (t,), (), param=omega, label="U.omega")]
-            return [Op(_ROT[block.name], (qs[0],), (), param=extract_parameter(block, config), label=str(block.name))]
-        return [Op(OpKind.MAT1, (qs[0],), (), matrix=CONST_MATS[str(block.name)].copy(), label=str(block.name))]
+                return _with_noise([Op(OpKind.RZ, (t,), (), param=phi, label="U.phi"), Op(OpKind.RY, (t,), (), param=theta, label="U.theta"),
+                                    Op(OpKind.RZ, (t,), (), param=omega, label="U.omega")], noise)
+            return _with_noise([Op(_ROT[block.name], (qs[0],), (), param=extract_parameter(block, config), label=str(block.name))], noise)
+        return _with_noise([Op(OpKind.MAT1, (qs[0],), (), matrix=CONST_MATS[str(block.name)].copy(), label=str(block.name))], noise)
 
     if isinstance(block, tuple(two_qubit_gateset)) or isinstance(block, tuple(three_qubit_gateset) + tuple(multi_qubit_gateset)):
         name = str(block.name)
         base = name[1:] if name.startswith("M") else name  # MCRX -> CRX, MCZ -> CZ (convert_ops.py:327)
         if base in ("SWAP",):
-            return [Op(OpKind.SWAP, (qs[0], qs[1]), (), label="SWAP")]
+            return _with_noise([Op(OpKind.SWAP, (qs[0], qs[1]), (), label="SWAP")], noise)
         if base == "CSWAP":
-            return [Op(OpKind.SWAP, tuple(qs[-2:]), tuple(qs[:-2]), label="CSWAP")]
+            return _with_noise([Op(OpKind.SWAP, tuple(qs[-2:]), tuple(qs[:-2]), label="CSWAP")], noise)
         controls, target = tuple(qs[:-1]), qs[-1]
         if isinstance(block, ParametricBlock):
-            return [Op(_ROT[base[1:]], (target,), controls, param=extract_parameter(block, config), label=name)]
+            return _with_noise([Op(_ROT[base[1:]], (target,), controls, param=extract_parameter(block, config), label=name)], noise)
         inner = {"CNOT": "X", "CZ": "Z", "Toffoli": "X"}[base]
-        return [Op(OpKind.MAT1, (target,), controls, matrix=CONST_MATS[inner].copy(), label=name)]
+        return _with_noise([Op(OpKind.MAT1, (target,), controls, matrix=CONST_MATS[inner].copy(), label=name)], noise)
 
     raise NotImplementedError(
         f"Non supported operation of type {type(block)}. "

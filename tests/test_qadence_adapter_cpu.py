@@ -61,9 +61,19 @@ def oracle_device(monkeypatch: pytest.MonkeyPatch) -> None:
         idx = oracle.sample_indices(oracle.probabilities(psi), u)
         return [Counter({(k[::-1] if little_endian else k): v for k, v in d.items()}) for d in oracle.counts_from_indices(idx, cp.n_qubits)]
 
+    def apply_observable(cob, psi, values):
+        if cob.pauli is not None:
+            return oracle.from_pyq_shape(oracle.paulisum_apply(cob.obs, oracle.to_pyq_shape(psi, cob.n_qubits), values))
+        return oracle.run(cob.obs, values, psi)
+
+    def sample_indices(psi, uniforms):
+        return torch.as_tensor(oracle.sample_indices(oracle.probabilities(psi), uniforms.numpy()))
+
     monkeypatch.setattr(engine, "run", run)
     monkeypatch.setattr(engine, "expectation", expectation)
     monkeypatch.setattr(engine, "sample", sample)
+    monkeypatch.setattr(engine, "apply_observable", apply_observable)
+    monkeypatch.setattr(engine, "sample_indices", sample_indices)
     monkeypatch.setattr(engine, "bit_reverse", lambda psi: oracle.invert_endianness_state(psi, int(psi.shape[1]).bit_length() - 1))
 
 
@@ -536,3 +546,169 @@ def test_custom_transpilation_passes() -> None:
     assert conv.circuit.original == conv_none.circuit.original
     assert conv.circuit.abstract != conv_none.circuit.abstract
     assert len(conv.circuit.native.program.ops) == len(conv_none.circuit.native.program.ops) == 2
+
+
+# ------------------------------------------------------------------------------------------ digital / readout noise
+def _dense_noisy_density(block, n: int, noise_after: dict, values: dict | None = None) -> np.ndarray:
+    """ρ of a chain of primitive blocks from the reference's dense matrices (block_to_tensor) and explicit Kraus sums."""
+    from qadence_b200 import density
+
+    rho = np.zeros((2**n, 2**n), dtype=np.complex128)
+    rho[0, 0] = 1.0
+    for k, b in enumerate(block.blocks if hasattr(block, "blocks") else [block]):
+        u = block_to_tensor(b, values or {}, qubit_support=tuple(range(n)))[0].numpy()
+        rho = u @ rho @ u.conj().T
+        for name, probs in noise_after.get(k, ()):
+            q = b.qubit_support[-1]
+            ks = [np.kron(np.kron(np.eye(2**q), kk), np.eye(2 ** (n - q - 1))) for kk in density.kraus_operators(name, probs)]
+            rho = sum(kk @ rho @ kk.conj().T for kk in ks)
+    return rho
+
+
+@pytest.mark.parametrize("noisy_config", ["BITFLIP", ["BITFLIP", "PHASEFLIP"]])
+def test_run_digital_noise_like_the_reference_test(oracle_device: None, noisy_config) -> None:
+    """Mirror of /root/reference/tests/qadence/test_noise/test_digital_noise.py:74-98 on this backend, plus the numbers."""
+    from qadence import NoiseHandler, NoiseProtocol, hamiltonian_factory, set_noise
+
+    protos = [getattr(NoiseProtocol.DIGITAL, p) for p in (noisy_config if isinstance(noisy_config, list) else [noisy_config])]
+    block = kron(H(0), Z(1))
+    circuit = QuantumCircuit(2, block)
+    observable = hamiltonian_factory(circuit.n_qubits, detuning=Z)
+    noise = NoiseHandler(protos if len(protos) > 1 else protos[0], {"error_probability": 0.1})
+    model = QuantumModel(circuit=circuit, observable=observable, backend="b200sv", diff_mode=DiffMode.GPSR)
+    noiseless_output = model.run()
+    assert noiseless_output.shape == (1, 4)
+    set_noise(circuit, noise)
+    noisy_model = QuantumModel(circuit=circuit, observable=observable, backend="b200sv", diff_mode=DiffMode.GPSR)
+    noisy_output = noisy_model.run()
+    assert type(noisy_output).__name__ == "DensityMatrix" and noisy_output.shape == (1, 4, 4)
+    pure = torch.einsum("bi,bj->bij", noiseless_output, noiseless_output.conj())
+    assert not torch.allclose(pure, noisy_output.as_subclass(torch.Tensor))
+    backend = backend_factory(backend="b200sv", diff_mode=DiffMode.GPSR)
+    (conv_circ, _, embed, params) = backend.convert(circuit)
+    native_output = backend.run(conv_circ, embed(params, {}))
+    assert torch.allclose(noisy_output.as_subclass(torch.Tensor), native_output.as_subclass(torch.Tensor))
+    each = tuple((str(p.value), (0.1,)) for p in protos)
+    want = _dense_noisy_density(block, 2, {0: each, 1: each})
+    assert np.abs(noisy_output[0].as_subclass(torch.Tensor).numpy() - want).max() < 1e-12
+    assert abs(np.trace(want) - 1) < 1e-12
+
+
+@pytest.mark.parametrize("noisy_config", ["BITFLIP", ["BITFLIP", "PHASEFLIP"]])
+def test_expectation_digital_noise_like_the_reference_test(oracle_device: None, noisy_config) -> None:
+    """Mirror of test_digital_noise.py:101-127: `noise=` at expectation time is sticky on the converted circuit."""
+    from qadence import NoiseHandler, NoiseProtocol, hamiltonian_factory
+
+    protos = [getattr(NoiseProtocol.DIGITAL, p) for p in (noisy_config if isinstance(noisy_config, list) else [noisy_config])]
+    block = kron(H(0), Z(1))
+    circuit = QuantumCircuit(2, block)
+    observable = hamiltonian_factory(circuit.n_qubits, detuning=Z)
+    noise = NoiseHandler(protos if len(protos) > 1 else protos[0], {"error_probability": 0.1})
+    backend = backend_factory(backend="b200sv", diff_mode=DiffMode.GPSR)
+    model = QuantumModel(circuit=circuit, observable=observable, backend="b200sv", diff_mode=DiffMode.GPSR)
+    noiseless_expectation = model.expectation(values={})
+    (conv_circ, conv_obs, embed, params) = backend.convert(circuit, observable)
+    native_noisy_expectation = backend.expectation(conv_circ, conv_obs, embed(params, {}), noise=noise)
+    assert not torch.allclose(noiseless_expectation, native_noisy_expectation)
+    noisy_model = QuantumModel(circuit=circuit, observable=observable, noise=noise, backend="b200sv", diff_mode=DiffMode.GPSR)
+    assert torch.allclose(noisy_model.expectation(values={}), native_noisy_expectation)
+    (conv_circ, conv_obs, embed, params) = backend.convert(circuit, observable)
+    assert torch.allclose(backend.expectation(conv_circ, conv_obs, embed(params, {})), native_noisy_expectation)
+    # numbers: Tr(O rho) with the dense Kraus evolution
+    each = tuple((str(p.value), (0.1,)) for p in protos)
+    rho = _dense_noisy_density(block, 2, {0: each, 1: each})
+    o = block_to_tensor(observable, {}, qubit_support=(0, 1))[0].numpy()
+    assert abs(float(native_noisy_expectation) - np.trace(o @ rho).real) < 1e-12
+
+
+@pytest.mark.parametrize("protocol,probs", [("BITFLIP", 0.2), ("PHASEFLIP", 0.15), ("DEPOLARIZING", 0.3), ("PAULI_CHANNEL", (0.1, 0.2, 0.05)),
+                                            ("AMPLITUDE_DAMPING", 0.4), ("PHASE_DAMPING", 0.35), ("GENERALIZED_AMPLITUDE_DAMPING", (0.6, 0.3))])
+def test_every_digital_protocol_on_a_parametric_circuit(oracle_device: None, protocol: str, probs) -> None:
+    from qadence import NoiseHandler, NoiseProtocol
+
+    n = 3
+    block = chain(RX(0, "a"), RY(1, "b"), CNOT(0, 1), RZ(2, "a"), CRX(1, 2, "b"), H(0), CPHASE(2, 0, 0.7))
+    noise = NoiseHandler(getattr(NoiseProtocol.DIGITAL, protocol), {"error_probability": probs})
+    obs = [add(Z(0), Z(1), Z(2)), kron(X(0), Y(2))]
+    from qadence_b200.qadence_backend.config import Configuration
+
+    backend = backend_factory(backend="b200sv", diff_mode=None, configuration=Configuration(noise=noise))
+    conv = backend.convert(QuantumCircuit(n, block), obs)
+    vals = {"a": torch.tensor([0.3, 1.1]), "b": torch.tensor([-0.8, 2.0])}
+    rho = backend.run(conv.circuit, conv.embedding_fn(conv.params, vals))
+    ex = backend.expectation(conv.circuit, conv.observable, conv.embedding_fn(conv.params, vals))
+    assert rho.shape == (2, 8, 8) and ex.shape == (2, 2)
+    p = tuple(probs) if isinstance(probs, tuple) else (probs,)
+    name = str(getattr(NoiseProtocol.DIGITAL, protocol).value)
+    for b in range(2):
+        v = {k: t[b:b + 1] for k, t in vals.items()}
+        want = _dense_noisy_density(block, n, {k: ((name, p),) for k in range(7)}, v)
+        assert np.abs(rho[b].as_subclass(torch.Tensor).numpy() - want).max() < 1e-12
+        for j, o in enumerate(obs):
+            om = block_to_tensor(o, {}, qubit_support=tuple(range(n)))[0].numpy()
+            assert abs(float(ex[b, j]) - np.trace(om @ want).real) < 1e-12
+
+
+def test_gpsr_gradient_of_a_noisy_expectation(oracle_device: None) -> None:
+    """The parameter-shift rules hold for noisy expectations: dE/dθ by GPSR == finite difference of Tr(O ρ(θ))."""
+    from qadence import NoiseHandler, NoiseProtocol
+
+    block = chain(RX(0, "th"), CNOT(0, 1), RY(1, 0.4))
+    noise = NoiseHandler(NoiseProtocol.DIGITAL.DEPOLARIZING, {"error_probability": 0.15})
+    model = QuantumModel(QuantumCircuit(2, block), observable=add(Z(0), Z(1)), backend="b200sv", diff_mode=DiffMode.GPSR, noise=noise)
+    th = [p_ for p_ in model.parameters() if p_.requires_grad][0]
+    e = model.expectation({})
+    (g,) = torch.autograd.grad(e.sum(), th)
+
+    def value(t: float) -> float:
+        each = (("Depolarizing", (0.15,)),)
+        rho = _dense_noisy_density(chain(RX(0, t), CNOT(0, 1), RY(1, 0.4)), 2, {0: each, 1: each, 2: each})
+        o = block_to_tensor(add(Z(0), Z(1)), {}, qubit_support=(0, 1))[0].numpy()
+        return float(np.trace(o @ rho).real)
+
+    t0 = float(th.detach().reshape(-1)[0])
+    assert abs(float(e) - value(t0)) < 1e-12
+    assert abs(float(g.reshape(-1)[0]) - (value(t0 + 1e-6) - value(t0 - 1e-6)) / 2e-6) < 1e-8
+
+
+def test_readout_noise_changes_the_sample_distribution(oracle_device: None) -> None:
+    """Statistical contract of /root/reference/tests/qadence/test_noise/test_readout.py:67-110."""
+    from qadence import NoiseHandler, NoiseProtocol
+
+    circuit = QuantumCircuit(2, kron(X(0), X(1)))
+    model = QuantumModel(circuit, backend="b200sv", diff_mode=DiffMode.GPSR)
+    clean = model.sample(n_shots=400)[0]
+    assert clean == Counter({"11": 400})
+    noise = NoiseHandler(NoiseProtocol.READOUT.INDEPENDENT, {"error_probability": 0.25, "seed": 0})
+    noisy = model.sample(n_shots=4000, noise=noise)[0]
+    assert sum(noisy.values()) == 4000 and set(noisy) == {"00", "01", "10", "11"}
+    assert abs(noisy["11"] / 4000 - 0.75**2) < 0.04 and abs(noisy["00"] / 4000 - 0.25**2) < 0.03
+    cm = torch.zeros(4, 4)
+    cm[0, 3] = 1.0  # every "11" is read as "00"
+    cm[1, 1] = cm[2, 2] = cm[3, 0] = 1.0
+    corr = NoiseHandler(NoiseProtocol.READOUT.CORRELATED, {"confusion_matrix": cm, "seed": 0})
+    model2 = QuantumModel(QuantumCircuit(2, kron(X(0), X(1))), backend="b200sv", diff_mode=DiffMode.GPSR)
+    assert model2.sample(n_shots=100, noise=corr)[0] == Counter({"00": 100})
+
+
+def test_density_matrix_initial_state_and_little_endian(oracle_device: None) -> None:
+    from qadence_b200.density import DensityMatrix
+
+    block = chain(RX(0, 0.3), CNOT(0, 1), RY(2, 1.2))
+    backend = backend_factory(backend="b200sv", diff_mode=None)
+    conv = backend.convert(QuantumCircuit(3, block), [Z(0) + Z(2)])
+    psi0 = torch.randn(2, 8, dtype=torch.cdouble)
+    psi0 = psi0 / psi0.norm(dim=1, keepdim=True)
+    rho0 = torch.einsum("bi,bj->bij", psi0, psi0.conj()).as_subclass(DensityMatrix)
+    psi = backend.run(conv.circuit, {}, state=psi0)
+    rho = backend.run(conv.circuit, {}, state=rho0)
+    assert type(rho).__name__ == "DensityMatrix"
+    assert torch.allclose(rho.as_subclass(torch.Tensor), torch.einsum("bi,bj->bij", psi, psi.conj()), atol=1e-12)
+    e_psi = backend.expectation(conv.circuit, conv.observable, {}, state=psi0)
+    e_rho = backend.expectation(conv.circuit, conv.observable, {}, state=rho0)
+    assert torch.allclose(e_psi, e_rho, atol=1e-12)
+    little = backend.run(conv.circuit, {}, state=rho0, endianness=Endianness.LITTLE).as_subclass(torch.Tensor)
+    psi_l = backend.run(conv.circuit, {}, state=psi0, endianness=Endianness.LITTLE)
+    assert torch.allclose(little, torch.einsum("bi,bj->bij", psi_l, psi_l.conj()), atol=1e-12)
+    with pytest.raises(ValueError):
+        backend.run(conv.circuit, {}, state=torch.zeros(1, 4, 4, dtype=torch.cdouble).as_subclass(DensityMatrix))

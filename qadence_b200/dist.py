@@ -466,7 +466,7 @@ class PeerShardedSimulator:
         cfg = TileConfig.default(dtype == torch.complex128, False)
         # (2^12-amplitude tiles, B200SV_TILE_FWD_C128=12,4,2, are 15 % faster up to n = 31 but slowed one straddling sweep of
         #  the 36-qubit run from ~0.4 s to 1.9 s — see profiles/r01_multi_gpu.md; the batch default 2^11 is kept)
-        self.plan = DevicePlan(build_plan(list(program.ops), self.n, self.slot_of, cfg), self.device)
+        self.plan = DevicePlan(build_plan(list(program.ops), self.n, self.slot_of, cfg, packer="greedy"), self.device)
         self.shards = PeerShards(self.n_local, dtype, rank, world, self.device, group)
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.time_sweeps = False  # diagnostics: per-sweep CUDA-event times (incl. the barrier) in `sweep_ms`

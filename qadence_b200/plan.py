@@ -197,6 +197,116 @@ def _pack(gates: list[_G], capacity: int, forced: set[int], max_gates: int) -> l
     return groups
 
 
+# ---- tile search ------------------------------------------------------------------------------------
+# `_pack` takes the tile bits in the order the gates ask for them.  On layered circuits that leaves short tail sweeps and
+# half-empty tiles (hea(20, 8): 11 forward / 13 adjoint sweeps).  `_pack_search` chooses each sweep's tile among a few
+# candidates — first-fit (with the first k frontier gates postponed) and contiguous windows of index bits, which let a sweep
+# run a whole light-cone "trapezoid" of several layers — by a small beam search on the cost model
+#   cost(plan) = Σ_sweeps (STREAM_COST + n_rounds)
+# (one streaming pass of the state costs about three rounds of in-tile work, profiles/r01h_final_build.md).  The acceptance
+# rule is `_pack`'s — a gate joins a sweep only if it commutes with every gate deferred before it — so the execution stays
+# equivalent to the source order by the same argument; hea(20, 8) becomes 8 forward / 8 adjoint sweeps.
+STREAM_COST = 3.0
+SEARCH_WINDOW = 6 * MAX_GATES_PER_SWEEP  # pending gates looked at per sweep (keeps planning linear in the gate count)
+BEAM_WIDTH = 3
+
+
+def _take(pending: list[_G], tile: set[int], max_gates: int) -> tuple[list[_G], list[_G]]:
+    """Gates of `pending` (ordered) a sweep over `tile` executes, and the rest (still ordered)."""
+    taken: list[_G] = []
+    deferred: list[_G] = []
+    def_any: set[int] = set()
+    def_hard: set[int] = set()
+    head, tail = pending[:SEARCH_WINDOW], pending[SEARCH_WINDOW:]
+    for g in head:
+        hard = set(g.hard)
+        if hard <= tile and len(taken) < max_gates and not (g.bits_any & def_hard) and not (hard & def_any):
+            taken.append(g)
+        else:
+            deferred.append(g)
+            def_any |= g.bits_any
+            def_hard |= hard
+    return taken, deferred + tail
+
+
+def _firstfit_bits(pending: list[_G], capacity: int, forced: set[int], skip: int) -> set[int]:
+    """Tile bits `_pack` would choose, after postponing the first `skip` frontier gates that ask for new bits."""
+    bits = set(forced)
+    def_any: set[int] = set()
+    def_hard: set[int] = set()
+    for g in pending[:SEARCH_WINDOW]:
+        hard = set(g.hard)
+        commutes = not (g.bits_any & def_hard) and not (hard & def_any)
+        wants_new = bool(hard) and not hard <= bits
+        if commutes and len(bits | hard) <= capacity and not (skip > 0 and wants_new):
+            bits |= hard
+        else:
+            if commutes and skip > 0 and wants_new:
+                skip -= 1
+            def_any |= g.bits_any
+            def_hard |= hard
+    return bits
+
+
+def _candidate_tiles(pending: list[_G], n: int, m: int, forced: set[int]) -> list[frozenset]:
+    cands: list[set[int]] = [_firstfit_bits(pending, m, forced, skip) for skip in range(6)]
+    w = m - len(forced)
+    for s in range(len(forced), n - w + 1):
+        cands.append(set(forced) | set(range(s, s + w)))
+    out: list[frozenset] = []
+    for t in cands:
+        for p in range(n):  # complete with the lowest unused bit positions (as build_plan does)
+            if len(t) >= m:
+                break
+            t.add(p)
+        ft = frozenset(t)
+        if ft not in out:
+            out.append(ft)
+    return out
+
+
+def _pack_search(gates: list[_G], n: int, m: int, r: int, forced: set[int], max_gates: int, chains: bool) -> list[tuple[list[_G], set[int]]]:
+    if n <= m or not gates:
+        return _pack(gates, m, forced, max_gates)
+    states: list[tuple[float, list[_G], list]] = [(0.0, list(gates), [])]
+    done: list[tuple[float, list[_G], list]] = []
+    while states:
+        nxt: list[tuple[float, list[_G], list]] = []
+        for cost, pending, groups in states:
+            opts = []
+            for tile in _candidate_tiles(pending, n, m, forced):
+                taken, deferred = _take(pending, set(tile), max_gates)
+                if not taken:
+                    continue
+                try:
+                    n_rounds = len(_pack_rounds(taken, r, set(tile), chains))
+                except RuntimeError:
+                    continue
+                work = sum(1.0 if not _is_perm(g) else 0.05 for g in taken)
+                opts.append((work / (STREAM_COST + n_rounds), taken, deferred, tile, n_rounds))
+            if not opts:
+                raise RuntimeError("planner stalled (gate needs more register bits than the tile offers)")
+            opts.sort(key=lambda o: -o[0])
+            for _, taken, deferred, tile, n_rounds in opts[:BEAM_WIDTH]:
+                st = (cost + STREAM_COST + n_rounds, deferred, groups + [(taken, set(tile))])
+                (nxt if deferred else done).append(st)
+        # rank partial plans by cost so far + an optimistic estimate of the rest (full rounds, no further streaming)
+        nxt.sort(key=lambda st: st[0] + sum(1 for g in st[1] if not _is_perm(g)) / r)
+        states = nxt[:BEAM_WIDTH]
+    best = min(done, key=lambda st: st[0])
+    # the beam is a heuristic: never return something the first-fit packer does better
+    greedy = _pack(gates, m, forced, max_gates)
+    greedy_cost = 0.0
+    for sgates, bits in greedy:
+        tile = set(bits)
+        for p in range(n):
+            if len(tile) >= m:
+                break
+            tile.add(p)
+        greedy_cost += STREAM_COST + len(_pack_rounds(sgates, r, tile, chains))
+    return best[2] if best[0] < greedy_cost else greedy
+
+
 @dataclass
 class _Round:
     """One round of a sweep: M chains (global target bit -> gates), G gates, P gates."""
@@ -383,7 +493,7 @@ class SweepPlan:
 
 
 def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConfig, chains: bool = True,
-               n_total: int | None = None) -> SweepPlan:
+               n_total: int | None = None, packer: str | None = None) -> SweepPlan:
     """Plan a run of simple gates on `n` LOCAL qubits.  With `n_total > n` the state is sharded by its
     highest-order qubits: qubit q maps to bit n_total-1-q, bits >= n are rank bits and may only be
     touched diagonally / as controls (evaluated from `index_hi` by the kernels)."""
@@ -398,7 +508,16 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         if any(b >= n for b in g_.hard):
             raise ValueError("non-diagonal gate on a global (rank) qubit: make it local first (dist.plan_layout)")
     forced = set(range(min(cfg.low, m)))
-    sweep_groups = _pack(lowered, m, forced, MAX_GATES_PER_SWEEP)
+    # tile choice: "search" (beam search on the sweep/round cost model) or "greedy" (first fit; the sharded paths keep it:
+    # their NVLink traffic was measured with it, and sweeps whose tiles avoid the rank bits stay local)
+    if packer is None:
+        import os
+
+        packer = os.environ.get("B200SV_PLANNER", "search")
+    if packer == "search" and n_total == n:
+        sweep_groups = _pack_search(lowered, n, m, r, forced, MAX_GATES_PER_SWEEP, chains)
+    else:
+        sweep_groups = _pack(lowered, m, forced, MAX_GATES_PER_SWEEP)
 
     sweeps = np.zeros(len(sweep_groups), dtype=SWEEP_DT)
     rounds_l: list[np.ndarray] = []

@@ -76,7 +76,9 @@ def test_hea_fuses_into_few_sweeps() -> None:
     cfg = TileConfig.default(True, False)
     plan = build_plan(prog.ops, n, slot_of, cfg)
     assert len(prog.ops) == 632
-    assert plan.n_sweeps <= 16, plan.n_sweeps  # vs 632 state round trips gate by gate
+    assert plan.n_sweeps <= 8, plan.n_sweeps  # vs 632 state round trips gate by gate (first-fit tiles: 11)
+    assert build_plan(prog.ops, n, slot_of, TileConfig.default(True, True)).n_sweeps <= 8  # adjoint geometry (first fit: 13)
+    assert build_plan(prog.ops, n, slot_of, cfg, packer="greedy").n_sweeps == 11
     assert int(plan.rounds["n_exec"].sum()) == 0  # no interpreter entries: merged 2x2 + folded CNOT permutations only
     for sw in plan.sweeps:
         assert set(range(cfg.low)) <= set(int(x) for x in sw["tile_bits"][: sw["m"]])  # coalesced low bits
@@ -131,3 +133,55 @@ def test_chain_moment_gradients_match_oracle(cfg: TileConfig) -> None:
     np.testing.assert_allclose(back_psi, psi0, atol=1e-12)
     for nm, i in slot_of.items():
         np.testing.assert_allclose(grads[i], want_g[nm].numpy(), atol=1e-11, err_msg=nm)
+
+
+@pytest.mark.parametrize("packer", ["search", "greedy"])
+@pytest.mark.parametrize("seed", range(4))
+def test_tile_search_keeps_the_program_semantics(packer: str, seed: int) -> None:
+    """Tiles chosen by the beam search (n > m: several sweeps, windows and postponed frontier gates) execute the same
+    program: forward state and adjoint gradients equal the gate-by-gate oracle."""
+    from qadence_b200.program import PauliSum, PauliTerm
+
+    rng = np.random.default_rng(40 + seed)
+    n, B = 9, 2
+    cfg = TileConfig(m=5 + seed % 2, r=2 + seed % 2, low=2, fold=3)
+    if seed < 2:
+        prog, names = random_program(n, 60, rng)
+    else:  # layered circuit: the case the search is built for
+        prog = hea_program(n, 3)
+        names = prog.param_names
+    values = {nm: torch.tensor(rng.uniform(0.2, 1.5, size=B)) for nm in names}
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, cfg, packer=packer)
+    assert sorted(set(plan.execution_order())) == list(range(len(prog.ops)))
+    params = np.stack([values[nm].numpy() for nm in prog.param_names]) if prog.param_names else np.zeros((1, B))
+    psi0 = rng.normal(size=(B, 2**n)) + 1j * rng.normal(size=(B, 2**n))
+    want = oracle.run(prog, values, torch.tensor(psi0)).numpy()
+    got = emulate(plan, psi0, params)
+    np.testing.assert_allclose(got, want, atol=1e-10 * max(1.0, np.abs(want).max()))
+    if seed >= 2:
+        obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)])
+        want_e, want_g = oracle.adjoint_expectation_and_grads(prog, obs, values)
+        z0 = oracle.zero_state(n, B).numpy()
+        psi = emulate(plan, z0, params)
+        lam = oracle.from_pyq_shape(oracle.paulisum_apply(obs, oracle.to_pyq_shape(torch.tensor(psi), n), values)).numpy()
+        back_psi, _, grads = emulate_adjoint(plan, psi, lam, params)
+        np.testing.assert_allclose(back_psi, z0, atol=1e-12)
+        for nm, i in slot_of.items():
+            np.testing.assert_allclose(grads[i], want_g[nm].numpy(), atol=1e-11, err_msg=nm)
+
+
+def test_tile_search_never_needs_more_sweeps_than_first_fit() -> None:
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        n = int(rng.integers(7, 13))
+        prog, _ = random_program(n, int(rng.integers(30, 120)), rng)
+        slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+        cfg = TileConfig(m=int(rng.integers(4, 7)), r=int(rng.integers(2, 4)), low=2, fold=3)
+
+        def cost(plan) -> float:
+            return 3.0 * plan.n_sweeps + float(plan.sweeps["n_rounds"].sum())
+
+        a = build_plan(prog.ops, n, slot_of, cfg, packer="greedy")
+        b = build_plan(prog.ops, n, slot_of, cfg, packer="search")
+        assert cost(b) <= cost(a) + 1e-9, (trial, cost(a), cost(b))

@@ -347,7 +347,11 @@ def main() -> None:
                                        "merged_2x2_fwd": n_chain_f, "merged_2x2_adj": n_chain_a, "achieved": fp64_tflops, "peak": FP64_PEAK_TFLOPS,
                                        "unit": "TFLOP/s", "frac": fp64_tflops / FP64_PEAK_TFLOPS,
                                        "floor_ms_per_step": 2 * fp64_instr / (FP64_PEAK_TFLOPS * 1e12) * 1e3},
-                         "note": "complex128 sweeps with ~10 merged 2x2 per tile are FP64-pipe/issue bound on B200, not HBM bound (an FP64 instruction holds the issue port 2 cycles; DMMA runs at the same pipe rate), see DESIGN.md §4.1 and profiles/r01_fp64_microbench.md"},
+                         "step": {"what": "algorithmic HBM bytes of the whole step (2S per forward sweep, 4S per adjoint sweep, S init, S <O>, 2S lambda=O psi): the tile-search planner trades bandwidth fraction per sweep for FEWER sweeps, i.e. fewer bytes per step",
+                                  "hbm_bytes_per_step": (2 * fwd.n_sweeps + 4 * adj.n_sweeps + 4) * S,
+                                  "hbm_floor_ms_per_step": (2 * fwd.n_sweeps + 4 * adj.n_sweeps + 4) * S / (peak * 1e9) * 1e3,
+                                  "rounds_fwd": int(fwd.plan.sweeps["n_rounds"].sum()), "rounds_adj": int(adj.plan.sweeps["n_rounds"].sum())},
+                         "note": "complex128 sweeps with ~20 merged 2x2 per tile are FP64-pipe/issue bound on B200, not HBM bound (an FP64 instruction holds the issue port 2 cycles; DMMA runs at the same pipe rate), see DESIGN.md §4.1 and profiles/r01_fp64_microbench.md"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

@@ -52,6 +52,10 @@ class EmbedProgram:
         self.nodes, self.slot_off, self.consts = nodes, slot_off, consts
         self.var_load_root, self.feat_load_root = var_load_root, feat_load_root  # load row -> root index
         self._dev: dict = {}
+        # row name -> names of the symbols its expression depends on (None: unknown); rows that depend on nothing that
+        # requires a gradient are handed out detached (qadence's GPSR treats `requires_grad` entries as differentiable gate
+        # parameters, engines/torch/differentiable_expectation.py:80-86)
+        self.slot_symbols: dict[str, frozenset] | None = None
 
     @property
     def n_slots(self) -> int:
@@ -270,8 +274,10 @@ class ParamTable(dict):
     (`name -> tensor[batch]`) for anyone who looks inside; `engine` takes the table itself."""
 
     def __init__(self, names: Sequence[str], table: Tensor, extras: Mapping[str, Any] | None = None,
-                 input_device: torch.device | None = None):
+                 input_device: torch.device | None = None, nograd: frozenset | None = None, scalar: frozenset | None = None):
         super().__init__()
+        self.nograd = nograd or frozenset()  # rows that carry no gradient: materialised detached
+        self.scalar = scalar or frozenset()  # rows that depend on no feature: materialised with shape [1] like the reference's
         self.names = list(names)
         self.slot = {nm: i for i, nm in enumerate(self.names)}
         self.table = table
@@ -288,6 +294,10 @@ class ParamTable(dict):
     def __missing__(self, key: str) -> Any:
         if key in self.slot:
             v = self.table[self.slot[key]]
+            if key in self.scalar:
+                v = v[:1]
+            if key in self.nograd:
+                v = v.detach()
         elif key in self.extras:
             v = self.extras[key]
         else:
@@ -346,7 +356,7 @@ class ParamTable(dict):
 
     def detach(self) -> "ParamTable":
         out = ParamTable(self.names, self.table.detach(), {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in self.extras.items()},
-                         self.input_device)
+                         self.input_device, self.nograd, self.scalar)
         return out
 
 
@@ -361,7 +371,7 @@ def _resolve_device(device: torch.device | str | None) -> torch.device:
 
 
 def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, stock_fn: Callable[[dict, dict], dict],
-                      passthrough: bool) -> Callable[[dict, dict], dict]:
+                      passthrough: bool, matrix_rows: Sequence[tuple[str, str]] = ()) -> Callable[[dict, dict], dict]:
     """embedding_fn(params, inputs) with the signature of qadence/blocks/embedding.py:118; `stock_fn` (the reference's
     host embedding) is kept for calls this table cannot serve (separate circuit/observable dicts, a variational
     parameter overridden through `inputs`, multi-element parameters)."""
@@ -399,11 +409,23 @@ def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, sto
         else:
             feat = torch.zeros(1, batch, dtype=torch.float64, device=dev)
         table = evaluate(prog, var, feat, batch)
+        nograd: frozenset = frozenset()
+        if prog.slot_symbols is not None and table.requires_grad:
+            live = {nm for nm, v in zip(prog.var_names, var_rows) if v.requires_grad} | {nm for nm, v in zip(prog.feat_names, feat_rows) if v.requires_grad}
+            nograd = frozenset(nm for nm in prog.names if nm in prog.slot_symbols and not (prog.slot_symbols[nm] & live))
         extras: dict = {}
+        for nm, key in matrix_rows:  # constant generator matrices: dict entries taken from `params` (embedding.py:147-148)
+            if key not in params:
+                return stock_fn(params, inputs)
+            extras[nm] = params[key]
         if passthrough:  # expression-level dicts also carry the raw inputs and parameters (embedding.py:155-166)
             for k, v in {**params, **inputs}.items():
                 t = torch.as_tensor(v)
                 extras[k] = t[None] if t.ndim == 0 else v
-        return ParamTable(prog.names, table, extras, input_device)
+        scalar: frozenset = frozenset()
+        if prog.slot_symbols is not None:
+            feats = set(prog.feat_names)
+            scalar = frozenset(nm for nm in prog.names if nm in prog.slot_symbols and not (prog.slot_symbols[nm] & feats))
+        return ParamTable(prog.names, table, extras, input_device, nograd, scalar)
 
     return fn

@@ -36,6 +36,9 @@ from .config import Configuration, default_passes
 from .convert_ops import convert_block, convert_observable, convert_readout_noise
 
 logger = getLogger(__name__)
+# replace mode (B200SV_REPLACE_PYQTORCH=1, qadence_extensions/__init__.py): this backend answers to the name "pyqtorch"
+_REPLACE = "b200sv" not in BackendName.list()
+_NAME, _ENGINE = ("pyqtorch", "torch") if _REPLACE else ("b200sv", "b200sv")
 _DTYPES = {"complex128": torch.complex128, "complex64": torch.complex64}
 
 
@@ -64,6 +67,19 @@ class NativeCircuit:
     @property
     def operations(self) -> list:
         return self.program.ops
+
+    if _REPLACE:  # replace mode only: this object stands where a `pyqtorch.QuantumCircuit` is expected
+
+        @property  # type: ignore[misc]
+        def __class__(self) -> type:
+            """`QuantumModel.to()` moves the model only `if isinstance(native, pyqtorch.QuantumCircuit)` (qadence/model.py:651);
+            isinstance falls back to `__class__`, `type(obj)` (used by copy / pickle) is untouched."""
+            try:
+                from pyqtorch import QuantumCircuit as PyQCircuit
+
+                return PyQCircuit if isinstance(PyQCircuit, type) else NativeCircuit
+            except Exception:
+                return NativeCircuit
 
     @property
     def device(self) -> torch.device:
@@ -182,14 +198,18 @@ def _device_embedding_fn(conv: Converted, config: Configuration) -> Any:
         if nm not in needed and not isinstance(e, sympy.Array) and not (isinstance(e, sympy.Basic) and e.is_Symbol and not config._use_gate_params):
             named.append((nm, e))
     prog = compile_expressions(named, is_feature=lambda nm: not getattr(symbols.get(nm), "trainable", False))
-    return make_embedding_fn(prog, config.device, conv.embedding_fn, passthrough=not config._use_gate_params)
+    prog.slot_symbols = {nm: frozenset(str(s_) for s_ in e.free_symbols) if isinstance(e, sympy.Basic) else frozenset() for nm, e in named}
+    # gate-level names of constant generator matrices (HamEvo of a Tensor): the reference's dict carries them too, and its
+    # GPSR machinery looks every uuid of the circuit up (engines/torch/differentiable_expectation.py:207)
+    matrices = [(nm, stringify(e)) for nm, e in by_name.items() if isinstance(e, sympy.Array)] if config._use_gate_params else []
+    return make_embedding_fn(prog, config.device, conv.embedding_fn, passthrough=not config._use_gate_params, matrix_rows=matrices)
 
 
 @dataclass(frozen=True, eq=True)
 class Backend(BackendInterface):
     """B200-native state-vector backend (hand-written sm_100a CUDA kernels behind a C-ABI)."""
 
-    name: BackendName = BackendName("b200sv")
+    name: BackendName = BackendName(_NAME)
     supports_ad: bool = True
     support_bp: bool = True
     supports_adjoint: bool = True
@@ -198,7 +218,7 @@ class Backend(BackendInterface):
     with_noise: bool = False
     native_endianness: Endianness = Endianness.BIG
     config: Configuration = field(default_factory=Configuration)
-    engine: Engine = Engine("b200sv")
+    engine: Engine = Engine(_ENGINE)
 
     # ------------------------------------------------------------------ conversion
     def convert(self, circuit: QuantumCircuit, observable: list[AbstractBlock] | AbstractBlock | None = None) -> Converted:

@@ -11,6 +11,12 @@ Shipping this package next to `qadence_b200` registers the B200-native backend u
 * `import_config` and `import_engine` only look under `qadence.backends.<name>.config` and
   `qadence.engines.<engine>.differentiable_backend` (`extensions.py:30-39,71-80`), so a lazy
   meta-path alias maps those dotted names onto `qadence_b200.qadence_backend`.
+
+**Replace mode.**  With `B200SV_REPLACE_PYQTORCH=1` in the environment the same alias mechanism also maps
+`qadence.backends.pyqtorch.{backend,config}` and `qadence.engines.torch.differentiable_backend` onto the b200sv modules, and
+the backend reports `name == "pyqtorch"`: every existing program — `QuantumModel(...)` with the default backend,
+`backend_factory("pyqtorch", ...)` — then runs on the B200 kernels without a source change (and the reference's own test
+suite can be pointed at this backend unmodified, tools/run_reference_suite.py).
 """
 
 from __future__ import annotations
@@ -20,6 +26,8 @@ import importlib.abc
 import importlib.util
 import sys
 
+from .types import REPLACE_PYQTORCH
+
 _ALIASES = {
     "qadence.backends.b200sv": "qadence_b200.qadence_backend",
     "qadence.backends.b200sv.backend": "qadence_b200.qadence_backend.backend",
@@ -27,6 +35,14 @@ _ALIASES = {
     "qadence.engines.b200sv": "qadence_b200.qadence_backend",
     "qadence.engines.b200sv.differentiable_backend": "qadence_b200.qadence_backend.differentiable_backend",
 }
+if REPLACE_PYQTORCH:
+    # only the three modules qadence resolves by name (extensions.py:30-80); `qadence.backends.pyqtorch` itself and its
+    # `convert_ops` stay the reference's own (other reference modules import helpers from there)
+    _ALIASES.update({
+        "qadence.backends.pyqtorch.backend": "qadence_b200.qadence_backend.backend",
+        "qadence.backends.pyqtorch.config": "qadence_b200.qadence_backend.config",
+        "qadence.engines.torch.differentiable_backend": "qadence_b200.qadence_backend.differentiable_backend",
+    })
 
 
 class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):

@@ -1,0 +1,183 @@
+"""pytest plugin that runs the REFERENCE's own, unmodified test files against the b200sv backend (CPU container only).
+
+Test infrastructure.  `python tools/run_reference_suite.py` (or `pytest -p tests.refsuite.plugin /root/reference/tests/...`)
+
+* makes `import qadence` work (reference front-end + the name-only shims of tests/_shims);
+* switches the plugin to its replace mode (`B200SV_REPLACE_PYQTORCH=1`): the dotted module names qadence resolves backends
+  through — `qadence.backends.pyqtorch.{backend,config}`, `qadence.engines.torch.differentiable_backend`
+  (`/root/reference/qadence/extensions.py:30-80`) — map onto the b200sv modules, so every
+  `backend_factory(BackendName.PYQTORCH, ...)`, `QuantumModel(..., backend="pyqtorch")` of the reference tests builds THIS
+  backend;
+* replaces the C-ABI-backed entry points of `qadence_b200.engine` by the CPU oracle (there is no GPU here and the product
+  has no CPU fallback) — so what these runs prove is the adapter: conversion, parameter conventions, batching, endianness,
+  error behaviour, differentiation modes.  The kernels are proven against the same oracle by `pytest -m gpu`.
+"""
+
+from __future__ import annotations
+
+import importlib
+import importlib.abc
+import importlib.util
+import os
+import sys
+from collections import Counter
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+for p in (str(ROOT), "/root/reference", str(ROOT / "tests" / "_shims"), "/root/reference/tests"):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+os.environ.setdefault("QADENCE_LOG_LEVEL", "ERROR")
+sys.dont_write_bytecode = True
+
+# packages the reference's conftest / test modules import at module level for OTHER backends or comparisons
+# (qutip: one fixture; jax / horqrux: the horqrux backend): empty stand-ins so that collection succeeds
+import types  # noqa: E402
+
+
+class _Absent:
+    def __init__(self, name: str):
+        self._name = name
+
+    def __call__(self, *a, **k):  # type: ignore[no-untyped-def]
+        return _Absent(f"{self._name}()")  # module-level constants of jax-based helpers are built at import time
+
+    def __getattr__(self, item: str) -> "_Absent":
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Absent(f"{self._name}.{item}")
+
+    def __getitem__(self, item):  # type: ignore[no-untyped-def]
+        return _Absent(f"{self._name}[]")
+
+    def _op(self, *a, **k):  # type: ignore[no-untyped-def]
+        return _Absent(f"{self._name}<op>")
+
+    __add__ = __radd__ = __sub__ = __rsub__ = __mul__ = __rmul__ = __truediv__ = __rtruediv__ = __matmul__ = __rmatmul__ = __neg__ = __pow__ = _op
+
+    def __mro_entries__(self, bases):  # type: ignore[no-untyped-def]
+        return (object,)  # `class Foo(absent.Thing)` in a module of another backend
+
+    def __repr__(self) -> str:
+        return f"<absent {self._name}>"
+
+
+class _StubModule(types.ModuleType):
+    def __getattr__(self, item: str):  # type: ignore[no-untyped-def]
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Absent(f"{self.__name__}.{item}")
+
+
+_ABSENT_ROOTS = {"qutip", "jax", "jaxlib", "horqrux", "pulser", "pulser_simulation", "sympy2jax", "optax", "flax", "jaxopt", "mlflow"}
+
+
+class _AbsentFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """LAST on the meta path: third-party packages of OTHER backends that this image does not have become permissive
+    stand-ins (any attribute resolves; calling one raises), so that collection of the reference's test modules succeeds."""
+
+    def find_spec(self, fullname, path=None, target=None):  # type: ignore[no-untyped-def]
+        if fullname.split(".")[0] in _ABSENT_ROOTS or fullname.startswith("pyqtorch."):  # submodules the pyqtorch shim lacks
+            return importlib.util.spec_from_loader(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):  # type: ignore[no-untyped-def]
+        m = _StubModule(spec.name)
+        m.__path__ = []  # type: ignore[attr-defined]
+        return m
+
+    def exec_module(self, module):  # type: ignore[no-untyped-def]
+        return None
+
+
+sys.meta_path.append(_AbsentFinder())
+
+import pyqtorch  # noqa: E402  (the name-only shim of tests/_shims)
+
+for _m in [m for nm, m in list(sys.modules.items()) if nm == "pyqtorch" or nm.startswith("pyqtorch.")]:
+    # test modules import more pyqtorch names than the shim defines (`from pyqtorch import U as pyqU`, ...): any missing
+    # name resolves to a stand-in, so the file collects and the tests that only use the qadence API run
+    _m.__dict__.setdefault("__getattr__", (lambda modname: (lambda item: _Absent(f"{modname}.{item}") if not item.startswith("__") else (_ for _ in ()).throw(AttributeError(item))))(_m.__name__))
+
+os.environ["B200SV_REPLACE_PYQTORCH"] = "1"  # b200sv answers to the name "pyqtorch" (qadence_extensions/__init__.py)
+import qadence_extensions  # noqa: E402,F401
+
+
+def _install_oracle_double() -> None:
+    from oracle import embedding as oemb
+    from oracle import statevec as oracle
+    from qadence_b200 import embedding as emb
+    from qadence_b200 import engine
+
+    def det(values):
+        return {k: (torch.as_tensor(v).detach() if not isinstance(v, str) else v) for k, v in (values or {}).items()}
+
+    def run(cp, values=None, state=None, dtype=torch.complex128, device=None):
+        return oracle.run(cp.program, det(values), None if state is None else state.detach().to(torch.complex128)).to(dtype)
+
+    def apply_observable(cob, psi, values):
+        if cob.pauli is not None:
+            return oracle.from_pyq_shape(oracle.paulisum_apply(cob.obs, oracle.to_pyq_shape(psi.to(torch.complex128), cob.n_qubits), values))
+        return oracle.run(cob.obs, values, psi)
+
+    def sample_indices(psi, uniforms):
+        return torch.as_tensor(oracle.sample_indices(oracle.probabilities(psi), uniforms.cpu().numpy()))
+
+    def sample(cp, values=None, n_shots=1, state=None, dtype=torch.complex128, device=None, uniforms=None, little_endian=False):
+        psi = run(cp, values, state)
+        u = torch.rand(psi.shape[0], n_shots, dtype=torch.float64) if uniforms is None else uniforms
+        return engine.counts_from_indices(sample_indices(psi, u), cp.n_qubits, little_endian)
+
+    def expectation(cp, observables, values=None, state=None, dtype=torch.complex128, device=None):
+        # the oracle is written in differentiable torch ops: autograd through it gives derivatives of any order, which is
+        # what the product's adjoint pass (+ shift rules for higher orders) delivers on the GPU
+        values = dict((values or {}).items())
+        real_dt = torch.float64 if dtype == torch.complex128 else torch.float32
+        st = None if state is None else state.detach().to(torch.complex128)
+        return oracle.expectation(cp.program, [o.obs for o in observables], values, st).to(real_dt)
+
+    engine.run = run
+    engine.expectation = expectation
+    engine.sample = sample
+    engine.apply_observable = apply_observable
+    engine.sample_indices = sample_indices
+    engine.bit_reverse = lambda psi: oracle.invert_endianness_state(psi, int(psi.shape[1]).bit_length() - 1)
+    engine.zero_state = lambda n, batch, dtype, device: oracle.zero_state(n, batch).to(dtype)
+    emb.evaluate = oemb.evaluate
+    emb._resolve_device = lambda device: torch.device("cpu")
+
+
+_install_oracle_double()
+
+
+def _tolerate_absent_backends() -> None:
+    """tests/strategies.py asks for the supported gates of EVERY backend name at import time; pulser / horqrux are not in
+    this image: answer with an empty list instead of failing the collection of unrelated tests."""
+    import qadence.extensions as qext
+    import qadence_extensions.extensions as ours
+
+    def wrap(fn):  # type: ignore[no-untyped-def]
+        def safe(name):  # type: ignore[no-untyped-def]
+            try:
+                return fn(name)
+            except Exception:
+                return []
+
+        return safe
+
+    qext._supported_gates = wrap(qext._supported_gates)
+    ours.supported_gates = wrap(ours.supported_gates)
+    if getattr(qext, "supported_gates", None) is not None:
+        qext.supported_gates = wrap(qext.supported_gates)
+
+
+_tolerate_absent_backends()
+
+
+def pytest_configure(config: pytest.Config) -> None:
+    for m in ("flaky", "slow", "reference", "gpu"):
+        config.addinivalue_line("markers", f"{m}: (reference suite)")

@@ -390,7 +390,8 @@ def test_device_embedding_equals_reference_embedding(oracle_embedding_device, id
     for k, (nm, nm_ref) in enumerate(zip(needed, needed_ref)):
         a, b = got[nm], want[nm_ref]
         assert torch.allclose(a.expand(5) if a.numel() == 1 else a, (b.expand(5) if b.numel() == 1 else b).to(torch.float64), atol=1e-13, rtol=0), nm
-        loss_a = loss_a + (k + 1) * a.sum()
+        assert a.shape == b.reshape(-1).shape, (nm, a.shape, b.shape)  # [1] for batch-independent rows, like the reference
+        loss_a = loss_a + (k + 1) * (a.expand(5) if a.numel() == 1 else a).sum()
         loss_b = loss_b + (k + 1) * (b.expand(5) if b.numel() == 1 else b).sum()
     loss_a.backward()
     loss_b.backward()

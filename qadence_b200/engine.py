@@ -463,10 +463,48 @@ def run(cp: CompiledProgram, values: Mapping[str, Tensor] | None = None, state: 
     B = infer_batch(values)
     if state is not None:
         B = max(B, state.shape[0])
+    ptable = pack_params(cp.names, values, B, dev)
+    state_grad = state is not None and state.requires_grad
+    if torch.is_grad_enabled() and cp.invertible and (ptable.requires_grad or state_grad):
+        # differentiable wavefunction (pyqtorch's `run` is differentiable by autograd; qadence's Overlap / fidelity
+        # training relies on it, /root/reference/tests/qadence/test_overlap.py:304-337): the backward pass is the same
+        # adjoint walk as for expectations, with torch's cotangent of the state as λ
+        return _RunState.apply(cp, values, state, dtype, dev, B, ptable, state if state_grad else torch.zeros(0, device=dev))
     with torch.no_grad():
         st = prepare_state(cp.n_qubits, B, state, dtype, dev)
-        ptable = pack_params(cp.names, values, B, dev)
-        return _run_segments(cp, st, ptable, values)
+        return _run_segments(cp, st, ptable.detach(), values)
+
+
+class _RunState(torch.autograd.Function):
+    """ψ_out = U(θ) ψ_in, differentiable (first order) w.r.t. the gate parameters and the input state.
+
+    For a real loss L torch hands `g = ∂L/∂Re ψ + i ∂L/∂Im ψ` to backward, and dL = Re⟨g|dψ⟩.  Hence
+    ∂L/∂θ = Re⟨g|∂U/∂θ ψ_in⟩ = ½ · (2 Re⟨λ|∂U/∂θ|ψ⟩ with λ = g) — half of what the adjoint walk reduces — and the cotangent of
+    the input state is U†g, the λ the walk ends with."""
+
+    @staticmethod
+    def forward(ctx, cp: CompiledProgram, values: Any, state: Tensor | None, dtype: torch.dtype, device: torch.device,
+                batch: int, ptable: Tensor, state_in: Tensor) -> Tensor:
+        st = prepare_state(cp.n_qubits, batch, state, dtype, device)
+        psi = _run_segments(cp, st, ptable, values)
+        detached = values.detach() if isinstance(values, ParamTable) else {k: (v.detach() if isinstance(v, Tensor) else v) for k, v in values.items()}
+        ctx.cp, ctx.values, ctx.batch = cp, detached, batch
+        ctx.grad_names = None if isinstance(values, ParamTable) else {k for k, v in values.items() if isinstance(v, Tensor) and v.requires_grad}
+        ctx.state_shape = None if state is None else tuple(state.shape)
+        ctx.state_device, ctx.state_dtype = (None, None) if state is None else (state.device, state.dtype)
+        ctx.save_for_backward(ptable, psi)
+        return psi
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        ptable, psi = ctx.saved_tensors
+        lam = g.detach().to(psi.dtype).contiguous().clone()
+        grads, _, lam_in = _adjoint_walk(ctx.cp, ctx.values, ctx.batch, ptable, psi.detach().clone(), lam, ctx.grad_names)
+        g_state = None
+        if ctx.needs_input_grad[7] and ctx.state_shape is not None:
+            g_state = lam_in if ctx.state_shape[0] == lam_in.shape[0] else lam_in.sum(0, keepdim=True)
+            g_state = g_state.to(device=ctx.state_device, dtype=ctx.state_dtype)
+        return None, None, None, None, None, None, (0.5 * grads if ctx.needs_input_grad[6] else None), g_state
 
 
 class CompiledObservable:
@@ -568,8 +606,26 @@ def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], v
                 t = cob.apply(psi, values)
                 scal(w, t)
                 lam = t if lam is None else lam + t
-        grads = torch.zeros(ptable.shape, dtype=torch.float64, device=dev)
         psi = psi.clone()  # keep ctx.psi intact for double calls of backward(retain_graph=True)
+    return _adjoint_walk(cp, values, B, ptable, psi, lam, grad_names)[0]
+
+
+def _adjoint_walk(cp: CompiledProgram, values: Mapping[str, Any], B: int, ptable: Tensor, psi: Tensor, lam: Tensor,
+                  grad_names: set | None = None) -> tuple[Tensor, Tensor, Tensor]:
+    """One backward walk over the circuit: un-applies it on ψ (the circuit's OUTPUT state) and λ (any cotangent state) in
+    place / segment by segment and reduces g[slot, b] = 2 Re⟨λ|∂U/∂θ_slot|ψ⟩ for every gate parameter in the same sweeps.
+    Returns (g, ψ_in, U†λ).  Linear in λ: λ = Oψ gives ∂⟨O⟩/∂θ, λ = ∂L/∂ψ (torch's cotangent) gives 2·∂L/∂θ."""
+    from . import hamevo
+
+    dev = psi.device
+    lib = cabi.load()
+    with torch.no_grad():
+        if not cp.invertible:
+            raise NotImplementedError(
+                "adjoint differentiation needs an invertible circuit (unitary gates, Scale, HamEvo); "
+                "use diff_mode='gpsr' for circuits with projectors / AddBlocks"
+            )
+        grads = torch.zeros(ptable.shape, dtype=torch.float64, device=dev)
         for seg in reversed(cp.segments):
             if seg.gates is not None:
                 dp = cp.device_plan(seg, psi.dtype, True, dev)
@@ -604,7 +660,7 @@ def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], v
                 lam = apply_dense(lam, md, bits)
             else:
                 raise NotImplementedError(op.kind)
-    return grads
+    return grads, psi, lam
 
 
 # parameter-shift rules used ONLY to differentiate the adjoint gradient once more (second order):

@@ -301,7 +301,11 @@ class Backend(BackendInterface):
         else:
             out = engine.run(nat.compiled, param_values, state, dtype=nat.dtype, device=nat._device)
             if endianness != self.native_endianness:
-                out = engine.bit_reverse(out)
+                if out.requires_grad:  # keep the autograd edge of a differentiable wavefunction: a torch gather, not the kernel
+                    idx = torch.tensor([int(format(i, f"0{n}b")[::-1], 2) for i in range(2**n)], device=out.device)
+                    out = out.index_select(1, idx)
+                else:
+                    out = engine.bit_reverse(out)
         dev = _result_device(self.config, param_values, state)
         return out if dev is None else out.to(dev)
 

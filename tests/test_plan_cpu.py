@@ -185,3 +185,40 @@ def test_tile_search_never_needs_more_sweeps_than_first_fit() -> None:
         a = build_plan(prog.ops, n, slot_of, cfg, packer="greedy")
         b = build_plan(prog.ops, n, slot_of, cfg, packer="search")
         assert cost(b) <= cost(a) + 1e-9, (trial, cost(a), cost(b))
+
+
+def test_adjoint_walk_is_linear_in_an_arbitrary_cotangent_state() -> None:
+    """`engine._RunState` (differentiable `run`) feeds torch's cotangent g of the output state to the adjoint walk as λ and
+    halves the result: dL/dθ = Re⟨g|∂ψ/∂θ⟩ = ½·(2 Re⟨λ|∂U|ψ⟩)|λ=g.  Checked here on the emulated plan against torch autograd
+    through the oracle for a loss that is NOT an expectation value (λ is not of the form Oψ)."""
+    rng = np.random.default_rng(21)
+    n, B = 6, 2
+    b = ProgramBuilder(n)
+    for q in range(n):
+        b.RX(q, f"a{q}").RY(q, "shared").PHASE(q, f"p{q}").H(q)
+    for q in range(n - 1):
+        b.CNOT(q, q + 1).CRZ(q, q + 1, f"c{q}").CPHASE(q + 1, q, "shared")
+    b.scale("s")
+    for q in range(n):
+        b.RZ(q, f"z{q}").RX(q, 0.3)
+    prog = b.build()
+    values = {nm: torch.tensor(rng.uniform(0.2, 1.5, size=B), requires_grad=True) for nm in prog.param_names}
+    psi0 = torch.tensor(rng.normal(size=(B, 2**n)) + 1j * rng.normal(size=(B, 2**n)))
+    target = torch.tensor(rng.normal(size=(B, 2**n)) + 1j * rng.normal(size=(B, 2**n)))
+    psi = oracle.run(prog, values, psi0)
+    loss = ((psi - target).abs() ** 2).sum() + (psi.real * target.imag).sum()  # any real function of the wavefunction
+    psi.retain_grad()
+    loss.backward()
+    g = psi.grad.detach().numpy()  # torch's cotangent: dL/dRe + i dL/dIm
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    plan = build_plan(prog.ops, n, slot_of, TileConfig(m=5, r=3, low=2, fold=3))
+    params = np.stack([values[nm].detach().numpy() for nm in prog.param_names])
+    back_psi, back_lam, grads = emulate_adjoint(plan, psi.detach().numpy(), g, params)
+    np.testing.assert_allclose(back_psi, psi0.numpy(), atol=1e-11)
+    for nm, i in slot_of.items():
+        np.testing.assert_allclose(0.5 * grads[i], values[nm].grad.numpy(), atol=1e-10, err_msg=nm)
+    # U^dagger g is the cotangent of the input state
+    psi0r = psi0.clone().requires_grad_(True)
+    out = oracle.run(prog, {k: v.detach() for k, v in values.items()}, psi0r)
+    (((out - target).abs() ** 2).sum() + (out.real * target.imag).sum()).backward()
+    np.testing.assert_allclose(back_lam, psi0r.grad.numpy(), atol=1e-10)

@@ -117,7 +117,10 @@ def _install_oracle_double() -> None:
         return {k: (torch.as_tensor(v).detach() if not isinstance(v, str) else v) for k, v in (values or {}).items()}
 
     def run(cp, values=None, state=None, dtype=torch.complex128, device=None):
-        return oracle.run(cp.program, det(values), None if state is None else state.detach().to(torch.complex128)).to(dtype)
+        # differentiable like the product's `engine.run` (adjoint walk with torch's cotangent, tests/test_gpu_run_grad.py):
+        # the oracle is written in torch ops, autograd through it is the double
+        vals = dict((values or {}).items()) if torch.is_grad_enabled() else det(values)
+        return oracle.run(cp.program, vals, None if state is None else state.to(torch.complex128)).to(dtype)
 
     def apply_observable(cob, psi, values):
         if cob.pauli is not None:

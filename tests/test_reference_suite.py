@@ -24,6 +24,6 @@ sys.path.insert(0, str(ROOT / "tools"))
 def test_reference_test_file_passes_on_b200sv(rel: str, min_passed: int) -> None:
     from run_reference_suite import run_file
 
-    res = run_file(rel, timeout=600, extra=[])
+    res = run_file(rel, timeout=600, extra=["--hypothesis-seed=0"])  # fixed examples: a reproducible gate for the CPU suite
     assert res["failed"] == 0 and res["errors"] == 0, res["failures"]
     assert res["passed"] >= min_passed, res

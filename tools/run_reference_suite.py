@@ -38,6 +38,13 @@ DEFAULT_FILES = [
     "analog/test_analog_emulation.py",
     "test_whitepaper.py",
     "test_finitediff.py",
+    "constructors/test_ansatz.py",
+    "constructors/test_daqc.py",
+    "constructors/test_feature_maps.py",
+    "constructors/test_hamiltonians.py",
+    "constructors/test_qft.py",
+    "constructors/test_rydberg_hea.py",
+    "ml_tools/test_qnn.py",
 ]
 # not in the default list: qadence/test_measurements/test_tomography.py and test_shadows.py (25 min of shot-based estimators on
 # the CPU oracle; their backend contact is `Backend.sample`, covered by tests/test_qadence_adapter_cpu.py)
@@ -52,8 +59,9 @@ NOT_APPLICABLE = [
     ("different_backends", "compares pyqtorch with horqrux (not in this image)"),
     ("NGOpt", "nevergrad is not in this image"),
     ("test_save_load_qm_pyq", "installed networkx serialises graphs with 'edges' instead of 'links': Register._from_dict of the reference fails before any backend is involved"),
-    ("test_model_inputs_in_observable", "installed sympy re-creates a Parameter on deepcopy (qadence/parameters.py:128 draws a new random value): `w != w` without any backend involved"),
+    ("test_model_inputs_in_observable", "installed sympy 1.14 (the reference pins sympy<1.13.4) re-creates a Parameter on deepcopy (qadence/parameters.py:128 draws a new random value): `w != w` without any backend involved"),
     ("test_first_order_hea_derivatives[adjoint_observables1]", "same deepcopy effect: the un-valued observable parameter 'xobs' gets a new random value at every convert()"),
+    ("test_constant_and_feature_transformed_module", "installed sympy 1.14 (the reference pins sympy<1.13.4) drops the `trainable=False` assumption when a Parameter is deep-copied: the non-trainable 'scale' / 'shift' inputs of the QNN come back as variational parameters before any backend is involved"),
     ("'torch.dtype' object has no attribute 'type'", "installed scipy / torch mismatch inside the reference's aGPSR shift optimiser"),
     ("FileNotFoundError", "test data path relative to the reference's repository root"),
 ]

@@ -577,11 +577,8 @@ class _AdjointExpectation(torch.autograd.Function):
 def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], values: Mapping[str, Any], B: int, ptable: Tensor,
                       grad_out: Tensor, psi: Tensor, grad_names: set | None = None) -> Tensor:
     """`[n_slots, B]` vector-Jacobian product Σ_o ḡ[b,o]·∂E[b,o]/∂θ[slot,b] by the adjoint method: λ = Σ_o ḡ·O_o ψ, then
-    one backward walk that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps."""
-    from . import hamevo
-
+    one backward walk (`_adjoint_walk`) that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps."""
     dev = psi.device
-    lib = cabi.load()
     with torch.no_grad():
         if not cp.invertible:
             raise NotImplementedError(

@@ -74,10 +74,10 @@ def classify(failure: str) -> str:
     return ""
 
 
-def run_file(rel: str, timeout: int, extra: list[str]) -> dict:
+def run_file(rel: str, timeout: int, extra: list[str], test_timeout: int = 300) -> dict:
     env = {**os.environ, "PYTHONPATH": f"{ROOT / 'tests' / 'refsuite'}:{ROOT}", "QADENCE_LOG_LEVEL": "ERROR"}
     cmd = [sys.executable, "-m", "pytest", "-p", "refsuite_plugin", "-p", "no:cacheprovider", rel, "-q", "--rootdir", str(REF_TESTS),
-           "-W", "ignore", "-k", DESELECT, "-rfE", "--timeout", "300", "--tb=line", *extra]
+           "-W", "ignore", "-k", DESELECT, "-rfE", "--timeout", str(test_timeout), "--tb=line", *extra]
     t0 = time.time()
     try:
         out = subprocess.run(cmd, cwd=REF_TESTS, env=env, capture_output=True, text=True, timeout=timeout)
@@ -103,7 +103,8 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", nargs="*", default=DEFAULT_FILES)
     ap.add_argument("--report", default="")
-    ap.add_argument("--timeout", type=int, default=1500)
+    ap.add_argument("--timeout", type=int, default=1500, help="seconds per file")
+    ap.add_argument("--test-timeout", type=int, default=300, help="seconds per test")
     ap.add_argument("pytest_args", nargs="*")
     args = ap.parse_args()
     rows = []
@@ -111,7 +112,7 @@ def main() -> None:
         if not (REF_TESTS / rel).exists():
             print(f"skip {rel}: not in the reference")
             continue
-        r = run_file(rel, args.timeout, args.pytest_args)
+        r = run_file(rel, args.timeout, args.pytest_args, args.test_timeout)
         rows.append(r)
         print(f"{rel}: {r['passed']} passed, {r['failed']} failed, {r['errors']} errors, {r['skipped']} skipped, {r['deselected']} deselected ({r['seconds']:.0f} s)", flush=True)
         for f in r["failures"]:

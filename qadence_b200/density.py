@@ -49,7 +49,6 @@ except Exception:  # pyqtorch absent: same definition (a bare Tensor subclass)
 
 
 logger = getLogger(__name__)
-_warned_no_autograd = False
 
 NEG = "__neg__"  # key prefix of the negated copy of a gate parameter (conjugated rotations)
 NEGCONJ = "__negconj__"  # ... of −conj(matrix) of a matrix-valued HamEvo generator entry
@@ -251,15 +250,28 @@ def lift_observable(obs: PauliSum | Program, n: int) -> PauliSum | Program:
 def expectation(cd: CompiledDensityProgram, observables: Sequence[Any], values: Mapping[str, Any] | None = None,
                 state: Tensor | None = None, dtype: torch.dtype = torch.complex128,
                 device: torch.device | str | None = None) -> Tensor:
-    """`[B, n_obs]` real `Tr(O ρ)`; `observables` are `engine.CompiledObservable`s of the LIFTED observables.
-    Not differentiable by autograd — use `diff_mode="gpsr"` (the shift rules hold for noisy expectations)."""
-    global _warned_no_autograd
+    """`[B, n_obs]` real `Tr(O ρ)`; `observables` are `engine.CompiledObservable`s of the LIFTED (Hermitian) observables.
+    Differentiable w.r.t. the gate parameters by the adjoint walk (see below) and, of course, by `diff_mode="gpsr"` (the
+    shift rules hold for noisy expectations); observable coefficients are not differentiated on this path."""
     N = 2**cd.n_qubits
     vals = cd.values(values)
-    if torch.is_grad_enabled() and not _warned_no_autograd and any(isinstance(x, Tensor) and x.requires_grad for x in vals.values()):
-        _warned_no_autograd = True
-        logger.warning("b200sv: expectations of noisy circuits (density matrices) are not differentiable by autograd; "
-                       "use diff_mode='gpsr' (parameter-shift rules hold for noisy expectations)")
+    real_dt = torch.float64 if dtype == torch.complex128 else torch.float32
+    needs_grad = torch.is_grad_enabled() and (any(isinstance(x, Tensor) and x.requires_grad for x in vals.values())
+                                              or (state is not None and state.requires_grad))
+    if needs_grad and cd.compiled.invertible:
+        # Tr(Oρ) = ⟨⟨vec(O)|vec(ρ)⟩⟩ for Hermitian O, vec(O) = (O ⊗ 1)|1⟩⟩: a LINEAR functional of the differentiable
+        # wavefunction `engine.run` returns for the vectorised program — its backward pass is the adjoint walk with
+        # λ = vec(O) (noise superoperators are un-applied with their inverse), so noisy expectations differentiate like
+        # noise-free ones in `ad` / `adjoint` mode
+        v = engine.run(cd.compiled, vals, vectorise_state(state, cd.n_qubits), dtype=dtype, device=device)
+        with torch.no_grad():
+            bell = torch.eye(N, dtype=v.dtype, device=v.device).reshape(1, N * N)
+            detached = {k: (x.detach() if isinstance(x, Tensor) else x) for k, x in vals.items()}
+            ovecs = [engine.apply_observable(cob, bell.clone(), detached) for cob in observables]
+        return torch.stack([(o.conj() * v).sum(-1).real for o in ovecs], dim=1).to(real_dt)
+    if needs_grad:
+        logger.warning("b200sv: this noisy circuit contains non-invertible ops (projectors, AddBlocks): its expectation is not "
+                       "differentiable by the adjoint walk; use diff_mode='gpsr'")
     with torch.no_grad():
         v = engine.run(cd.compiled, vals, vectorise_state(state, cd.n_qubits), dtype=dtype, device=device)
         cols = []
@@ -267,7 +279,7 @@ def expectation(cd: CompiledDensityProgram, observables: Sequence[Any], values: 
             w = engine.apply_observable(cob, v, vals)
             cols.append(w.reshape(w.shape[0], N, N).diagonal(dim1=1, dim2=2).sum(-1).real)
         out = torch.stack(cols, dim=1)
-    return out.to(torch.float64 if dtype == torch.complex128 else torch.float32)
+    return out.to(real_dt)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -652,8 +652,15 @@ def _adjoint_walk(cp: CompiledProgram, values: Mapping[str, Any], B: int, ptable
                     lam = hamevo.evolve(op, seg.compiled, lam, values, cp.n_qubits, dagger=True)
             elif op.kind == OpKind.MATK:
                 bits = [cp.n_qubits - 1 - q for q in op.targets]
-                md = np.asarray(op.matrix, dtype=np.complex128).conj().T
-                psi = apply_dense(psi, md, bits)
+                m = np.asarray(op.matrix, dtype=np.complex128)
+                md = m.conj().T
+                if np.allclose(m @ md, np.eye(m.shape[0]), atol=1e-12, rtol=0):
+                    psi = apply_dense(psi, md, bits)
+                else:  # not unitary (noise superoperators of the density-matrix path): ψ is un-applied with M⁻¹, λ takes M†
+                    if np.linalg.cond(m) > 1e8:
+                        raise NotImplementedError("adjoint differentiation through a (nearly) singular matrix op — a projector, or a "
+                                                  "noise channel at its fully mixing point — is not possible; use diff_mode='gpsr'")
+                    psi = apply_dense(psi, np.linalg.inv(m), bits)
                 lam = apply_dense(lam, md, bits)
             else:
                 raise NotImplementedError(op.kind)

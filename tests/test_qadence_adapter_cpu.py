@@ -49,7 +49,9 @@ def oracle_device(monkeypatch: pytest.MonkeyPatch) -> None:
     """Replace the GPU entry points of `qadence_b200.engine` by the CPU oracle (test double)."""
 
     def run(cp, values=None, state=None, dtype=torch.complex128, device=None):
-        return oracle.run(cp.program, {k: torch.as_tensor(v).detach() for k, v in (values or {}).items()}, state).to(dtype)
+        # differentiable like the product's `engine.run` (tests/test_gpu_run_grad.py): autograd through the oracle's torch ops
+        vals = {k: (torch.as_tensor(v) if torch.is_grad_enabled() else torch.as_tensor(v).detach()) for k, v in (values or {}).items()}
+        return oracle.run(cp.program, vals, state).to(dtype)
 
     def expectation(cp, observables, values=None, state=None, dtype=torch.complex128, device=None):
         out = oracle.expectation(cp.program, [o.obs for o in observables], values or {}, state)
@@ -713,3 +715,37 @@ def test_density_matrix_initial_state_and_little_endian(oracle_device: None) -> 
     assert torch.allclose(little, torch.einsum("bi,bj->bij", psi_l, psi_l.conj()), atol=1e-12)
     with pytest.raises(ValueError):
         backend.run(conv.circuit, {}, state=torch.zeros(1, 4, 4, dtype=torch.cdouble).as_subclass(DensityMatrix))
+
+
+@pytest.mark.parametrize("mode", [DiffMode.AD, DiffMode.ADJOINT])
+def test_noisy_expectation_is_differentiable_in_ad_and_adjoint_mode(oracle_device: None, mode) -> None:
+    """Tr(O rho) is a linear functional of the vectorised density matrix: autograd through the differentiable `run` of the
+    vectorised program == GPSR == finite differences of the dense Kraus evolution."""
+    from qadence import NoiseHandler, NoiseProtocol
+
+    block = chain(RX(0, "th"), CNOT(0, 1), RY(1, 0.4), CRZ(1, 0, "ph"))
+    noise = NoiseHandler([NoiseProtocol.DIGITAL.DEPOLARIZING, NoiseProtocol.DIGITAL.AMPLITUDE_DAMPING], [{"error_probability": 0.15}, {"error_probability": 0.2}])
+    obs = [add(Z(0), Z(1)), kron(X(0), Y(1))]
+    model = QuantumModel(QuantumCircuit(2, block), observable=obs, backend="b200sv", diff_mode=mode, noise=noise)
+    ref = QuantumModel(QuantumCircuit(2, block), observable=obs, backend="b200sv", diff_mode=DiffMode.GPSR, noise=noise)
+    ref.load_state_dict(model.state_dict())
+    e, e_ref = model.expectation({}), ref.expectation({})
+    assert e.requires_grad and torch.allclose(e, e_ref, atol=1e-12)
+    w = torch.tensor([[0.7, -1.3]])
+    g = torch.autograd.grad((e * w).sum(), [p_ for p_ in model.parameters() if p_.requires_grad])
+    g_ref = torch.autograd.grad((e_ref * w).sum(), [p_ for p_ in ref.parameters() if p_.requires_grad])
+    assert len(g) == 2
+    for a, b in zip(g, g_ref):
+        assert torch.allclose(a, b, atol=1e-10), (a, b)
+    vals = {k: float(v) for k, v in model.vparams.items()}
+
+    def value(th: float, ph: float) -> float:
+        each = (("Depolarizing", (0.15,)), ("AmplitudeDamping", (0.2,)))
+        rho = _dense_noisy_density(chain(RX(0, th), CNOT(0, 1), RY(1, 0.4), CRZ(1, 0, ph)), 2, {k: each for k in range(4)})
+        return float(sum(wt * np.trace(block_to_tensor(o, {}, qubit_support=(0, 1))[0].numpy() @ rho).real for wt, o in zip([0.7, -1.3], obs)))
+
+    names = [k for k, p_ in model._params.items() if p_.requires_grad]
+    for gi, nm in zip(g, names):
+        hi = value(vals["th"] + (1e-6 if nm == "th" else 0), vals["ph"] + (1e-6 if nm == "ph" else 0))
+        lo = value(vals["th"] - (1e-6 if nm == "th" else 0), vals["ph"] - (1e-6 if nm == "ph" else 0))
+        assert abs(float(gi) - (hi - lo) / 2e-6) < 1e-7, nm

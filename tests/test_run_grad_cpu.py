@@ -98,3 +98,36 @@ def test_run_is_differentiable_wrt_parameters_and_state(doubles: None, monkeypat
     o32 = engine.run(cp, {k: v.detach() for k, v in vals.items()}, s32, dtype=torch.complex64)
     o32.abs().pow(2).sum().backward()
     assert s32.grad.dtype == torch.complex64 and s32.grad.shape == (1, 8)
+
+
+def test_adjoint_walk_through_non_unitary_matrix_ops(monkeypatch: pytest.MonkeyPatch) -> None:
+    """Noise superoperators (density-matrix path) are dense, invertible, NON-unitary ops: the walk must un-apply ψ with M⁻¹
+    and move λ with M†; singular ops (projectors) must be refused.  `apply_dense` is doubled by the oracle."""
+    from qadence_b200 import density
+    from qadence_b200.program import Op, OpKind, Program
+
+    def apply_dense(psi, matrix, target_bits):
+        n = int(psi.shape[1]).bit_length() - 1
+        op = Op(OpKind.MATK, tuple(n - 1 - b for b in target_bits), (), matrix=np.asarray(torch.as_tensor(matrix).numpy(), dtype=np.complex128))
+        return oracle.run(Program(n, [op]), {}, psi.to(torch.complex128)).to(psi.dtype)
+
+    monkeypatch.setattr(engine, "apply_dense", apply_dense)
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+    noise = density.noise_superoperator((("AmplitudeDamping", (0.3,)), ("Depolarizing", (0.2,))))
+    assert not np.allclose(noise @ noise.conj().T, np.eye(4))
+    prog = Program(3, [Op(OpKind.MATK, (0, 1), (), matrix=q), Op(OpKind.MATK, (1, 2), (), matrix=noise), Op(OpKind.MATK, (2, 0), (), matrix=q.T.copy())])
+    cp = engine.CompiledProgram(prog)
+    psi0 = torch.tensor(rng.normal(size=(2, 8)) + 1j * rng.normal(size=(2, 8)))
+    lam = torch.tensor(rng.normal(size=(2, 8)) + 1j * rng.normal(size=(2, 8)))
+    psi = oracle.run(prog, {}, psi0)
+    grads, psi_back, lam_back = engine._adjoint_walk(cp, {}, 2, torch.zeros(1, 2, dtype=torch.float64), psi.clone(), lam.clone())
+    assert torch.allclose(psi_back, psi0, atol=1e-12)
+    # <lam | M psi0> = <M† lam | psi0> for every psi0: compare through the inner product with a random probe
+    probe = torch.tensor(rng.normal(size=(2, 8)) + 1j * rng.normal(size=(2, 8)))
+    lhs = (lam.conj() * oracle.run(prog, {}, probe)).sum(-1)
+    rhs = (lam_back.conj() * probe).sum(-1)
+    assert torch.allclose(lhs, rhs, atol=1e-12)
+    singular = Program(2, [Op(OpKind.MATK, (0, 1), (), matrix=np.diag([1.0, 0, 0, 1.0]).astype(np.complex128))])
+    with pytest.raises(NotImplementedError, match="singular"):
+        engine._adjoint_walk(engine.CompiledProgram(singular), {}, 1, torch.zeros(1, 1, dtype=torch.float64), psi0[:1, :4].clone(), lam[:1, :4].clone())

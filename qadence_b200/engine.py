@@ -751,7 +751,8 @@ def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], 
     out = _AdjointExpectation.apply(cp, cobs, values, state, dtype, dev, B, ptable)
     if any(isinstance(values.get(nm), Tensor) and values[nm].requires_grad for o in cobs for nm in o.names):
         # recompute ψ is avoided: the Function keeps it; add the (value-free) observable-parameter path
-        psi = run(cp, values, state, dtype, dev)
+        with torch.no_grad():  # the wavefunction itself is not differentiated here
+            psi = run(cp, values, state, dtype, dev)
         out = out + _observable_param_term(cobs, psi, values)
     return out.to(real_dt)
 
@@ -814,7 +815,8 @@ def sample(cp: CompiledProgram, values: Mapping[str, Tensor] | None = None, n_sh
            dtype: torch.dtype = torch.complex128, device: torch.device | str | None = None,
            uniforms: Tensor | None = None, little_endian: bool = False) -> list[Counter]:
     """`list[Counter]` of big-endian bitstrings — `Backend.sample` (backends/pyqtorch/backend.py:283-310)."""
-    psi = run(cp, values, state, dtype, device)
+    with torch.no_grad():
+        psi = run(cp, values, state, dtype, device)
     if uniforms is None:
         uniforms = torch.rand(psi.shape[0], n_shots, dtype=torch.float64, device=psi.device)
     idx = sample_indices(psi, uniforms)

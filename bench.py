@@ -309,9 +309,9 @@ def main() -> None:
 
     # FP64 pipe view of the same step: every merged 2x2 costs 8 FP64 instructions per amplitude going forward and
     # 24 going backward (un-apply on psi and lambda + the four gradient moments), see DESIGN.md §4.1
-    n_chain_f = int((fwd.plan.rounds["mslot"] >= 0).sum())
-    n_chain_a = int((adj.plan.rounds["mslot"] >= 0).sum())
-    fp64_instr = (8 * n_chain_f + 24 * n_chain_a) * float(BATCH) * float(1 << N_QUBITS)
+    n_chain_f = int((fwd.plan.rounds["mslot"] >= 0).sum()) + int((fwd.plan.rounds["mslot4"] >= 0).sum())
+    n_chain_a = int((adj.plan.rounds["mslot"] >= 0).sum()) + int((adj.plan.rounds["mslot4"] >= 0).sum())
+    fp64_instr = (6 * n_chain_f + 18 * n_chain_a) * float(BATCH) * float(1 << N_QUBITS)
     fp64_tflops = 2 * fp64_instr / (ms_per_step * 1e-3) / 1e12
 
     if rank == 0:

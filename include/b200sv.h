@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define B200SV_ABI_VERSION 1
+#define B200SV_ABI_VERSION 2
 
 enum { B200SV_C64 = 0, B200SV_C128 = 1 };
 
@@ -93,7 +93,7 @@ typedef struct b200sv_gate {   /* 56 bytes */
  *      GF(2)-affine map of the tile index  pi(i) = XOR_{bits of i} pcol[bit] ^ pconst ^ XOR_k pext[k].vec
  *      (k over external control bits that are 1 for this CTA) and applied for free by storing the
  *      registers at pi(index) instead of index.  Backward execution loads from pi(index). */
-typedef struct b200sv_round {  /* 96 bytes */
+typedef struct b200sv_round {  /* 112 bytes */
   int32_t first_gate; /* absolute index into the gate array                                        */
   int32_t n_gates;
   uint8_t regpos[4];  /* tile-local bit positions held in registers (ascending)                    */
@@ -106,6 +106,9 @@ typedef struct b200sv_round {  /* 96 bytes */
   uint16_t n_pext;
   struct { uint8_t bit; uint8_t pad; uint16_t vec; } pext[4]; /* external control bit (global position) -> xor vector */
   int32_t flags;      /* B200SV_RF_*                                                               */
+  int32_t mslot4;     /* M-phase entry of register bit 4 (lean sweeps with r = 5), or -1                   */
+  uint8_t regpos4;    /* tile-local bit position of register bit 4                                         */
+  uint8_t pad4[11];
 } b200sv_round;
 
 typedef struct b200sv_sweep {  /* 128 bytes: one kernel launch = one read + one write of the state */
@@ -118,12 +121,40 @@ typedef struct b200sv_sweep {  /* 128 bytes: one kernel launch = one read + one 
   int32_t n_outer;      /* = n_local - m                                                           */
   int32_t n_exec;       /* resolved entries (chains) in this sweep                                  */
   uint8_t tile_bits[16];  /* global bit position of tile-local bit i (ascending)                   */
-  uint8_t outer_bits[48]; /* global bit positions enumerated by the CTA index (ascending)          */
+  uint8_t outer_bits[44]; /* global bit positions enumerated by the CTA index (ascending)          */
+  uint8_t io_mode;      /* B200SV_IO_*: which kernel runs the sweep and how its tiles move                 */
+  uint8_t pad_io[3];
   int32_t first_exec;   /* offset of this sweep's resolved entries in the plan-wide tables          */
   int16_t n_seg;        /* CTA index -> base index: sum_s ((c >> src) & (2^len - 1)) << dst; -1: bit loop */
   int16_t n_gen;        /* generic-phase entries in this sweep (0: the lean kernel variant is launched) */
   struct { uint8_t src, len, dst, pad; } seg[6];
 } b200sv_sweep;
+
+/* Which kernel executes a sweep (chosen by the planner, b200sv_lean_supported):
+ *   GENERIC   sweep_kernel: any gate mix (controlled gates, external diagonals, scales), cp.async tile staging;
+ *   LEAN      lean_sweep_kernel: merged 1-qubit chains + folded permutations only, persistent CTAs, normalised 2x2,
+ *             tiles gathered with cp.async (the tile is not a box of the state tensor);
+ *   LEAN_TMA  the same kernel, tiles staged by TMA (cp.async.bulk.tensor through the box described by b200sv_tma). */
+enum { B200SV_IO_GENERIC = 0, B200SV_IO_LEAN = 1, B200SV_IO_LEAN_TMA = 2 };
+
+/* The tile of a LEAN_TMA sweep as a box of the state seen as a rank-`rank` tensor (innermost dimension first).
+ * Dimension d covers index bits [start[d], start[d] + nbits[d]) of the amplitude index; a tile dimension is taken whole
+ * (box = size), a gap dimension one element at a time: its coordinate is bits [src[d], src[d] + nbits[d]) of the tile
+ * counter.  The last dimension is the remaining high index bits times the batch. */
+typedef struct b200sv_tma {  /* 24 bytes */
+  int32_t rank;
+  uint8_t start[5], nbits[5], is_tile[5], src[5];
+} b200sv_tma;
+
+/* Lean index tables: B200SV_LT_STRIDE uint32 words per round and direction (built by qadence_b200/plan.py).
+ *   [0,16)  XOR contribution of thread-index bits 0..3 (entry v = XOR over the set bits of v), [16,32) of bits 4..7:
+ *           low 16 bits = byte offset on the LOAD side of the round, high 16 bits = on the STORE side
+ *           (forward: load = plain index, store = permuted index; backward: the other way round);
+ *   [32,37) contribution of register bit a;   [37] bit 0: barrier needed between the round's loads and stores;
+ *   [38,43) resolved-entry index (relative to the sweep) of register bit a's merged 2x2, or 0xffff;
+ *   [43]    n_pext | bit_k << (8 + 6k): external control bits of the permutation;  [44,48) their XOR vectors, already
+ *           placed in the half (load / store) the permuted side occupies. */
+#define B200SV_LT_STRIDE 48
 
 /* Device-resident plan: the three arrays above plus the constant pool, uploaded once at convert
  * time (replaces the nn.Module tree built by backends/pyqtorch/convert_ops.py:177-351). */
@@ -136,6 +167,10 @@ typedef struct b200sv_plan {
   int32_t n_sweeps;
   int32_t n_exec_total;         /* resolved entries over all sweeps */
   const int32_t* exec_leader;   /* device: gate-record index of the leader of resolved entry x */
+  const uint32_t* lean_tab_fwd; /* device: [n_rounds_total][B200SV_LT_STRIDE], forward execution */
+  const uint32_t* lean_tab_bwd; /* device: the same for backward (adjoint) execution */
+  const b200sv_tma* tma_host;   /* host: one record per sweep (rank 0 unless io_mode == LEAN_TMA) */
+  const uint8_t* exec_mode;     /* device: io_mode of the sweep that owns resolved entry x */
 } b200sv_plan;
 
 /* ---- Pauli-sum records (observables, Rydberg / Pauli-like HamEvo generators) ----------------- */
@@ -150,6 +185,9 @@ typedef struct b200sv_pterm {  /* 32 bytes: coef * (-i)^{nY} * (-1)^{popc(i & zm
 /* ---- entry points ---------------------------------------------------------------------------- */
 
 int b200sv_abi_version(void);
+/* 1 if lean_sweep_kernel is instantiated for tiles of 2^m amplitudes with r register bits (host-side query used by the
+ * planner to choose io_mode; needs no device). */
+int b200sv_lean_supported(int dtype, int m, int r, int adjoint);
 /* number of SMs of the current device, or a negative error code (no device => B200SV_E_NODEVICE:
  * there is no CPU fallback anywhere in this library). */
 int b200sv_device_sm_count(void);

@@ -20,6 +20,7 @@ C64, C128 = 0, 1
 
 EXPORTS = [
     "b200sv_abi_version",
+    "b200sv_lean_supported",
     "b200sv_device_sm_count",
     "b200sv_init_zero_state",
     "b200sv_plan_workspace_bytes",
@@ -59,6 +60,10 @@ class PlanStruct(C.Structure):
         ("n_sweeps", C.c_int32),
         ("n_exec_total", C.c_int32),
         ("exec_leader", C.c_void_p),
+        ("lean_tab_fwd", C.c_void_p),
+        ("lean_tab_bwd", C.c_void_p),
+        ("tma_host", C.c_void_p),
+        ("exec_mode", C.c_void_p),
     ]
 
 
@@ -88,6 +93,7 @@ def load() -> C.CDLL:
     vp, i32, i64, u64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
     protos = {
         "b200sv_abi_version": [],
+        "b200sv_lean_supported": [i32, i32, i32, i32],
         "b200sv_device_sm_count": [],
         "b200sv_init_zero_state": [vp, i32, i32, i64, vp],
         "b200sv_plan_workspace_bytes": [vp, i32, i64, i32],
@@ -117,7 +123,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int64 if name == "b200sv_plan_workspace_bytes" else C.c_int
-    if lib.b200sv_abi_version() != 1:
+    if lib.b200sv_abi_version() != 2:
         raise B200svError("libb200sv.so ABI version mismatch")
     _lib = lib
     return lib

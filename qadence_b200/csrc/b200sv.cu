@@ -4,12 +4,19 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef B200SV_LEAN_NBUF_DEFAULT
+#define B200SV_LEAN_NBUF_DEFAULT 1
+#endif
 #ifndef B200SV_PERSISTENT_DEFAULT
 #define B200SV_PERSISTENT_DEFAULT 0
 #endif
 
+#include <mutex>
+#include <type_traits>
+
 #include "b200sv.h"
 #include "sweep.cuh"
+#include "lean.cuh"
 
 using namespace b200sv;
 
@@ -31,26 +38,67 @@ namespace {
 // sweep launchers
 // ------------------------------------------------------------------------------------------------
 template <typename real> struct Workspace {
-  ExecGate<real>* xtab;
-  double* mom;
+  ExecGate<real>* xtab;       // generic sweeps: [n_exec_total][batch]
+  double* mom;                // adjoint: [n_exec_total][batch][4]
+  LeanGate<real>* ltab;       // lean sweeps: [batch][n_exec_total]
+  typename C2<real>::type* sscal;  // lean sweeps: [n_sweeps][batch]
 };
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 template <typename real>
 Workspace<real> carve_workspace(void* ws, const b200sv_plan* plan, int64_t batch) {
   Workspace<real> w;
-  w.xtab = reinterpret_cast<ExecGate<real>*>(ws);
-  size_t bytes = (size_t)plan->n_exec_total * (size_t)batch * sizeof(ExecGate<real>);
-  bytes = (bytes + 255) & ~(size_t)255;
-  w.mom = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + bytes);
+  unsigned char* p = reinterpret_cast<unsigned char*>(ws);
+  const size_t ne = (size_t)plan->n_exec_total * (size_t)batch;
+  w.xtab = reinterpret_cast<ExecGate<real>*>(p);
+  p += align256(ne * sizeof(ExecGate<real>));
+  w.mom = reinterpret_cast<double*>(p);
+  p += align256(ne * 4 * sizeof(double));
+  w.ltab = reinterpret_cast<LeanGate<real>*>(p);
+  p += align256(ne * sizeof(LeanGate<real>));
+  w.sscal = reinterpret_cast<typename C2<real>::type*>(p);
   return w;
 }
 
 template <typename real>
-size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool adjoint) {
-  size_t bytes = (size_t)plan->n_exec_total * (size_t)batch * sizeof(ExecGate<real>);
-  bytes = (bytes + 255) & ~(size_t)255;
-  if (adjoint) bytes += (size_t)plan->n_exec_total * (size_t)batch * 4 * sizeof(double);
+size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool /*adjoint*/) {
+  const size_t ne = (size_t)plan->n_exec_total * (size_t)batch;
+  size_t bytes = align256(ne * sizeof(ExecGate<real>)) + align256(ne * 4 * sizeof(double)) + align256(ne * sizeof(LeanGate<real>));
+  bytes += align256((size_t)plan->n_sweeps * (size_t)batch * 2 * sizeof(real));
   return bytes + 256;
+}
+
+// per-device launch state of one kernel instantiation (the opt-in shared-memory size and the occupancy are properties of
+// the (device, function) pair: a second device in the same process needs its own cudaFuncSetAttribute)
+struct DeviceLaunchState {
+  std::mutex mu;
+  size_t configured[64] = {};
+  size_t occ_smem[64] = {};
+  int occ_blocks[64] = {};
+};
+
+template <typename K>
+int prepare_kernel(K kern, DeviceLaunchState& stt, size_t smem, int threads, int* resident_ctas) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return B200SV_E_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(stt.mu);
+  if (smem > stt.configured[dev]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stt.configured[dev] = smem;
+  }
+  if (resident_ctas) {
+    if (stt.occ_blocks[dev] == 0 || stt.occ_smem[dev] != smem) {
+      int sms = 0, per_sm = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+      stt.occ_blocks[dev] = sms * (per_sm > 0 ? per_sm : 1);
+      stt.occ_smem[dev] = smem;
+    }
+    *resident_ctas = stt.occ_blocks[dev];
+  }
+  return 0;
 }
 
 template <typename real, int R, bool ADJ, bool GEN, bool PEER = false>
@@ -64,23 +112,13 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   const size_t smem = sweep_smem_bytes<real, ADJ>(sw.m, sw.n_exec, sw.n_rounds, nbuf);
   auto kern = sweep_kernel<real, R, ADJ, GEN, PEER>;
-  static size_t configured = 0;  // per instantiation
-  if (smem > configured) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DeviceLaunchState lstate;  // per instantiation, per device inside
   const int nt = 1 << (sw.m - R);
   if (nt > SweepCfg<real, R, ADJ>::MAXT) return B200SV_E_ARG;
   const long long total = PEER ? peers->n_tiles : (((long long)batch) << sw.n_outer);
   if (total <= 0) return PEER ? 0 : B200SV_E_ARG;  // a rank may have no tile of a very small sweep
-  static int resident = 0;  // persistent grid: CTAs that fit on the device at once
-  if (resident == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SweepCfg<real, R, ADJ>::MAXT, smem));
-    resident = sms * (per_sm > 0 ? per_sm : 1);
-  }
+  int resident = 0;  // persistent grid: CTAs that fit on the device at once
+  if (int rc = prepare_kernel(kern, lstate, smem, nt, persistent ? &resident : nullptr)) return rc;
   long long grid = (!persistent || total < resident) ? total : resident;
   const long long per_cta = (total + grid - 1) / grid;
   grid = (total + per_cta - 1) / per_cta;
@@ -164,6 +202,171 @@ int launch_sweep_r(void* psi, void* lam, const double* params, double* grads, co
 #undef B200SV_LAUNCH
 }
 
+// ------------------------------------------------------------------------------------------------
+// lean sweeps: TMA tensor maps, persistent launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<TmapEncodeFn>(p);
+  }();
+  return fn;
+}
+
+// The state [batch][2^n] (complex, `amp_bytes` per amplitude) as the tensor `tm` describes it (see b200sv_tma): elements are
+// 8 bytes wide, so a complex128 amplitude is two elements and dimension 0 carries one extra bit.
+int make_tensor_map(CUtensorMap* out, void* state, int amp_bytes, int64_t batch, const b200sv_tma& tm) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (!enc) return B200SV_E_UNSUPPORTED;
+  const int rank = tm.rank;
+  if (rank < 2 || rank > 5 || tm.start[0] != 0 || !tm.is_tile[0]) return B200SV_E_ARG;
+  const int ebit = amp_bytes == 16 ? 1 : 0;
+  cuuint64_t size[5], stride[5];
+  cuuint32_t box[5], estr[5];
+  for (int d = 0; d < rank; ++d) {
+    const int bits = tm.nbits[d] + (d == 0 ? ebit : 0);
+    size[d] = 1ull << bits;
+    if (d == rank - 1) size[d] = (cuuint64_t)batch << tm.nbits[d];
+    box[d] = tm.is_tile[d] ? (cuuint32_t)size[d] : 1u;
+    estr[d] = 1;
+    if (box[d] > 256u || size[d] > (1ull << 32)) return B200SV_E_UNSUPPORTED;
+    if (d >= 1) {
+      stride[d - 1] = (cuuint64_t)amp_bytes << tm.start[d];
+      if (stride[d - 1] % 16 != 0 || stride[d - 1] >= (1ull << 40)) return B200SV_E_UNSUPPORTED;
+    }
+  }
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, state, size, stride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : B200SV_E_ARG;
+}
+
+// (real, R, M, ADJ) combinations lean_sweep_kernel is compiled for
+#define B200SV_LEAN_INSTANCES(X)                                                                          \
+  X(double, 4, 11, false) X(double, 5, 12, false) X(double, 4, 10, false)                                 \
+  X(double, 3, 10, true) X(double, 4, 11, true) X(double, 3, 11, true)                                    \
+  X(float, 4, 12, false) X(float, 5, 12, false) X(float, 4, 11, false)                                    \
+  X(float, 3, 11, true) X(float, 4, 12, true) X(float, 4, 11, true)
+
+template <typename real, int R, int M, bool ADJ>
+int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<real>& ws, int s, int n, int64_t batch,
+                uint64_t index_hi, cudaStream_t st) {
+  using c2 = typename C2<real>::type;
+  const b200sv_sweep& sw = plan->sweeps_host[s];
+  const char* nbuf_s = getenv("B200SV_LEAN_NBUF");  // read per launch: tests switch it
+  const int nbuf_env = nbuf_s ? atoi(nbuf_s) : B200SV_LEAN_NBUF_DEFAULT;
+  static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
+  static const int occ_env = [] { const char* e = getenv("B200SV_LEAN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const bool tma = sw.io_mode == B200SV_IO_LEAN_TMA;
+  const int nbuf = (tma && nbuf_env == 2) ? 2 : 1;
+  const size_t smem = lean_smem_bytes<real, R, M, ADJ>(sw.n_rounds, sw.n_exec, nbuf);
+  if (smem > 227 * 1024) return B200SV_E_UNSUPPORTED;
+  auto kern = lean_sweep_kernel<real, R, M, ADJ>;
+  static DeviceLaunchState lstate;
+  constexpr int NT = 1 << (M - R);
+  int resident = 0;
+  if (int rc = prepare_kernel(kern, lstate, smem, NT, &resident)) return rc;
+  if (occ_env > 0) {  // tuning experiments: cap the CTAs per SM
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms * occ_env < resident) resident = sms * occ_env;
+  }
+  const long long total = ((long long)batch) << sw.n_outer;
+  if (total <= 0) return B200SV_E_ARG;
+  long long grid = total < resident ? total : resident;
+  const long long per_cta = (total + grid - 1) / grid;
+  grid = (total + per_cta - 1) / per_cta;
+
+  LeanArgs<real> a{};
+  a.psi = (c2*)psi;
+  a.lam = (c2*)lam;
+  a.tab = (ADJ ? plan->lean_tab_bwd : plan->lean_tab_fwd) + (size_t)sw.first_round * LT_STRIDE;
+  a.gtab = ws.ltab;
+  a.sscal = ws.sscal + (size_t)s * batch;
+  a.mom = ws.mom;
+  a.n = n;
+  a.n_exec_total = plan->n_exec_total;
+  a.batch = batch;
+  a.index_hi = index_hi;
+  a.total_tiles = total;
+  a.tiles_per_cta = per_cta;
+  a.nbuf = nbuf;
+  a.dbg = dbg_flags;
+  CUtensorMap tm_psi{}, tm_lam{};
+  if (tma) {
+    if (!plan->tma_host) return B200SV_E_ARG;
+    const b200sv_tma& tm = plan->tma_host[s];
+    if (int rc = make_tensor_map(&tm_psi, psi, (int)sizeof(c2), batch, tm)) return rc;
+    if (ADJ) { if (int rc = make_tensor_map(&tm_lam, lam, (int)sizeof(c2), batch, tm)) return rc; }
+    a.tg.rank = tm.rank;
+    a.tg.top_shift = tm.nbits[tm.rank - 1];
+    for (int d = 0; d < 5; ++d) { a.tg.src[d] = tm.src[d]; a.tg.nbits[d] = tm.nbits[d]; a.tg.is_tile[d] = tm.is_tile[d]; }
+  }
+  kern<<<(unsigned)grid, NT, smem, st>>>(a, sw, tm_psi, tm_lam);
+  LAUNCH_CK();
+  return 0;
+}
+
+template <typename real, bool ADJ>
+int launch_lean_r(void* psi, void* lam, const b200sv_plan* plan, const Workspace<real>& ws, int s, int n, int64_t batch,
+                  uint64_t index_hi, cudaStream_t st) {
+  const b200sv_sweep& sw = plan->sweeps_host[s];
+  if (sw.n_outer != n - sw.m || !plan->lean_tab_fwd || !plan->lean_tab_bwd) return B200SV_E_ARG;
+#define B200SV_X(REAL, RR, MM, AA)                                                                                    \
+  if constexpr (std::is_same<real, REAL>::value && ADJ == AA) {                                                       \
+    if (sw.r == RR && sw.m == MM) return launch_lean<real, RR, MM, ADJ>(psi, lam, plan, ws, s, n, batch, index_hi, st); \
+  }
+  B200SV_LEAN_INSTANCES(B200SV_X)
+#undef B200SV_X
+  return B200SV_E_UNSUPPORTED;
+}
+
+bool lean_supported(int dtype, int m, int r, bool adjoint) {
+#define B200SV_X(REAL, RR, MM, AA) \
+  if ((dtype == B200SV_C128) == std::is_same<REAL, double>::value && adjoint == AA && r == RR && m == MM) return true;
+  B200SV_LEAN_INSTANCES(B200SV_X)
+#undef B200SV_X
+  return false;
+}
+
+// gradient kernel: moments of every chain -> gradient of every parametric gate of the chain (generic and lean sweeps)
+template <typename real>
+__global__ void gradient2_kernel(const b200sv_gate* __restrict__ gates, const int* __restrict__ exec_leader,
+                                 const uint8_t* __restrict__ exec_mode, const double* __restrict__ params,
+                                 const double* __restrict__ consts, const ExecGate<real>* __restrict__ xtab,
+                                 const LeanGate<real>* __restrict__ ltab, const double* __restrict__ mom_g,
+                                 double* __restrict__ grads, int x_first, int x_count, int n_exec_total, long long batch) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)x_count * batch) return;
+  const int x = x_first + (int)(t / batch);
+  const long long b = t % batch;
+  const b200sv_gate* rec = gates + exec_leader[x];
+  const double* mom = mom_g + ((long long)x * batch + b) * 4;
+  if (exec_mode[x] == B200SV_IO_GENERIC) {
+    const int gr = xtab[(long long)x * batch + b].gr;
+    if (gr == GR_CHAIN) chain_gradients(rec, mom, params, consts, grads, batch, b);
+    else if (gr == GR_SCALE && rec->grad_row >= 0) atomicAdd(&grads[(long long)rec->grad_row * batch + b], mom[0]);
+    return;
+  }
+  const LeanGate<real> g = ltab[b * n_exec_total + x];
+  if ((g.gr & 0xff) != GR_CHAIN) return;
+  // measured with both states divided by the pending scalar s (real factor |s|^2) and, after a column flip, with the
+  // pair relabelled by X: X P X = P for I, X and -P for Y, Z
+  const double sc = (double)g.mscale, sg = (g.gr >> 8) & 1 ? -1.0 : 1.0;
+  const double m4[4] = {sc * mom[0], sc * mom[1], sg * sc * mom[2], sg * sc * mom[3]};
+  chain_gradients(rec, m4, params, consts, grads, batch, b);
+}
+
 // forward (ADJ = false) or adjoint (ADJ = true) execution of sweeps [first, last)
 template <typename real, bool ADJ>
 int run_plan(void* psi, void* lam, int n, int64_t batch, const double* params, double* grads,
@@ -175,21 +378,47 @@ int run_plan(void* psi, void* lam, int n, int64_t batch, const double* params, d
   const int x_count = x_last - x_first;
   const long long nthreads = (long long)x_count * batch;
   const unsigned rgrid = (unsigned)((nthreads + 127) / 128);
-  if (x_count > 0) {
+  bool any_generic = false, any_lean = false, lean_ok = true;
+  for (int s = first; s < last; ++s) {
+    const b200sv_sweep& sw = plan->sweeps_host[s];
+    (sw.io_mode == B200SV_IO_GENERIC ? any_generic : any_lean) = true;
+    // a plan marked for the lean kernel but executed in the direction / dtype it was not built for: generic kernels
+    if (sw.io_mode != B200SV_IO_GENERIC && !lean_supported(sizeof(real) == 8 ? B200SV_C128 : B200SV_C64, sw.m, sw.r, ADJ)) lean_ok = false;
+  }
+  if (any_lean && (!plan->exec_mode || !plan->lean_tab_fwd || !plan->lean_tab_bwd)) return B200SV_E_ARG;
+  if (!lean_ok) { any_generic = true; any_lean = false; }
+  if (x_count > 0 && any_generic) {
     resolve_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab, x_first,
                                                 x_count, (long long)batch, ADJ ? -1 : +1, ADJ ? 1 : 0);
     LAUNCH_CK();
-    if (ADJ) CK(cudaMemsetAsync(ws.mom + (size_t)x_first * batch * 4, 0, (size_t)x_count * batch * 4 * sizeof(double), st));
   }
+  if (any_lean) {
+    const long long nt = (long long)(last - first) * batch;
+    resolve_lean_kernel<real><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>(plan->sweeps, plan->rounds, plan->gates, plan->exec_leader,
+                                                                         params, plan->consts, ws.ltab, ws.sscal, first, last - first,
+                                                                         plan->n_exec_total, (long long)batch, ADJ ? -1 : +1);
+    LAUNCH_CK();
+  }
+  if (ADJ && x_count > 0) CK(cudaMemsetAsync(ws.mom + (size_t)x_first * batch * 4, 0, (size_t)x_count * batch * 4 * sizeof(double), st));
+  auto one = [&](int s) -> int {
+    if (!any_lean || plan->sweeps_host[s].io_mode == B200SV_IO_GENERIC)
+      return launch_sweep_r<real, ADJ>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, ADJ ? -1 : +1, st);
+    return launch_lean_r<real, ADJ>(psi, lam, plan, ws, s, n, batch, index_hi, st);
+  };
   if (!ADJ) {
     for (int s = first; s < last; ++s)
-      if (int rc = launch_sweep_r<real, false>(psi, nullptr, params, nullptr, plan, ws, s, n, batch, index_hi, +1, st)) return rc;
+      if (int rc = one(s)) return rc;
   } else {
     for (int s = last - 1; s >= first; --s)
-      if (int rc = launch_sweep_r<real, true>(psi, lam, params, grads, plan, ws, s, n, batch, index_hi, -1, st)) return rc;
+      if (int rc = one(s)) return rc;
     if (x_count > 0) {
-      gradient_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab, ws.mom,
-                                                   grads, x_first, x_count, (long long)batch);
+      if (any_lean) {
+        gradient2_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, plan->exec_mode, params, plan->consts, ws.xtab,
+                                                      ws.ltab, ws.mom, grads, x_first, x_count, plan->n_exec_total, (long long)batch);
+      } else {
+        gradient_kernel<real><<<rgrid, 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab, ws.mom,
+                                                     grads, x_first, x_count, (long long)batch);
+      }
       LAUNCH_CK();
     }
   }
@@ -662,6 +891,11 @@ inline int grid_for(long long total, int threads) {
 extern "C" {
 
 int b200sv_abi_version(void) { return B200SV_ABI_VERSION; }
+
+int b200sv_lean_supported(int dtype, int m, int r, int adjoint) {
+  if (dtype != B200SV_C64 && dtype != B200SV_C128) return 0;
+  return lean_supported(dtype, m, r, adjoint != 0) ? 1 : 0;
+}
 
 int b200sv_device_sm_count(void) {
   int dev = 0, sms = 0;

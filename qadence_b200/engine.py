@@ -62,6 +62,10 @@ class DevicePlan:
         self._gates = up(plan.gates)
         self._consts = up(plan.consts)
         self._leaders = up(plan.exec_leader)
+        self._lean_fwd = up(plan.lean_tab_fwd)
+        self._lean_bwd = up(plan.lean_tab_bwd)
+        self._exec_mode = up(plan.exec_mode)
+        self._host_tma = np.ascontiguousarray(plan.tma) if len(plan.tma) else np.zeros(1, dtype=plan.tma.dtype)
         self.struct = cabi.PlanStruct(
             self._sweeps.data_ptr(),
             self._rounds.data_ptr(),
@@ -71,6 +75,10 @@ class DevicePlan:
             plan.n_sweeps,
             plan.n_exec_total,
             self._leaders.data_ptr(),
+            self._lean_fwd.data_ptr(),
+            self._lean_bwd.data_ptr(),
+            self._host_tma.ctypes.data,
+            self._exec_mode.data_ptr(),
         )
         self._workspaces: dict = {}
 

@@ -37,18 +37,24 @@ ROUND_DT = np.dtype(
     [
         ("first_gate", "<i4"), ("n_gates", "<i4"), ("regpos", "u1", (4,)), ("thrpos", "u1", (12,)), ("first_exec", "<i4"),
         ("n_exec", "<i4"), ("mslot", "<i4", (4,)), ("pcol", "<u2", (12,)), ("pconst", "<u2"), ("n_pext", "<u2"),
-        ("pext", PEXT_DT, (4,)), ("flags", "<i4"),
+        ("pext", PEXT_DT, (4,)), ("flags", "<i4"), ("mslot4", "<i4"), ("regpos4", "u1"), ("pad4", "u1", (11,)),
     ]
 )
 SWEEP_DT = np.dtype(
     [
         ("m", "<i4"), ("r", "<i4"), ("first_round", "<i4"), ("n_rounds", "<i4"), ("first_gate", "<i4"),
-        ("n_gates", "<i4"), ("n_outer", "<i4"), ("n_exec", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (48,)),
+        ("n_gates", "<i4"), ("n_outer", "<i4"), ("n_exec", "<i4"), ("tile_bits", "u1", (16,)), ("outer_bits", "u1", (44,)),
+        ("io_mode", "u1"), ("pad_io", "u1", (3,)),
         ("first_exec", "<i4"), ("n_seg", "<i2"), ("n_gen", "<i2"), ("seg", np.dtype([("src", "u1"), ("len", "u1"), ("dst", "u1"), ("pad", "u1")]), (6,)),
     ]
 )
 PTERM_DT = np.dtype([("xmask", "<u8"), ("zmask", "<u8"), ("coef_row", "<i4"), ("n_y", "<i4"), ("pad", "<i4", (2,))])
-assert GATE_DT.itemsize == 56 and ROUND_DT.itemsize == 96 and SWEEP_DT.itemsize == 128 and PTERM_DT.itemsize == 32
+TMA_DT = np.dtype([("rank", "<i4"), ("start", "u1", (5,)), ("nbits", "u1", (5,)), ("is_tile", "u1", (5,)), ("src", "u1", (5,))])
+assert GATE_DT.itemsize == 56 and ROUND_DT.itemsize == 112 and SWEEP_DT.itemsize == 128 and PTERM_DT.itemsize == 32
+assert TMA_DT.itemsize == 24
+IO_GENERIC, IO_LEAN, IO_LEAN_TMA = 0, 1, 2
+LT_STRIDE = 48
+LT_EMPTY = 0xFFFF
 
 GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
 GF_GRAD = 1
@@ -72,6 +78,12 @@ class TileConfig:
     r: int
     low: int
     fold: int  # bank-swizzle fold width: 3 for 16-byte amplitudes, 4 for 8-byte
+    adjoint: bool = False  # direction the plan will be executed in (decides which kernels exist for it)
+    lean: bool = True  # let sweeps without generic-phase entries run on lean_sweep_kernel (B200SV_LEAN=0 disables)
+
+    @property
+    def c128(self) -> bool:
+        return self.fold == 3
 
     @staticmethod
     def default(dtype_is_c128: bool, adjoint: bool) -> "TileConfig":
@@ -80,12 +92,12 @@ class TileConfig:
         key = f"B200SV_TILE_{'ADJ' if adjoint else 'FWD'}_{'C128' if dtype_is_c128 else 'C64'}"
         if key in os.environ:  # tuning override: "m,r,low"
             m, r, low = (int(x) for x in os.environ[key].split(","))
-            return TileConfig(m=m, r=r, low=low, fold=3 if dtype_is_c128 else 4)
+            return TileConfig(m=m, r=r, low=low, fold=3 if dtype_is_c128 else 4, adjoint=adjoint)
         # measured on B200 (profiles/r01_tile_geometry.md): 64-byte runs (low = 2 for 16-byte amplitudes) already
         # stream at ~80 % of the HBM roofline, and every forced low bit costs a "hard" bit, i.e. more sweeps
         if dtype_is_c128:
-            return TileConfig(m=11, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3)
-        return TileConfig(m=12, r=4, low=2, fold=4) if not adjoint else TileConfig(m=11, r=3, low=2, fold=4)
+            return TileConfig(m=11, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3, adjoint=True)
+        return TileConfig(m=12, r=4, low=2, fold=4) if not adjoint else TileConfig(m=11, r=3, low=2, fold=4, adjoint=True)
 
 
 @dataclass
@@ -128,8 +140,10 @@ class ConstPool:
         return a
 
 
-def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, r: int = 2) -> list[_G]:
-    """`n` is the TOTAL qubit count: bit positions >= n_local refer to the rank bits of a sharded state."""
+def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, r: int = 2, harden_diag: bool = False) -> list[_G]:
+    """`n` is the TOTAL qubit count: bit positions >= n_local refer to the rank bits of a sharded state.
+    `harden_diag`: uncontrolled diagonal 1-qubit gates ask for their target as a tile bit like any other 1-qubit gate, so
+    that they merge into the 2x2 chains of lean sweeps instead of becoming interpreted "external diagonal" entries."""
     out: list[_G] = []
     for i, op in enumerate(ops):
         bit = lambda q: n - 1 - q  # noqa: E731
@@ -144,7 +158,10 @@ def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, 
             m = np.asarray(op.matrix, dtype=np.complex128).reshape(2, 2)
             t = bit(op.targets[0])
             if m[0, 1] == 0 and m[1, 0] == 0:
-                out.append(_G(GK_DIAG, (), t, ctrl, -1, pool.add([m[0, 0], m[1, 1]]), False, i))
+                if harden_diag and not ctrl:
+                    out.append(_G(GK_DIAG, (t,), -1, ctrl, -1, pool.add([m[0, 0], m[1, 1]]), False, i))
+                else:
+                    out.append(_G(GK_DIAG, (), t, ctrl, -1, pool.add([m[0, 0], m[1, 1]]), False, i))
             elif np.array_equal(m, _X):
                 out.append(_G(GK_X, (t,), -1, ctrl, -1, -1, False, i))
             elif np.all(m.imag == 0):
@@ -154,7 +171,10 @@ def _lower(ops: Sequence[Op], n: int, slot_of: dict[str, int], pool: ConstPool, 
         elif op.kind in (OpKind.RX, OpKind.RY):
             out.append(_G(GK_RX if op.kind == OpKind.RX else GK_RY, (bit(op.targets[0]),), -1, ctrl, slot, cidx, grad, i))
         elif op.kind in (OpKind.RZ, OpKind.PHASE):
-            out.append(_G(GK_RZ if op.kind == OpKind.RZ else GK_PHASE, (), bit(op.targets[0]), ctrl, slot, cidx, grad, i))
+            if harden_diag and not ctrl:
+                out.append(_G(GK_RZ if op.kind == OpKind.RZ else GK_PHASE, (bit(op.targets[0]),), -1, ctrl, slot, cidx, grad, i))
+            else:
+                out.append(_G(GK_RZ if op.kind == OpKind.RZ else GK_PHASE, (), bit(op.targets[0]), ctrl, slot, cidx, grad, i))
         elif op.kind == OpKind.SWAP:
             ta, tb = (bit(q) for q in op.targets)
             if r >= 2:
@@ -368,7 +388,11 @@ def _pack_rounds(sgates: list[_G], r: int, tile: set[int], phases: bool) -> list
                     rd.mchains[t] = [g]
                     rd.regbits.add(t)
                     placed = True
-            if ok and not placed and not (phases and _is_perm(g) and all(b in tile for b in g.hard)):
+            # an uncontrolled 1-qubit gate on a tile bit that cannot join the M phase of THIS round (it follows a permutation
+            # or a generic gate on its bit) waits for the next round instead of entering the interpreted G phase: rounds
+            # stay "lean" (merged 2x2 + permutations only), which is what lean_sweep_kernel executes
+            waits = phases and _is_matrix(g) and (g.hard[0] if g.hard else g.soft) in tile
+            if ok and not placed and not waits and not (phases and _is_perm(g) and all(b in tile for b in g.hard)):
                 # generic phase: must commute with the accepted permutation gates; needs registers for hard bits
                 before_p = not (g.bits_any & p_hard) and not (hard & p_any)
                 if before_p and len(rd.regbits | hard) <= r:
@@ -477,6 +501,10 @@ class SweepPlan:
     consts: np.ndarray  # [n_const, 2] float64
     n_source_gates: int
     exec_leader: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))  # gate-record index per resolved entry
+    lean_tab_fwd: np.ndarray = field(default_factory=lambda: np.zeros((0, LT_STRIDE), dtype=np.uint32))
+    lean_tab_bwd: np.ndarray = field(default_factory=lambda: np.zeros((0, LT_STRIDE), dtype=np.uint32))
+    tma: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=TMA_DT))
+    exec_mode: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.uint8))  # io_mode of the owning sweep, per resolved entry
     # diagnostics: for each sweep, list of rounds, each a list of source-op indices (execution order)
     order: list[list[list[int]]] = field(default_factory=list)
 
@@ -503,7 +531,7 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
     r = max(1, min(cfg.r, m)) if n > 0 else 1
     if m - r > 8:
         m = r + 8
-    lowered = _lower(ops, n_total, slot_of, pool, r)
+    lowered = _lower(ops, n_total, slot_of, pool, r, harden_diag=(n_total == n and cfg.lean))
     for g_ in lowered:
         if any(b >= n for b in g_.hard):
             raise ValueError("non-diagonal gate on a global (rank) qubit: make it local first (dist.plan_layout)")
@@ -574,17 +602,24 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
             ordered = [g for ch in entries for g in ch] + list(rnd.pgates)
             rd = np.zeros(1, dtype=ROUND_DT)
             rd["first_gate"], rd["n_gates"] = n_gates_total, len(ordered)
-            rd["regpos"][0, :r] = regs
+            rd["regpos"][0, : min(r, 4)] = regs[:4]
+            if r > 4:
+                rd["regpos4"] = regs[4]
             thr = _thread_positions(m, regs, cfg.fold)
             rd["thrpos"][0, : len(thr)] = thr
             rd["mslot"][0, :] = -1
+            rd["mslot4"] = -1
             ga = np.zeros(len(ordered), dtype=GATE_DT)
             gi = 0
             for ei, ch in enumerate(entries):
                 is_m = ei < len(m_entries)
                 xk = _chain_xkind(ch)
                 if is_m:
-                    rd["mslot"][0, reg_index[ch[0].hard[0] if ch[0].hard else ch[0].soft]] = n_exec_sweep
+                    ra = reg_index[ch[0].hard[0] if ch[0].hard else ch[0].soft]
+                    if ra < 4:
+                        rd["mslot"][0, ra] = n_exec_sweep
+                    else:
+                        rd["mslot4"] = n_exec_sweep
                 elif ei == len(m_entries):
                     rd["first_exec"] = n_exec_sweep
                 for ci, g in enumerate(ch):
@@ -652,7 +687,144 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
         for gi in range(fg, fg + ng):
             if gates[gi]["chain"] >= 1:
                 leaders[fx + int(gates[gi]["xidx"])] = gi
-    return SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), leaders, order)
+    plan = SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), leaders, order=order)
+    finish_lean(plan, n_total)
+    return plan
+
+
+# ---- lean sweeps: kernel choice, TMA boxes, index tables --------------------------------------------------
+def _lean_supported(c128: bool, m: int, r: int, adjoint: bool) -> bool:
+    """Whether `lean_sweep_kernel` is instantiated for this geometry (asks the library; host-only call)."""
+    from . import cabi
+
+    try:
+        return bool(cabi.load().b200sv_lean_supported(cabi.C128 if c128 else cabi.C64, m, r, int(adjoint)))
+    except cabi.B200svError:
+        return False
+
+
+def tma_box(tile_bits: Sequence[int], n: int, c128: bool) -> np.ndarray | None:
+    """The tile as a box of the [batch][2^n] state seen as a tensor of 8-byte elements (see `b200sv_tma`), or None when it
+    needs more than 5 dimensions.  Runs of consecutive tile bits become tile dimensions (at most 256 elements each, so long
+    runs are split), the gaps between them dimensions walked one element at a time by the tile counter."""
+    tile = sorted(int(t) for t in tile_bits)
+    if not tile or tile[0] != 0:
+        return None
+    if not c128 and (len(tile) < 2 or tile[1] != 1):
+        return None  # the innermost box row must be at least 16 bytes
+    runs: list[list[int]] = []
+    for t in tile:
+        if runs and runs[-1][0] + runs[-1][1] == t:
+            runs[-1][1] += 1
+        else:
+            runs.append([t, 1])
+    dims: list[tuple[int, int, int, int]] = []  # (start bit, n bits, is_tile, src bit of the tile counter)
+    pos = src = 0
+    for start, length in runs:
+        if start > pos:
+            dims.append((pos, start - pos, 0, src))
+            src += start - pos
+        st, rem = start, length
+        while rem > 0:
+            k = min(rem, 8 - (1 if (c128 and st == 0) else 0))
+            dims.append((st, k, 1, 0))
+            st += k
+            rem -= k
+        pos = start + length
+    dims.append((pos, n - pos, 0, src))  # remaining high bits x batch
+    if len(dims) > 5 or len(dims) < 2:
+        return None
+    rec = np.zeros(1, dtype=TMA_DT)
+    rec["rank"] = len(dims)
+    for d, (st, nb, it, sr) in enumerate(dims):
+        rec["start"][0, d], rec["nbits"][0, d], rec["is_tile"][0, d], rec["src"][0, d] = st, nb, it, sr
+    return rec
+
+
+def _swz_b(e: int, c128: bool) -> int:
+    """Bank swizzle of the in-tile layout between rounds (`swz<real>` in sweep.cuh); GF(2)-linear."""
+    return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9)) & 7) if c128 else e ^ (((e >> 4) ^ (e >> 8)) & 15)
+
+
+def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_layout: bool, store_plain_layout: bool) -> np.ndarray:
+    """One round's B200SV_LT_STRIDE words for one direction (layout documented in include/b200sv.h)."""
+    shift = 4 if c128 else 3
+    perm = bool(int(rd["flags"]) & RF_PERM)
+    pcol = [int(x) for x in rd["pcol"][:m]]
+    regs = [int(x) for x in rd["regpos"][: min(r, 4)]] + ([int(rd["regpos4"])] if r > 4 else [])
+    thr = [int(x) for x in rd["thrpos"][: m - r]]
+
+    def lay(v: int, plain_layout: bool) -> int:
+        return (v if plain_layout else _swz_b(v, c128)) << shift
+
+    def word(plain_v: int, perm_v: int) -> int:
+        lv, sv = (plain_v, perm_v) if forward else (perm_v, plain_v)
+        lo, hi = lay(lv, load_plain_layout), lay(sv, store_plain_layout)
+        assert lo < 65536 and hi < 65536
+        return lo | (hi << 16)
+
+    T = np.zeros(LT_STRIDE, dtype=np.uint32)
+    for half in range(2):
+        for v in range(16):
+            plain = permd = 0
+            for k in range(4):
+                tb = k + 4 * half
+                if tb < len(thr) and (v >> k) & 1:
+                    plain |= 1 << thr[tb]
+                    permd ^= pcol[thr[tb]] if perm else (1 << thr[tb])
+            if half == 0 and perm:
+                permd ^= int(rd["pconst"])
+            T[16 * half + v] = word(plain, permd)
+    for a, pos in enumerate(regs):
+        T[32 + a] = word(1 << pos, pcol[pos] if perm else (1 << pos))
+    T[37] = 1 if (perm or load_plain_layout != store_plain_layout) else 0
+    ms = [int(x) for x in rd["mslot"]] + [int(rd["mslot4"])]
+    for a in range(5):
+        T[38 + a] = ms[a] if (a < r and ms[a] >= 0) else LT_EMPTY
+    npx = int(rd["n_pext"])
+    w = npx
+    for k in range(npx):
+        bit, vec = int(rd["pext"][k]["bit"]), int(rd["pext"][k]["vec"])
+        w |= bit << (8 + 6 * k)
+        T[44 + k] = word(0, vec)  # only the permuted half is non-zero
+    T[43] = w
+    return T
+
+
+def finish_lean(plan: "SweepPlan", n_total: int) -> None:
+    """Choose the kernel of every sweep and build what the lean kernel needs (tables for both directions, TMA boxes)."""
+    import os
+
+    cfg = plan.cfg
+    n = plan.n_qubits
+    ns = plan.n_sweeps
+    plan.tma = np.zeros(ns, dtype=TMA_DT)
+    plan.lean_tab_fwd = np.zeros((max(1, len(plan.rounds)), LT_STRIDE), dtype=np.uint32)
+    plan.lean_tab_bwd = np.zeros((max(1, len(plan.rounds)), LT_STRIDE), dtype=np.uint32)
+    plan.exec_mode = np.zeros(max(1, plan.n_exec_total), dtype=np.uint8)
+    allow = cfg.lean and os.environ.get("B200SV_LEAN", "1") != "0" and n_total == n
+    allow_tma = os.environ.get("B200SV_TMA", "1") != "0"
+    for si in range(ns):
+        sw = plan.sweeps[si]
+        m, r = int(sw["m"]), int(sw["r"])
+        mode = IO_GENERIC
+        if allow and int(sw["n_gen"]) == 0 and m == cfg.m and _lean_supported(cfg.c128, m, r, cfg.adjoint):
+            mode = IO_LEAN
+            box = tma_box(sw["tile_bits"][:m], n, cfg.c128) if allow_tma else None
+            if box is not None:
+                mode = IO_LEAN_TMA
+                plan.tma[si] = box[0]
+        sw["io_mode"] = mode
+        fx = int(sw["first_exec"])
+        plan.exec_mode[fx : fx + int(sw["n_exec"])] = mode
+        if mode == IO_GENERIC:
+            continue
+        fr, nr = int(sw["first_round"]), int(sw["n_rounds"])
+        plain_io = mode == IO_LEAN_TMA  # TMA writes / reads the tile un-swizzled
+        for k in range(nr):
+            rd = plan.rounds[fr + k]
+            plan.lean_tab_fwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, True, plain_io and k == 0, plain_io and k == nr - 1)
+            plan.lean_tab_bwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, False, plain_io and k == nr - 1, plain_io and k == 0)
 
 
 # ---- Pauli sums -----------------------------------------------------------------------------------

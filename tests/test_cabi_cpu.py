@@ -31,15 +31,17 @@ def test_every_declared_symbol_is_exported(lib: C.CDLL) -> None:
     assert declared == set(cabi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.b200sv_abi_version() == 1
+    assert lib.b200sv_abi_version() == 2
 
 
 def test_record_layouts_match_header() -> None:
     header = (ROOT / "include" / "b200sv.h").read_text()
-    for struct, dt in (("b200sv_gate", plan.GATE_DT), ("b200sv_round", plan.ROUND_DT), ("b200sv_sweep", plan.SWEEP_DT), ("b200sv_pterm", plan.PTERM_DT)):
+    for struct, dt in (("b200sv_gate", plan.GATE_DT), ("b200sv_round", plan.ROUND_DT), ("b200sv_sweep", plan.SWEEP_DT), ("b200sv_pterm", plan.PTERM_DT),
+                       ("b200sv_tma", plan.TMA_DT)):
         m = re.search(r"typedef struct %s \{\s*/\* (\d+) bytes" % struct, header)
         assert m and int(m.group(1)) == dt.itemsize, struct
-    assert C.sizeof(cabi.PlanStruct) == 56
+    assert C.sizeof(cabi.PlanStruct) == 88
+    assert int(re.search(r"#define B200SV_LT_STRIDE (\d+)", header).group(1)) == plan.LT_STRIDE
     from qadence_b200 import embedding
 
     fields = re.search(r"typedef struct b200sv_enode \{\s*int32_t ([^;]+);", header).group(1).split(",")

@@ -1,26 +1,61 @@
-"""One expectation+adjoint step of the bench workload (for ncu captures; prints nothing timed)."""
+#!/usr/bin/env python
+"""Two expectation+adjoint steps of cfg2 (hea(20, 8), batch 256, complex128) with nothing else on the device: the program
+the ncu launch list / full captures under profiles/ are taken from (`ncu ... python tools/profile_step.py`).
+Optional: --steps N, --dtype c64."""
+from __future__ import annotations
+
+import argparse
 import ctypes as C
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
 import torch
 
 from qadence_b200 import cabi, engine
 from qadence_b200.engine import _DT, _stream_ptr
 from qadence_b200.program import hea_program, total_magnetization
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-depth = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-dt = torch.complex128 if (len(sys.argv) <= 4 or sys.argv[4] == "c128") else torch.complex64
-dev = torch.device("cuda:0")
-prog = hea_program(n, depth)
-cp = engine.CompiledProgram(prog)
-cob = engine.CompiledObservable(total_magnetization(n))
-vals = {nm: (torch.rand(B, dtype=torch.float64, device=dev) * 6.28).requires_grad_(True) for nm in cp.names}
-for _ in range(2):
-    out = engine.expectation(cp, [cob], vals, dtype=dt, device=dev)
-    out.sum().backward()
-torch.cuda.synchronize()
-print("ok", out[:2, 0].tolist())
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--dtype", default="c128")
+    ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=256)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    dtype = torch.complex128 if a.dtype == "c128" else torch.complex64
+    lib = cabi.load()
+    prog = hea_program(a.n, a.depth)
+    cp = engine.CompiledProgram(prog)
+    cob = engine.CompiledObservable(total_magnetization(a.n))
+    seg = cp.segments[0]
+    fwd = cp.device_plan(seg, dtype, False, dev)
+    adj = cp.device_plan(seg, dtype, True, dev)
+    coef = cob.pauli.coef({}, dev)
+    g = torch.Generator().manual_seed(1234)
+    ptable = (2 * torch.pi * torch.rand(len(cp.names), a.batch, generator=g, dtype=torch.float64)).to(dev)
+    psi = torch.empty(a.batch, 1 << a.n, dtype=dtype, device=dev)
+    lam = torch.empty_like(psi)
+    grads = torch.zeros(len(cp.names), a.batch, dtype=torch.float64, device=dev)
+    ws_f = fwd.workspace(dtype, a.batch, False).data_ptr()
+    ws_a = adj.workspace(dtype, a.batch, True).data_ptr()
+    st = _stream_ptr(dev)
+    for _ in range(a.steps):
+        cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], a.n, a.batch, st), "init")
+        cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
+        e = engine.pauli_expectation(cob.pauli, coef, psi)
+        engine.pauli_apply(cob.pauli, coef, psi, out=lam)
+        grads.zero_()
+        cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0,
+                                           adj.n_sweeps, 0, ws_a, st), "adj")
+    torch.cuda.synchronize(dev)
+    print("E[0:3] =", e[:3].tolist(), " |grad| =", float(grads.abs().sum()), " psi[0,0] =", complex(psi[0, 0]))
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef B200SV_LEAN_STAGGER_DEFAULT
+#define B200SV_LEAN_STAGGER_DEFAULT 100
+#endif
 #ifndef B200SV_LEAN_NBUF_DEFAULT
 #define B200SV_LEAN_NBUF_DEFAULT 1
 #endif
@@ -281,6 +284,12 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (sms * occ_env < resident) resident = sms * occ_env;
   }
+  int n_sms = 0;
+  {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const long long total = ((long long)batch) << sw.n_outer;
   if (total <= 0) return B200SV_E_ARG;
   long long grid = total < resident ? total : resident;
@@ -302,6 +311,16 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
   a.tiles_per_cta = per_cta;
   a.nbuf = nbuf;
   a.dbg = dbg_flags;
+  a.n_sms = n_sms > 0 ? n_sms : 1;
+  {
+    // one share of a tile period: the FP64 work of a tile (6 / 18 instructions per amplitude and merged 2x2, 64 lanes per
+    // clock and SM at ~1.9 GHz, ~70 % pipe efficiency); B200SV_LEAN_STAGGER scales it in percent (0 = off)
+    const char* sg = getenv("B200SV_LEAN_STAGGER");
+    const double pct = sg ? atof(sg) : (double)B200SV_LEAN_STAGGER_DEFAULT;
+    const double cycles = (double)(1 << M) * (double)sw.n_exec * (ADJ ? 18.0 : 6.0) / 64.0 / 0.7;
+    const double ns = cycles / 1.9 * pct / 100.0;
+    a.stagger_ns = (grid > n_sms && ns > 0.0) ? (unsigned)(ns < 2.0e6 ? ns : 2.0e6) : 0u;
+  }
   CUtensorMap tm_psi{}, tm_lam{};
   if (tma) {
     if (!plan->tma_host) return B200SV_E_ARG;
@@ -532,11 +551,20 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
   const long long base = blk * (long long)(EXP_THREADS * EXP_PER_THREAD);
   double w0r = 0.0, w0i = 0.0;  // single-Z weight of this thread's k = 0 index
   if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
-#pragma unroll 1
+  // all of the thread's amplitudes are requested before the first one is used: the kernel is a pure stream (1·S bytes) and
+  // needs EXP_PER_THREAD independent 16-byte loads in flight per thread to fill the HBM pipe
+  c2 av[EXP_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < EXP_PER_THREAD; ++k) {
+    const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
+    av[k].x = 0; av[k].y = 0;
+    if (i < N) av[k] = __ldcs(p + i);
+  }
+#pragma unroll
   for (int k = 0; k < EXP_PER_THREAD; ++k) {
     const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
     if (i >= N) break;
-    const c2 a = p[i];
+    const c2 a = av[k];
     const unsigned long long gi = (unsigned long long)i | index_hi;
     double wr = w0r;             // diagonal weight (k only changes the bits above log2(EXP_THREADS))
     if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * EXP_THREADS, kr, ki); wr += kr - sz.c0r; }
@@ -578,12 +606,22 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
   const long long base = blk * (long long)(256 * 4);
   double w0r = 0.0, w0i = 0.0;
   if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
-#pragma unroll 1
+  c2 av[4], zv[4];  // loads first (memory-level parallelism), see pauli_expect_kernel
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + (long long)k * 256 + threadIdx.x;
+    av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0;
+    if (i < N) {
+      av[k] = p[i];
+      if (acc != nullptr) zv[k] = acc[(b << n) + i];
+    }
+  }
+#pragma unroll
   for (int k = 0; k < 4; ++k) {
     const long long i = base + (long long)k * 256 + threadIdx.x;
     if (i >= N) break;
     const unsigned long long gi = (unsigned long long)i | index_hi;
-    const c2 a = p[i];
+    const c2 a = av[k];
     double wr = w0r, wi = w0i, sr = 0.0, si = 0.0;
     if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * 256, kr, ki); wr += kr - sz.c0r; wi += ki - sz.c0i; }
     for (int t = 0; t < T; ++t) {
@@ -601,7 +639,7 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
     si += wr * (double)a.y + wi * (double)a.x;
     double rr = ar * sr - ai * si, ri = ar * si + ai * sr;
     if (acc != nullptr) {
-      const c2 z = acc[(b << n) + i];
+      const c2 z = zv[k];
       rr += br * (double)z.x - bi * (double)z.y;
       ri += br * (double)z.y + bi * (double)z.x;
     }

@@ -57,6 +57,8 @@ template <typename real> struct LeanArgs {
   long long total_tiles, tiles_per_cta;
   int nbuf;
   int dbg;  // timing experiments only: 1 = skip the 2x2 math, 2 = skip the rounds (results are wrong in both)
+  unsigned stagger_ns;  // start-up delay per co-resident CTA slot (see the kernel prologue)
+  int n_sms;
   TmaGeom tg;
 };
 
@@ -369,6 +371,23 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
     }
   };
 
+  // De-phase the CTAs that share an SM.  All persistent CTAs start together and do identical work, so without this they
+  // stay in lockstep: every CTA of the device waits for HBM at the same time (FP64 pipe idle), then they all compute
+  // (HBM idle) — the sweep takes T_stream + T_compute instead of max(...).  The k-th CTA on an SM (blocks are dealt to the
+  // SMs round-robin, so k = blockIdx / #SMs) starts k shares of a tile period late; from then on one CTA's memory phase
+  // overlaps the others' compute phases.
+  if (A.stagger_ns != 0u && (use_tma ? tid == 0 : true)) {
+    const unsigned slot = blockIdx.x / (unsigned)A.n_sms;
+    if (slot != 0u) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      const unsigned long long wait_ns = (unsigned long long)slot * A.stagger_ns;
+      do {
+        __nanosleep(256);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (t1 - t0 < wait_ns);
+    }
+  }
   long long cur_b = -1;
   unsigned phase0 = 0, phase1 = 0;
   if (use_tma) { if (tid == 0) issue_load_tma(tile_first, 0); }

@@ -428,4 +428,5 @@ def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, sto
             scalar = frozenset(nm for nm in prog.names if nm in prog.slot_symbols and not (prog.slot_symbols[nm] & feats))
         return ParamTable(prog.names, table, extras, input_device, nograd, scalar)
 
+    fn.embed_program = prog  # type: ignore[attr-defined]  # introspection (tests rebuild the table with the CPU restatement)
     return fn

@@ -65,7 +65,7 @@ def test_lean_forward_instances(inst, io: str, monkeypatch) -> None:
     dtype = torch.complex128 if c128 else torch.complex64
     monkeypatch.setenv("B200SV_TMA", "0" if io == "gather" else "1")
     monkeypatch.setenv("B200SV_LEAN_NBUF", "2" if io == "tma2buf" else "1")
-    n, B = m + 2, 3
+    n, B = m + 1, 3  # one outer bit: every tile has at most two runs, i.e. is a TMA box
     rng = np.random.default_rng(31 * m + r + len(io))
     prog, names = lean_random_program(n, 90, rng, unitary=not c128)  # complex64: keep the norm O(1)
     values = {nm: torch.tensor(rng.uniform(0.2, 2.5, size=B)) for nm in names}
@@ -74,10 +74,8 @@ def test_lean_forward_instances(inst, io: str, monkeypatch) -> None:
     got, plan = _forward(prog, values, psi0, TileConfig(m=m, r=r, low=2, fold=3 if c128 else 4), dtype, n, B)
     modes = [int(s["io_mode"]) for s in plan.sweeps]
     assert all(md != P.IO_GENERIC for md in modes), modes
-    if io == "gather":
-        assert all(md == P.IO_LEAN for md in modes)
-    else:
-        assert any(md == P.IO_LEAN_TMA for md in modes), modes
+    boxes = [P.tma_box(sw["tile_bits"][:m], n, c128) is not None for sw in plan.sweeps]
+    assert modes == [(P.IO_LEAN_TMA if (bx and io != "gather") else P.IO_LEAN) for bx in boxes], (modes, boxes)
     scale = max(1.0, want.abs().max().item())
     assert (got - want).abs().max().item() <= TOL[dtype] * scale
 

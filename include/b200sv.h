@@ -142,7 +142,8 @@ enum { B200SV_IO_GENERIC = 0, B200SV_IO_LEAN = 1, B200SV_IO_LEAN_TMA = 2 };
  * (box = size), a gap dimension one element at a time: its coordinate is bits [src[d], src[d] + nbits[d]) of the tile
  * counter.  The last dimension is the remaining high index bits times the batch. */
 typedef struct b200sv_tma {  /* 24 bytes */
-  int32_t rank;
+  int32_t rank;       /* bits 0..7: rank; bit 8: CU_TENSOR_MAP_SWIZZLE_128B (the lean tables then address the staged tile
+                         with 16-byte chunk bits 4..6 XOR-ed with address bits 7..9) */
   uint8_t start[5], nbits[5], is_tile[5], src[5];
 } b200sv_tma;
 

@@ -27,7 +27,8 @@ known-answer vector of `/root/reference/tests/backends/pyq/test_quantum_pyq.py`
 (:180-209, :279-316, :394-431, :518-545, :620-632) and `tests/backends/test_endianness.py:113-167`
 (committed as `tests/golden/kat_reference.json`), and — whenever `/root/reference` is importable —
 against qadence's own dense `block_to_tensor` on every gate family / hea / qft / feature map /
-HamEvo (`tests/test_convert_vs_reference.py`, mirroring `tests/qadence/test_matrices.py:582-771`).
+HamEvo (`tests/test_qadence_adapter_cpu.py::test_converted_program_equals_dense_oracle` and the fixture generator
+`tests/golden/make_golden.py`, both mirroring `tests/qadence/test_matrices.py:582-771`).
 
 It consumes the same flat IR (`qadence_b200.program`) as the CUDA engine so that golden fixtures
 generated here travel to the GPU box.

@@ -1,6 +1,7 @@
 // b200sv C-ABI implementation (see include/b200sv.h).  sm_100a only; no CPU fallback.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -230,7 +231,8 @@ TmapEncodeFn tmap_encode_fn() {
 int make_tensor_map(CUtensorMap* out, void* state, int amp_bytes, int64_t batch, const b200sv_tma& tm) {
   TmapEncodeFn enc = tmap_encode_fn();
   if (!enc) return B200SV_E_UNSUPPORTED;
-  const int rank = tm.rank;
+  const int rank = tm.rank & 0xff;
+  const bool swizzle = (tm.rank & 0x100) != 0;
   if (rank < 2 || rank > 5 || tm.start[0] != 0 || !tm.is_tile[0]) return B200SV_E_ARG;
   const int ebit = amp_bytes == 16 ? 1 : 0;
   cuuint64_t size[5], stride[5];
@@ -248,7 +250,8 @@ int make_tensor_map(CUtensorMap* out, void* state, int amp_bytes, int64_t batch,
     }
   }
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)rank, state, size, stride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : B200SV_E_ARG;
 }
@@ -327,12 +330,42 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
     const b200sv_tma& tm = plan->tma_host[s];
     if (int rc = make_tensor_map(&tm_psi, psi, (int)sizeof(c2), batch, tm)) return rc;
     if (ADJ) { if (int rc = make_tensor_map(&tm_lam, lam, (int)sizeof(c2), batch, tm)) return rc; }
-    a.tg.rank = tm.rank;
-    a.tg.top_shift = tm.nbits[tm.rank - 1];
+    a.tg.rank = tm.rank & 0xff;
+    a.tg.top_shift = tm.nbits[a.tg.rank - 1];
     for (int d = 0; d < 5; ++d) { a.tg.src[d] = tm.src[d]; a.tg.nbits[d] = tm.nbits[d]; a.tg.is_tile[d] = tm.is_tile[d]; }
+  }
+  // diagnostics: B200SV_LEAN_TRACE=<file prefix> records per-tile globaltimer stamps of the first 64 tiles of every CTA
+  // (tile landed / rounds done / store+next load issued, SM id) and writes them to <prefix>.<sweep>.<fwd|adj>.bin.  This
+  // path synchronises and allocates: never set it outside a debugging session.
+  const char* trace_prefix = getenv("B200SV_LEAN_TRACE");
+  unsigned long long* d_trace = nullptr;
+  const int trace_tiles = 64;
+  if (trace_prefix && *trace_prefix) {
+    CK(cudaMalloc(&d_trace, (size_t)grid * trace_tiles * 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_trace, 0, (size_t)grid * trace_tiles * 4 * sizeof(unsigned long long), st));
+    a.trace = d_trace;
+    a.trace_tiles = trace_tiles;
   }
   kern<<<(unsigned)grid, NT, smem, st>>>(a, sw, tm_psi, tm_lam);
   LAUNCH_CK();
+  if (d_trace) {
+    CK(cudaStreamSynchronize(st));
+    const size_t nwords = (size_t)grid * trace_tiles * 4;
+    unsigned long long* h = (unsigned long long*)malloc(nwords * sizeof(unsigned long long));
+    if (h) {
+      CK(cudaMemcpy(h, d_trace, nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      char path[512];
+      snprintf(path, sizeof(path), "%s.%d.%s.bin", trace_prefix, s, ADJ ? "adj" : "fwd");
+      if (FILE* f = fopen(path, "wb")) {
+        const long long hdr[4] = {grid, trace_tiles, per_cta, (long long)NT};
+        fwrite(hdr, sizeof(hdr), 1, f);
+        fwrite(h, sizeof(unsigned long long), nwords, f);
+        fclose(f);
+      }
+      free(h);
+    }
+    CK(cudaFree(d_trace));
+  }
   return 0;
 }
 

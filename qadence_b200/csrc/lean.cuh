@@ -59,6 +59,8 @@ template <typename real> struct LeanArgs {
   int dbg;  // timing experiments only: 1 = skip the 2x2 math, 2 = skip the rounds (results are wrong in both)
   unsigned stagger_ns;  // start-up delay per co-resident CTA slot (see the kernel prologue)
   int n_sms;
+  unsigned long long* trace;  // diagnostics (B200SV_LEAN_TRACE): [cta][trace_tiles][4] globaltimer stamps, else nullptr
+  int trace_tiles;
   TmaGeom tg;
 };
 
@@ -197,18 +199,31 @@ template <typename real, int R> struct LeanRegs {
   }
   // four moments Im<l|P|p>, P = I, X, Y, Z on register bit A (pure FMA chains, 12 per amplitude pair)
   template <int A> static __device__ __forceinline__ void moments(const c2 (&p)[NV], const c2 (&l)[NV], double (&mo)[4]) {
-    real s00 = 0, s11 = 0, x_im = 0, y_re = 0;
+    // two independent accumulator sets (even / odd pairs): 8 FMA chains in flight instead of 4 — at 4 warps per scheduler
+    // the FP64 result latency is otherwise exposed (ncu: "wait" stalls on these lines)
+    real s00 = 0, s11 = 0, x_im = 0, y_re = 0, s00b = 0, s11b = 0, x_imb = 0, y_reb = 0;
+    int pair = 0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       if (j & (1 << A)) continue;
       const int k = j | (1 << A);
-      s00 = fma(l[j].x, p[j].y, s00); s00 = fma(-l[j].y, p[j].x, s00);
-      s11 = fma(l[k].x, p[k].y, s11); s11 = fma(-l[k].y, p[k].x, s11);
-      x_im = fma(l[j].x, p[k].y, x_im); x_im = fma(-l[j].y, p[k].x, x_im);
-      x_im = fma(l[k].x, p[j].y, x_im); x_im = fma(-l[k].y, p[j].x, x_im);
-      y_re = fma(l[k].x, p[j].x, y_re); y_re = fma(l[k].y, p[j].y, y_re);
-      y_re = fma(-l[j].x, p[k].x, y_re); y_re = fma(-l[j].y, p[k].y, y_re);
+      if ((pair++ & 1) == 0) {
+        s00 = fma(l[j].x, p[j].y, s00); s00 = fma(-l[j].y, p[j].x, s00);
+        s11 = fma(l[k].x, p[k].y, s11); s11 = fma(-l[k].y, p[k].x, s11);
+        x_im = fma(l[j].x, p[k].y, x_im); x_im = fma(-l[j].y, p[k].x, x_im);
+        x_im = fma(l[k].x, p[j].y, x_im); x_im = fma(-l[k].y, p[j].x, x_im);
+        y_re = fma(l[k].x, p[j].x, y_re); y_re = fma(l[k].y, p[j].y, y_re);
+        y_re = fma(-l[j].x, p[k].x, y_re); y_re = fma(-l[j].y, p[k].y, y_re);
+      } else {
+        s00b = fma(l[j].x, p[j].y, s00b); s00b = fma(-l[j].y, p[j].x, s00b);
+        s11b = fma(l[k].x, p[k].y, s11b); s11b = fma(-l[k].y, p[k].x, s11b);
+        x_imb = fma(l[j].x, p[k].y, x_imb); x_imb = fma(-l[j].y, p[k].x, x_imb);
+        x_imb = fma(l[k].x, p[j].y, x_imb); x_imb = fma(-l[k].y, p[j].x, x_imb);
+        y_reb = fma(l[k].x, p[j].x, y_reb); y_reb = fma(l[k].y, p[j].y, y_reb);
+        y_reb = fma(-l[j].x, p[k].x, y_reb); y_reb = fma(-l[j].y, p[k].y, y_reb);
+      }
     }
+    s00 += s00b; s11 += s11b; x_im += x_imb; y_re += y_reb;
     mo[0] = (double)s00 + (double)s11; mo[1] = (double)x_im; mo[2] = (double)y_re; mo[3] = (double)s00 - (double)s11;
   }
 };
@@ -433,6 +448,15 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
       cp_async_wait<0>();
     }
     __syncthreads();  // tile landed (all threads' gathers), gates / ext visible
+    const long long tl = t - tile_first;
+    const bool tracing = A.trace != nullptr && tid == 0 && tl < A.trace_tiles;
+    unsigned long long* trow = tracing ? A.trace + ((long long)blockIdx.x * A.trace_tiles + tl) * 4 : nullptr;
+    if (tracing) {
+      unsigned long long now; unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trow[0] = now; trow[3] = smid;
+    }
 
     const c2 sc = sscal_s[0];
     const bool scale = !(sc.x == (real)1 && sc.y == (real)0);
@@ -529,6 +553,7 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
       __syncthreads();
     }
 
+    if (tracing) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trow[1] = now; }
     // ---- write the tile back ----
     if (use_tma) {
       if (tid == 0) {
@@ -541,6 +566,7 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
           bulk_wait_read0();
           issue_load_tma(t + 1, 0);
         }
+        if (tracing) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trow[2] = now; }
       }
     } else {
       const long long state_off = b << A.n;

@@ -55,6 +55,8 @@ assert TMA_DT.itemsize == 24
 IO_GENERIC, IO_LEAN, IO_LEAN_TMA = 0, 1, 2
 LT_STRIDE = 48
 LT_EMPTY = 0xFFFF
+TMA_SWIZZLE_FLAG = 0x100  # b200sv_tma.rank bit 8: the tensor map uses CU_TENSOR_MAP_SWIZZLE_128B
+TMA_SWIZZLE_DEFAULT = "0"
 
 GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
 GF_GRAD = 1
@@ -703,7 +705,7 @@ def _lean_supported(c128: bool, m: int, r: int, adjoint: bool) -> bool:
         return False
 
 
-def tma_box(tile_bits: Sequence[int], n: int, c128: bool) -> np.ndarray | None:
+def tma_box(tile_bits: Sequence[int], n: int, c128: bool, swizzle: bool = False) -> np.ndarray | None:
     """The tile as a box of the [batch][2^n] state seen as a tensor of 8-byte elements (see `b200sv_tma`), or None when it
     needs more than 5 dimensions.  Runs of consecutive tile bits become tile dimensions (at most 256 elements each, so long
     runs are split), the gaps between them dimensions walked one element at a time by the tile counter."""
@@ -726,7 +728,10 @@ def tma_box(tile_bits: Sequence[int], n: int, c128: bool) -> np.ndarray | None:
             src += start - pos
         st, rem = start, length
         while rem > 0:
-            k = min(rem, 8 - (1 if (c128 and st == 0) else 0))
+            cap = 8 - (1 if (c128 and st == 0) else 0)
+            if swizzle and st == 0:
+                cap = 3 if c128 else 4  # SWIZZLE_128B: the innermost box row is at most 128 bytes
+            k = min(rem, cap)
             dims.append((st, k, 1, 0))
             st += k
             rem -= k
@@ -741,13 +746,22 @@ def tma_box(tile_bits: Sequence[int], n: int, c128: bool) -> np.ndarray | None:
     return rec
 
 
+def _swz_a(e: int, c128: bool) -> int:
+    """Layout a TMA load with CU_TENSOR_MAP_SWIZZLE_128B leaves in shared memory: dense box order, then the 16-byte chunk
+    index (byte-address bits 4..6) XOR-ed with address bits 7..9 (measured: tools/ubench/tma_probe.cu).  In amplitude
+    units: complex128 (16 B) bits 0..2 ^= bits 3..5; complex64 (8 B) bits 1..3 ^= bits 4..6."""
+    return e ^ ((e >> 3) & 7) if c128 else e ^ (((e >> 4) & 7) << 1)
+
+
 def _swz_b(e: int, c128: bool) -> int:
     """Bank swizzle of the in-tile layout between rounds (`swz<real>` in sweep.cuh); GF(2)-linear."""
     return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9)) & 7) if c128 else e ^ (((e >> 4) ^ (e >> 8)) & 15)
 
 
-def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_layout: bool, store_plain_layout: bool) -> np.ndarray:
-    """One round's B200SV_LT_STRIDE words for one direction (layout documented in include/b200sv.h)."""
+def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_layout: bool, store_plain_layout: bool,
+                      tma_swizzle: bool = False) -> np.ndarray:
+    """One round's B200SV_LT_STRIDE words for one direction (layout documented in include/b200sv.h).  `*_plain_layout`:
+    that side of the round faces the TMA-written / TMA-read tile (box order, hardware-swizzled if `tma_swizzle`)."""
     shift = 4 if c128 else 3
     perm = bool(int(rd["flags"]) & RF_PERM)
     pcol = [int(x) for x in rd["pcol"][:m]]
@@ -755,7 +769,9 @@ def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_
     thr = [int(x) for x in rd["thrpos"][: m - r]]
 
     def lay(v: int, plain_layout: bool) -> int:
-        return (v if plain_layout else _swz_b(v, c128)) << shift
+        if plain_layout:
+            return (_swz_a(v, c128) if tma_swizzle else v) << shift
+        return _swz_b(v, c128) << shift
 
     def word(plain_v: int, perm_v: int) -> int:
         lv, sv = (plain_v, perm_v) if forward else (perm_v, plain_v)
@@ -804,16 +820,19 @@ def finish_lean(plan: "SweepPlan", n_total: int) -> None:
     plan.exec_mode = np.zeros(max(1, plan.n_exec_total), dtype=np.uint8)
     allow = cfg.lean and os.environ.get("B200SV_LEAN", "1") != "0" and n_total == n
     allow_tma = os.environ.get("B200SV_TMA", "1") != "0"
+    tma_swizzle = os.environ.get("B200SV_TMA_SWIZZLE", TMA_SWIZZLE_DEFAULT) != "0"
     for si in range(ns):
         sw = plan.sweeps[si]
         m, r = int(sw["m"]), int(sw["r"])
         mode = IO_GENERIC
         if allow and int(sw["n_gen"]) == 0 and m == cfg.m and _lean_supported(cfg.c128, m, r, cfg.adjoint):
             mode = IO_LEAN
-            box = tma_box(sw["tile_bits"][:m], n, cfg.c128) if allow_tma else None
+            box = tma_box(sw["tile_bits"][:m], n, cfg.c128, tma_swizzle) if allow_tma else None
             if box is not None:
                 mode = IO_LEAN_TMA
                 plan.tma[si] = box[0]
+                if tma_swizzle:
+                    plan.tma[si]["rank"] |= TMA_SWIZZLE_FLAG
         sw["io_mode"] = mode
         fx = int(sw["first_exec"])
         plan.exec_mode[fx : fx + int(sw["n_exec"])] = mode
@@ -823,8 +842,9 @@ def finish_lean(plan: "SweepPlan", n_total: int) -> None:
         plain_io = mode == IO_LEAN_TMA  # TMA writes / reads the tile un-swizzled
         for k in range(nr):
             rd = plan.rounds[fr + k]
-            plan.lean_tab_fwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, True, plain_io and k == 0, plain_io and k == nr - 1)
-            plan.lean_tab_bwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, False, plain_io and k == nr - 1, plain_io and k == 0)
+            sz = plain_io and tma_swizzle
+            plan.lean_tab_fwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, True, plain_io and k == 0, plain_io and k == nr - 1, sz)
+            plan.lean_tab_bwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, False, plain_io and k == nr - 1, plain_io and k == 0, sz)
 
 
 # ---- Pauli sums -----------------------------------------------------------------------------------

@@ -69,7 +69,15 @@ class DifferentiableBackend(DifferentiableBackendInterface):
                 backend=self.backend, circuit=circuit, observable=observable, param_values=param_values, state=state,
                 measurement=measurement, noise=noise, mitigation=mitigation, endianness=endianness,
             )
-            return partial(de.psr, psr_fn=general_psr, **self.psr_args)()
+            out = partial(de.psr, psr_fn=general_psr, **self.psr_args)()
+            # PSR hands the backend plain dicts of (shifted) device rows of the embedding table, so the backend no longer
+            # sees where the user's inputs lived: restore the "results on the input device" contract here
+            from qadence_b200.embedding import ParamTable
+
+            if (isinstance(out, Tensor) and isinstance(param_values, ParamTable) and param_values.input_device is not None
+                    and getattr(self.backend.config, "results_on_input_device", False) and out.device != param_values.input_device):
+                out = out.to(param_values.input_device)
+            return out
         # AD and ADJOINT: the backend's expectation is itself differentiable (adjoint method)
         return self.backend.expectation(
             circuit=circuit, observable=observable, param_values=param_values, state=state, noise=noise,

@@ -84,7 +84,9 @@ def emulate_lean_sweep(plan: P.SweepPlan, si: int, psi: np.ndarray, lam: np.ndar
     lay = e_idx if plain_io else np.array([P._swz_b(int(e), c128) for e in e_idx])
     if plain_io:  # the TMA box must enumerate the tile in ascending tile-bit order and walk the outer bits with the counter
         tm = plan.tma[si]
-        assert int(tm["rank"]) >= 2
+        assert int(tm["rank"]) & 0xFF >= 2
+        if int(tm["rank"]) & P.TMA_SWIZZLE_FLAG:  # hardware swizzle of the TMA-written tile
+            lay = np.array([P._swz_a(int(e), c128) for e in e_idx])
     tid = np.arange(NT)
     jj = np.arange(NV)
     for b in range(B):
@@ -168,7 +170,7 @@ def emulate_lean_sweep(plan: P.SweepPlan, si: int, psi: np.ndarray, lam: np.ndar
 def _check_tma_coords(tm, c: int, b: int, base: int, n: int, tile_bits) -> None:
     """The box origin the kernel computes from (tile counter, batch element) must be the tile's base offset, and the box
     must enumerate exactly the tile bits in ascending order."""
-    rank = int(tm["rank"])
+    rank = int(tm["rank"]) & 0xFF
     off = 0
     enum_bits = []
     for d in range(rank):

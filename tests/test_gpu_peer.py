@@ -47,6 +47,42 @@ def test_single_rank_peer_table_equals_plain_path() -> None:
         sim.close()
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_rank_bit_addressing_with_peer_buffers_on_one_device(world: int) -> None:
+    """`b200sv_apply_plan_peers` with `world` separately allocated shards that all live on THIS device: the rank-bit
+    addressing (index bits >= n_local select the buffer), the per-rank tile slices and the straddling sweeps are
+    exercised on a single-GPU box.  The "ranks" take turns on one stream, sweep by sweep (stream order is the barrier)."""
+    import ctypes as C
+
+    from qadence_b200 import cabi, engine
+    from qadence_b200.engine import DevicePlan, _DT, _stream_ptr
+    from qadence_b200.plan import TileConfig, build_plan
+
+    n = 17
+    g = world.bit_length() - 1
+    n_local = n - g
+    prog = _program(n)
+    gen = torch.Generator().manual_seed(5)
+    values = {nm: 6.28 * torch.rand(1, generator=gen, dtype=torch.float64) for nm in prog.param_names}
+    dev = torch.device("cuda:0")
+    want = engine.run(engine.CompiledProgram(prog), values, device=dev)
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    dp = DevicePlan(build_plan(list(prog.ops), n, slot_of, TileConfig.default(True, False), packer="greedy"), dev)
+    shards = [torch.zeros(1, 1 << n_local, dtype=torch.complex128, device=dev) for _ in range(world)]
+    shards[0][0, 0] = 1.0
+    ptrs = (C.c_void_p * world)(*[s.data_ptr() for s in shards])
+    tab = engine.pack_params(prog.param_names, values, 1, dev)
+    ws = dp.workspace(torch.complex128, 1, False)
+    lib = cabi.load()
+    for s in range(dp.n_sweeps):
+        for rank in range(world):
+            rc = lib.b200sv_apply_plan_peers(ptrs, world, rank, _DT[torch.complex128], n, tab.data_ptr(), C.byref(dp.struct), s, s + 1,
+                                             ws.data_ptr(), _stream_ptr(dev))
+            assert rc == 0
+    got = torch.cat([s.reshape(-1) for s in shards]).reshape(1, -1)
+    assert (got - want).abs().max().item() < 1e-12
+
+
 def test_traffic_model_counts_global_bits() -> None:
     from qadence_b200.dist import peer_traffic
     from qadence_b200.plan import TileConfig, build_plan

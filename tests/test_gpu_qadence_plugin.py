@@ -115,7 +115,7 @@ def test_backend_factory_call_sequence() -> None:
     bk = backend_factory("b200sv", diff_mode="adjoint")
     conv = bk.convert(circ, total_magnetization(n))
     x = torch.linspace(-0.5, 0.5, 3, dtype=torch.float64)
-    params = {k: (v.clone().requires_grad_(True) if v.requires_grad else v) for k, v in conv.params.items()}
+    params = {k: (v.detach().clone().requires_grad_(True) if v.requires_grad else v) for k, v in conv.params.items()}
     e = bk.expectation(conv.circuit, conv.observable, conv.embedding_fn(params, {"x": x}))
     assert e.shape == (3, 1)
     e.sum().backward()

@@ -5,12 +5,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#ifndef B200SV_LEAN_STAGGER_DEFAULT
-#define B200SV_LEAN_STAGGER_DEFAULT 100
-#endif
-#ifndef B200SV_LEAN_NBUF_DEFAULT
-#define B200SV_LEAN_NBUF_DEFAULT 1
-#endif
 #ifndef B200SV_PERSISTENT_DEFAULT
 #define B200SV_PERSISTENT_DEFAULT 0
 #endif
@@ -46,6 +40,7 @@ template <typename real> struct Workspace {
   double* mom;                // adjoint: [n_exec_total][batch][4]
   LeanGate<real>* ltab;       // lean sweeps: [batch][n_exec_total]
   typename C2<real>::type* sscal;  // lean sweeps: [n_sweeps][batch]
+  unsigned* tile_counters;    // lean sweeps: [n_sweeps] next unclaimed tile (dynamic scheduling)
 };
 
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -62,6 +57,8 @@ Workspace<real> carve_workspace(void* ws, const b200sv_plan* plan, int64_t batch
   w.ltab = reinterpret_cast<LeanGate<real>*>(p);
   p += align256(ne * sizeof(LeanGate<real>));
   w.sscal = reinterpret_cast<typename C2<real>::type*>(p);
+  p += align256((size_t)plan->n_sweeps * (size_t)batch * 2 * sizeof(real));
+  w.tile_counters = reinterpret_cast<unsigned*>(p);
   return w;
 }
 
@@ -70,6 +67,7 @@ size_t workspace_bytes(const b200sv_plan* plan, int64_t batch, bool /*adjoint*/)
   const size_t ne = (size_t)plan->n_exec_total * (size_t)batch;
   size_t bytes = align256(ne * sizeof(ExecGate<real>)) + align256(ne * 4 * sizeof(double)) + align256(ne * sizeof(LeanGate<real>));
   bytes += align256((size_t)plan->n_sweeps * (size_t)batch * 2 * sizeof(real));
+  bytes += align256((size_t)plan->n_sweeps * sizeof(unsigned));
   return bytes + 256;
 }
 
@@ -268,13 +266,10 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
                 uint64_t index_hi, cudaStream_t st) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
-  const char* nbuf_s = getenv("B200SV_LEAN_NBUF");  // read per launch: tests switch it
-  const int nbuf_env = nbuf_s ? atoi(nbuf_s) : B200SV_LEAN_NBUF_DEFAULT;
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   static const int occ_env = [] { const char* e = getenv("B200SV_LEAN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const bool tma = sw.io_mode == B200SV_IO_LEAN_TMA;
-  const int nbuf = (tma && nbuf_env == 2) ? 2 : 1;
-  const size_t smem = lean_smem_bytes<real, R, M, ADJ>(sw.n_rounds, sw.n_exec, nbuf);
+  const size_t smem = lean_smem_bytes<real, R, M, ADJ>(sw.n_rounds, sw.n_exec);
   if (smem > 227 * 1024) return B200SV_E_UNSUPPORTED;
   auto kern = lean_sweep_kernel<real, R, M, ADJ>;
   static DeviceLaunchState lstate;
@@ -287,17 +282,16 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (sms * occ_env < resident) resident = sms * occ_env;
   }
-  int n_sms = 0;
-  {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   const long long total = ((long long)batch) << sw.n_outer;
-  if (total <= 0) return B200SV_E_ARG;
-  long long grid = total < resident ? total : resident;
-  const long long per_cta = (total + grid - 1) / grid;
-  grid = (total + per_cta - 1) / per_cta;
+  if (total <= 0 || total > 0x7fffffffll) return B200SV_E_ARG;
+  const long long grid = total < resident ? total : resident;
+  // chunks of consecutive tiles: small, so that the tail (the last chunk of the slowest CTA) stays short; the price is a
+  // reload of the ~2 KB gate table and a flush of the moment partials whenever a chunk starts in another batch element
+  static const int chunk_env = [] { const char* e = getenv("B200SV_LEAN_CHUNK"); return e ? atoi(e) : 0; }();
+  long long chunk = chunk_env > 0 ? chunk_env : 4;
+  if (chunk > total / grid) chunk = total / grid;
+  if (chunk < 1) chunk = 1;
+  const long long per_cta = (total + grid - 1) / grid;  // (diagnostics header only)
 
   LeanArgs<real> a{};
   a.psi = (c2*)psi;
@@ -311,19 +305,9 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
   a.batch = batch;
   a.index_hi = index_hi;
   a.total_tiles = total;
-  a.tiles_per_cta = per_cta;
-  a.nbuf = nbuf;
+  a.tile_counter = ws.tile_counters + s;
+  a.chunk = (int)chunk;
   a.dbg = dbg_flags;
-  a.n_sms = n_sms > 0 ? n_sms : 1;
-  {
-    // one share of a tile period: the FP64 work of a tile (6 / 18 instructions per amplitude and merged 2x2, 64 lanes per
-    // clock and SM at ~1.9 GHz, ~70 % pipe efficiency); B200SV_LEAN_STAGGER scales it in percent (0 = off)
-    const char* sg = getenv("B200SV_LEAN_STAGGER");
-    const double pct = sg ? atof(sg) : (double)B200SV_LEAN_STAGGER_DEFAULT;
-    const double cycles = (double)(1 << M) * (double)sw.n_exec * (ADJ ? 18.0 : 6.0) / 64.0 / 0.7;
-    const double ns = cycles / 1.9 * pct / 100.0;
-    a.stagger_ns = (grid > n_sms && ns > 0.0) ? (unsigned)(ns < 2.0e6 ? ns : 2.0e6) : 0u;
-  }
   CUtensorMap tm_psi{}, tm_lam{};
   if (tma) {
     if (!plan->tma_host) return B200SV_E_ARG;
@@ -447,8 +431,8 @@ int run_plan(void* psi, void* lam, int n, int64_t batch, const double* params, d
   if (any_lean) {
     const long long nt = (long long)(last - first) * batch;
     resolve_lean_kernel<real><<<(unsigned)((nt + 63) / 64), 64, 0, st>>>(plan->sweeps, plan->rounds, plan->gates, plan->exec_leader,
-                                                                         params, plan->consts, ws.ltab, ws.sscal, first, last - first,
-                                                                         plan->n_exec_total, (long long)batch, ADJ ? -1 : +1);
+                                                                         params, plan->consts, ws.ltab, ws.sscal, ws.tile_counters, first,
+                                                                         last - first, plan->n_exec_total, (long long)batch, ADJ ? -1 : +1);
     LAUNCH_CK();
   }
   if (ADJ && x_count > 0) CK(cudaMemsetAsync(ws.mom + (size_t)x_first * batch * 4, 0, (size_t)x_count * batch * 4 * sizeof(double), st));

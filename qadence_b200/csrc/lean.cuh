@@ -6,7 +6,9 @@
 //    that describes the tile as a <= 5-D box of the [batch][2^n] state (low run x window x ...), completion on an
 //    mbarrier; no per-element address arithmetic, no LDGSTS issue slots.  Tiles that are not such a box fall back to
 //    cp.async gathers inside the same kernel.
-//  * persistent CTAs: index tables are built ONCE on the host (plan.py: `lean tables`) and copied once per CTA.
+//  * persistent CTAs that claim chunks of tiles from a device counter (dynamic scheduling: the warp schedulers favour the
+//    older CTAs of an SM, a static split leaves the young ones alone at the end); index tables are built ONCE on the host
+//    (plan.py: `lean tables`) and copied once per CTA.
 //  * normalised 2x2:  U = nu * [[1, b], [g, d]] after moving the largest entry to position (0,0) by flipping the pair on
 //    the load side (column flip) and / or the store side (row flip) — both are address XORs.  Applying the normalised
 //    matrix costs 12 FP64 instructions per amplitude pair instead of 16; the scalars nu of a sweep are multiplied
@@ -54,11 +56,10 @@ template <typename real> struct LeanArgs {
   int n_exec_total;
   long long batch;
   unsigned long long index_hi;
-  long long total_tiles, tiles_per_cta;
-  int nbuf;
+  long long total_tiles;
+  unsigned* tile_counter;  // device counter of this launch (zeroed beforehand): next unclaimed tile
+  int chunk;               // consecutive tiles claimed at once (keeps a CTA on one batch element)
   int dbg;  // timing experiments only: 1 = skip the 2x2 math, 2 = skip the rounds (results are wrong in both)
-  unsigned stagger_ns;  // start-up delay per co-resident CTA slot (see the kernel prologue)
-  int n_sms;
   unsigned long long* trace;  // diagnostics (B200SV_LEAN_TRACE): [cta][trace_tiles][4] globaltimer stamps, else nullptr
   int trace_tiles;
   TmaGeom tg;
@@ -258,14 +259,60 @@ template <typename real, int R, bool ADJ> __host__ __device__ inline size_t lean
   s += 128 * sizeof(unsigned long long);
   return (s + 15) & ~(size_t)15;
 }
-template <typename real, int R, int M, bool ADJ> inline size_t lean_smem_bytes(int n_rounds, int n_exec, int nbuf) {
+template <typename real, int R, int M, bool ADJ> inline size_t lean_smem_bytes(int n_rounds, int n_exec) {
   const size_t tile_bytes = ((size_t)1 << M) * 2 * sizeof(real);
   const size_t tables = lean_table_bytes<real, R, ADJ>(n_rounds, n_exec, 1 << (M - R));
   // buffers are aligned to tile_bytes inside the window: one tile of slack, split before / after the buffers; the tables
   // go into whichever part holds them (the kernel decides from the actual window address)
   size_t slack = tile_bytes;
   while (slack / 2 < tables && slack < 4 * tile_bytes) slack += tile_bytes;
-  return (size_t)nbuf * (ADJ ? 2 : 1) * tile_bytes + slack;
+  return (size_t)(ADJ ? 2 : 1) * tile_bytes + slack;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp reduction of the 4 moments of up to R slots at once (transposed butterfly over 4*R values: after the level with
+// lane-bit b only the lanes' own half of the values is kept, so 4R values cost ~4R shuffles instead of 5 * 4R).  On return
+// lane L holds the warp total of value `lean_reduce_index<R>(L)` (or garbage if that is < 0).
+template <int R> __device__ __forceinline__ int lean_reduce_index(int lane) {
+  // value kept by a lane after the levels 16, 8, 4, 2 (level 1 leaves both lanes of a pair with the total); -1: padding
+  static_assert(4 * R <= 16, "one value per lane pair");
+  int n = 4 * R, base = 0;
+#pragma unroll
+  for (int bit = 4; bit >= 1; --bit) {
+    const int half = (n + 1) >> 1;
+    if ((lane >> bit) & 1) { base += half; n = n - half; }
+    else n = half;
+  }
+  return n >= 1 ? base : -1;
+}
+
+template <int R> __device__ __forceinline__ double lean_reduce_moments(double (&mo)[4 * R], int lane) {
+  constexpr int N0 = 4 * R;
+  double v[N0];
+#pragma unroll
+  for (int i = 0; i < N0; ++i) v[i] = mo[i];
+  int n = N0;  // compile-time after unrolling
+#pragma unroll
+  for (int bit = 4; bit >= 1; --bit) {
+    if (n > 1) {
+      const int half = (n + 1) >> 1;  // low lanes keep [0, half), high lanes keep [half, n) (padded with zero)
+      const bool hi = ((lane >> bit) & 1) != 0;
+#pragma unroll
+      for (int i = 0; i < N0; ++i) {
+        if (i < half) {
+          const double other_hi = (i + half < n) ? v[i + half] : 0.0;
+          const double keep = hi ? other_hi : v[i];
+          const double send = hi ? v[i] : other_hi;
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << bit);
+        }
+      }
+      n = half;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1 << bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -287,17 +334,17 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
 
   const int tid = threadIdx.x;
   const int n_rounds = sw.n_rounds, n_exec = sw.n_exec;
-  const int nbuf = A.nbuf;
   const bool use_tma = A.tg.rank > 0;
 
   // ---- shared-memory carve-up: tile buffers aligned to TILE_BYTES (so that address = base ^ mask), tables in the slack
   const unsigned sbase = smem_u32(smem_raw);
   const unsigned pad = (0u - sbase) & (TILE_BYTES - 1u);
-  const unsigned buf_bytes = (unsigned)nbuf * NSTATE * TILE_BYTES;
+  const unsigned buf_bytes = (unsigned)NSTATE * TILE_BYTES;
   const unsigned tbl_bytes = (unsigned)lean_table_bytes<real, R, ADJ>(n_rounds, n_exec, NT);
   unsigned char* tbl = (pad >= tbl_bytes) ? smem_raw : smem_raw + pad + buf_bytes;
-  const unsigned buf0 = sbase + pad;
+  const unsigned tile_psi = sbase + pad;
   const unsigned mbar0 = smem_u32(tbl);
+  volatile long long* s_tile = reinterpret_cast<volatile long long*>(tbl + 16);  // the tile this CTA works on next (-1: none)
   c2* sscal_s = reinterpret_cast<c2*>(tbl + 32);
   LeanGate<real>* gt = reinterpret_cast<LeanGate<real>*>(tbl + 64);
   double* gsum = reinterpret_cast<double*>(gt + n_exec + 1);
@@ -307,10 +354,6 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
   unsigned long long* t_hi = t_lo + 64;
 
   const long long tiles_per_state = 1ll << sw.n_outer;
-  const long long tile_first = (long long)blockIdx.x * A.tiles_per_cta;
-  long long tile_end = tile_first + A.tiles_per_cta;
-  if (tile_end > A.total_tiles) tile_end = A.total_tiles;
-  if (tile_first >= tile_end) return;
 
   // ---- one-time prologue ----
   for (int w = tid; w < n_rounds * LT_STRIDE; w += NT) tab_s[w] = A.tab[w];
@@ -327,10 +370,8 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
   if (ADJ) for (int g = tid; g < 4 * n_exec * NWARP; g += NT) gsum[g] = 0.0;
   if (tid == 0) {
     mbar_init(mbar0, 1);
-    mbar_init(mbar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
   auto tile_base = [&](long long t) -> unsigned long long {  // CTA-index bits of tile t deposited into the basis index
     const unsigned long long c = (unsigned long long)(t % tiles_per_state);
@@ -352,14 +393,12 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
     }
     crd[A.tg.rank - 1] += (int)(b << A.tg.top_shift);
   };
-  auto issue_load_tma = [&](long long t, int which) {  // thread 0 only
+  auto issue_load_tma = [&](long long t) {  // thread 0 only
     int crd[5];
     tma_coords(t, crd);
-    const unsigned mbar = mbar0 + 8u * which;
-    const unsigned dst = buf0 + (unsigned)which * NSTATE * TILE_BYTES;
-    mbar_expect_tx(mbar, NSTATE * TILE_BYTES);
-    tma_load(&tm_psi, dst, mbar, A.tg.rank, crd);
-    if constexpr (ADJ) tma_load(&tm_lam, dst + TILE_BYTES, mbar, A.tg.rank, crd);
+    mbar_expect_tx(mbar0, NSTATE * TILE_BYTES);
+    tma_load(&tm_psi, tile_psi, mbar0, A.tg.rank, crd);
+    if constexpr (ADJ) tma_load(&tm_lam, tile_psi + TILE_BYTES, mbar0, A.tg.rank, crd);
   };
   auto issue_load_manual = [&](long long t, unsigned long long base) {  // all threads: coalesced gathers into the swizzled layout
     const long long off = ((t / tiles_per_state) << A.n) + (long long)base;
@@ -367,7 +406,7 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
     for (int i = 0; i < NV; ++i) {
       const int e = i * NT + tid;
       const long long g = off + (long long)(t_lo[e & 63] + t_hi[e >> 6]);
-      const unsigned dst = buf0 + (unsigned)swz<real>(e) * (unsigned)sizeof(c2);
+      const unsigned dst = tile_psi + (unsigned)swz<real>(e) * (unsigned)sizeof(c2);
       cp_async_s<sizeof(c2)>(dst, A.psi + g);
       if constexpr (ADJ) cp_async_s<sizeof(c2)>(dst + TILE_BYTES, A.lam + g);
     }
@@ -385,40 +424,35 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
       }
     }
   };
-
-  // De-phase the CTAs that share an SM.  All persistent CTAs start together and do identical work, so without this they
-  // stay in lockstep: every CTA of the device waits for HBM at the same time (FP64 pipe idle), then they all compute
-  // (HBM idle) — the sweep takes T_stream + T_compute instead of max(...).  The k-th CTA on an SM (blocks are dealt to the
-  // SMs round-robin, so k = blockIdx / #SMs) starts k shares of a tile period late; from then on one CTA's memory phase
-  // overlaps the others' compute phases.
-  if (A.stagger_ns != 0u && (use_tma ? tid == 0 : true)) {
-    const unsigned slot = blockIdx.x / (unsigned)A.n_sms;
-    if (slot != 0u) {
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      const unsigned long long wait_ns = (unsigned long long)slot * A.stagger_ns;
-      do {
-        __nanosleep(256);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      } while (t1 - t0 < wait_ns);
-    }
+  // Dynamic tile scheduling: CTAs claim chunks of consecutive tiles from a device counter.  The warp schedulers favour
+  // the older of the CTAs that share an SM (measured: 17 / 22 / 33 / 49 us per tile for the 1st .. 4th CTA of an SM), so a
+  // static split leaves the late CTAs running alone at the end of the sweep.
+  long long chunk_end = 0;  // thread 0 only
+  auto claim = [&](long long after) -> long long {  // thread 0 only
+    if (after >= 0 && after + 1 < chunk_end) return after + 1;
+    const long long c = (long long)atomicAdd(A.tile_counter, (unsigned)A.chunk);
+    if (c >= A.total_tiles) return -1;
+    chunk_end = c + A.chunk < A.total_tiles ? c + A.chunk : A.total_tiles;
+    return c;
+  };
+  if (tid == 0) {
+    const long long t0 = claim(-1);
+    s_tile[0] = t0;
+    if (use_tma && t0 >= 0) issue_load_tma(t0);
   }
-  long long cur_b = -1;
-  unsigned phase0 = 0, phase1 = 0;
-  if (use_tma) { if (tid == 0) issue_load_tma(tile_first, 0); }
-  else issue_load_manual(tile_first, tile_base(tile_first));
+  __syncthreads();
+  if (!use_tma && s_tile[0] >= 0) issue_load_manual(s_tile[0], tile_base(s_tile[0]));
 
-  for (long long t = tile_first; t < tile_end; ++t) {
-    const int which = (nbuf == 2) ? (int)((t - tile_first) & 1) : 0;
+  long long cur_b = -1;
+  unsigned phase0 = 0;
+  long long traced = 0;
+  while (true) {
+    const long long t = s_tile[0];
+    if (t < 0) break;
     const long long b = t / tiles_per_state;
     const unsigned long long cta_base = tile_base(t);
     const unsigned long long cta_index = cta_base | A.index_hi;
-    const unsigned tile_psi = buf0 + (unsigned)which * NSTATE * TILE_BYTES;
 
-    if (use_tma && nbuf == 2 && t + 1 < tile_end && tid == 0) {
-      bulk_wait_read0();  // the store that read buffer which^1 (tile t-1) has drained
-      issue_load_tma(t + 1, which ^ 1);
-    }
     if (b != cur_b) {  // new batch element: its normalised gates and the sweep scalar
       if (ADJ && cur_b >= 0) { flush_moments(cur_b); __syncthreads(); }
       constexpr int W = sizeof(LeanGate<real>) / 16;
@@ -441,22 +475,18 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
         if ((cta_index >> ((w >> (8 + 6 * k)) & 63u)) & 1ull) e ^= T[44 + k];
       ext_s[rr] = e;
     }
-    if (use_tma) {
-      if (which == 0) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
-      else { mbar_wait(mbar0 + 8, phase1); phase1 ^= 1u; }
-    } else {
-      cp_async_wait<0>();
-    }
+    if (use_tma) { mbar_wait(mbar0, phase0); phase0 ^= 1u; }
+    else cp_async_wait<0>();
     __syncthreads();  // tile landed (all threads' gathers), gates / ext visible
-    const long long tl = t - tile_first;
-    const bool tracing = A.trace != nullptr && tid == 0 && tl < A.trace_tiles;
-    unsigned long long* trow = tracing ? A.trace + ((long long)blockIdx.x * A.trace_tiles + tl) * 4 : nullptr;
+    const bool tracing = A.trace != nullptr && tid == 0 && traced < A.trace_tiles;
+    unsigned long long* trow = tracing ? A.trace + ((long long)blockIdx.x * A.trace_tiles + traced) * 4 : nullptr;
     if (tracing) {
       unsigned long long now; unsigned smid;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       trow[0] = now; trow[3] = smid;
     }
+    ++traced;
 
     const c2 sc = sscal_s[0];
     const bool scale = !(sc.x == (real)1 && sc.y == (real)0);
@@ -476,7 +506,7 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
         ms[a] = (int)T[38 + a];
         if (ms[a] != (int)LT_EMPTY) base ^= ro[a] & gt[ms[a]].flipmask;
       }
-      const unsigned la0 = tile_psi | (base & 0xffffu);  // buffers are TILE_BYTES-aligned: OR == ADD, later XORs stay inside
+      const unsigned la0 = tile_psi | (base & 0xffffu);  // the buffer is TILE_BYTES-aligned: OR == ADD, later XORs stay inside
       const unsigned sa0 = tile_psi | (base >> 16);
       auto xmask = [&](int j, int sh) {
         unsigned o = 0;
@@ -503,25 +533,32 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
             if (ms[a] != (int)LT_EMPTY) RG::template nmat<a>(p, gt[ms[a]].m);
           });
         } else {
+          // The chains of one round act on different qubits, so <lambda|P_a|psi> does not care whether the OTHER slots
+          // are already un-applied (their 2x2 commute with P_a and cancel between bra and ket up to the real factor the
+          // resolve kernel tracks): all moments of the round are taken first, from the same registers, and reduced together.
+          bool any = false;
+#pragma unroll
+          for (int a = 0; a < R; ++a) any |= ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN;
+          if (any) {  // uniform across the CTA
+            double mo[4 * R];
+            static_for_up<0, R>([&](auto ic) {
+              constexpr int a = decltype(ic)::value;
+              double m4[4] = {0.0, 0.0, 0.0, 0.0};
+              if (ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN) RG::template moments<a>(p, l, m4);
+              mo[4 * a] = m4[0]; mo[4 * a + 1] = m4[1]; mo[4 * a + 2] = m4[2]; mo[4 * a + 3] = m4[3];
+            });
+            const int lane = tid & 31;
+            const double tot = lean_reduce_moments<R>(mo, lane);
+            const int vi = lean_reduce_index<R>(lane);
+            if ((lane & 1) == 0 && vi >= 0) {
+              const int x = ms[vi >> 2];
+              if (x != (int)LT_EMPTY) gsum[(x * NWARP + (tid >> 5)) * 4 + (vi & 3)] += tot;
+            }
+          }
           static_for_down<R - 1>([&](auto ic) {
             constexpr int a = decltype(ic)::value;
             if (ms[a] != (int)LT_EMPTY) {
               const LeanGate<real>& g = gt[ms[a]];
-              if ((g.gr & 0xff) == GR_CHAIN) {  // uniform across the CTA
-                double mo[4];
-                RG::template moments<a>(p, l, mo);
-                // transposed butterfly: 6 double shuffles for 4 values; totals land in lanes 0, 8, 16, 24
-                const int lane = tid & 31;
-                const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
-                const double r0 = __shfl_xor_sync(0xffffffffu, h16 ? mo[0] : mo[2], 16);
-                const double r1 = __shfl_xor_sync(0xffffffffu, h16 ? mo[1] : mo[3], 16);
-                const double a0 = (h16 ? mo[2] : mo[0]) + r0, a1 = (h16 ? mo[3] : mo[1]) + r1;
-                double v = (h8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, h8 ? a0 : a1, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if ((lane & 7) == 0) gsum[(ms[a] * NWARP + (tid >> 5)) * 4 + (lane >> 3)] += v;
-              }
               RG::template nmat<a>(p, g.m);
               RG::template nmat<a>(l, g.m);
             }
@@ -531,15 +568,15 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
       if (rr == n_rounds - 1 && scale) {  // the sweep's pending scalar, once per amplitude
 #pragma unroll
         for (int j = 0; j < NV; ++j) {  // in place (one temporary), see nmat
-          real t = p[j].x * sc.y;
+          real t1 = p[j].x * sc.y;
           p[j].x = p[j].x * sc.x;
           p[j].x = fma(-p[j].y, sc.y, p[j].x);
-          p[j].y = fma(p[j].y, sc.x, t);
+          p[j].y = fma(p[j].y, sc.x, t1);
           if constexpr (ADJ) {
-            t = l[j].x * sc.y;
+            t1 = l[j].x * sc.y;
             l[j].x = l[j].x * sc.x;
             l[j].x = fma(-l[j].y, sc.y, l[j].x);
-            l[j].y = fma(l[j].y, sc.x, t);
+            l[j].y = fma(l[j].y, sc.x, t1);
           }
         }
       }
@@ -552,9 +589,9 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
       if (use_tma && rr == n_rounds - 1) fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
       __syncthreads();
     }
-
     if (tracing) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trow[1] = now; }
-    // ---- write the tile back ----
+
+    // ---- write the tile back, claim the next one ----
     if (use_tma) {
       if (tid == 0) {
         int crd[5];
@@ -562,12 +599,13 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
         tma_store(&tm_psi, tile_psi, A.tg.rank, crd);
         if constexpr (ADJ) tma_store(&tm_lam, tile_psi + TILE_BYTES, A.tg.rank, crd);
         bulk_commit();
-        if (nbuf == 1 && t + 1 < tile_end) {
-          bulk_wait_read0();
-          issue_load_tma(t + 1, 0);
-        }
+        const long long nxt = claim(t);
+        bulk_wait_read0();  // the store has drained the buffer
+        if (nxt >= 0) issue_load_tma(nxt);
+        s_tile[0] = nxt;
         if (tracing) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trow[2] = now; }
       }
+      __syncthreads();  // publishes s_tile
     } else {
       const long long state_off = b << A.n;
 #pragma unroll
@@ -578,8 +616,10 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
         A.psi[g] = lds_c2<c2>(src);
         if constexpr (ADJ) A.lam[g] = lds_c2<c2>(src + TILE_BYTES);
       }
+      if (tid == 0) s_tile[0] = claim(t);
       __syncthreads();
-      if (t + 1 < tile_end) issue_load_manual(t + 1, tile_base(t + 1));
+      const long long nxt = s_tile[0];
+      if (nxt >= 0) issue_load_manual(nxt, tile_base(nxt));
     }
   }
   if (ADJ && cur_b >= 0) { __syncthreads(); flush_moments(cur_b); }
@@ -596,7 +636,8 @@ __global__ void resolve_lean_kernel(const b200sv_sweep* __restrict__ sweeps, con
                                     const b200sv_gate* __restrict__ gates, const int* __restrict__ exec_leader,
                                     const double* __restrict__ params, const double* __restrict__ consts,
                                     LeanGate<real>* __restrict__ gtab, typename C2<real>::type* __restrict__ sscal,
-                                    int s_first, int s_count, int n_exec_total, long long batch, int dir) {
+                                    unsigned* __restrict__ tile_counters, int s_first, int s_count, int n_exec_total,
+                                    long long batch, int dir) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)s_count * batch) return;
   const int s = s_first + (int)(t / batch);
@@ -606,6 +647,7 @@ __global__ void resolve_lean_kernel(const b200sv_sweep* __restrict__ sweeps, con
   double acc_r = 1.0, acc_i = 0.0;
   for (int rr = 0; rr < sw.n_rounds; ++rr) {
     const b200sv_round& rd = rounds[sw.first_round + (dir > 0 ? rr : sw.n_rounds - 1 - rr)];
+    const double round_scale = acc_r * acc_r + acc_i * acc_i;  // all moments of a round are taken before its un-applies
     for (int ai = 0; ai < sw.r; ++ai) {
       const int a = dir > 0 ? ai : sw.r - 1 - ai;
       const int x = a < 4 ? rd.mslot[a] : rd.mslot4;
@@ -635,7 +677,7 @@ __global__ void resolve_lean_kernel(const b200sv_sweep* __restrict__ sweeps, con
         g.m[2 * k] = (real)(er * inv_r - ei * inv_i);
         g.m[2 * k + 1] = (real)(er * inv_i + ei * inv_r);
       }
-      g.mscale = (real)(acc_r * acc_r + acc_i * acc_i);
+      g.mscale = (real)round_scale;
       g.flipmask = (cf ? 0xffffu : 0u) | (rf ? 0xffff0000u : 0u);
       g.gr = ((dir < 0 && any_grad) ? GR_CHAIN : GR_NONE) | (cf << 8);
       const double tr = acc_r * nr - acc_i * ni, ti = acc_r * ni + acc_i * nr;
@@ -646,6 +688,7 @@ __global__ void resolve_lean_kernel(const b200sv_sweep* __restrict__ sweeps, con
   typename C2<real>::type sc;
   sc.x = (real)acc_r; sc.y = (real)acc_i;
   sscal[(long long)s * batch + b] = sc;
+  if (b == 0) tile_counters[s] = 0u;  // dynamic tile scheduling of this sweep's launch starts at tile 0
 }
 
 }  // namespace b200sv

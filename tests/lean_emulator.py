@@ -36,6 +36,7 @@ def resolve_lean(plan: P.SweepPlan, si: int, params: np.ndarray, b: int, forward
     for rr in rounds:
         rd = plan.rounds[int(sw["first_round"]) + rr]
         ms = [int(x) for x in rd["mslot"]] + [int(rd["mslot4"])]
+        round_scale = abs(acc) ** 2  # the kernel takes all moments of a round before un-applying any of its slots
         for a in (range(r) if forward else reversed(range(r))):
             x = ms[a]
             if x < 0:
@@ -55,7 +56,7 @@ def resolve_lean(plan: P.SweepPlan, si: int, params: np.ndarray, b: int, forward
             nu = prod[rf, cf]
             E = np.array([[prod[i ^ rf, j ^ cf] for j in range(2)] for i in range(2)])
             N = E / nu if nu != 0 else np.zeros((2, 2), dtype=np.complex128)
-            out[x] = dict(beta=N[0, 1], gamma=N[1, 0], delta=N[1, 1], mscale=abs(acc) ** 2, cf=cf, rf=rf,
+            out[x] = dict(beta=N[0, 1], gamma=N[1, 0], delta=N[1, 1], mscale=round_scale, cf=cf, rf=rf,
                           grad=(not forward) and any(int(c["flags"]) & P.GF_GRAD for c in recs), recs=recs)
             acc = acc * nu
     return out, acc
@@ -135,18 +136,23 @@ def emulate_lean_sweep(plan: P.SweepPlan, si: int, psi: np.ndarray, lam: np.ndar
                 p = smem_p[la]
                 l = smem_l[la] if lam is not None else None
                 order = range(r) if forward else reversed(range(r))
+                for a in range(r):  # adjoint: every moment of the round from the registers as loaded
+                    if ms[a] == P.LT_EMPTY or not gates[ms[a]]["grad"]:
+                        continue
+                    g = gates[ms[a]]
+                    lo = jj[(jj >> a) & 1 == 0]
+                    hi = lo | (1 << a)
+                    assert lam is not None and grads is not None
+                    mo = _moments(p, l, lo, hi)
+                    sg = -1.0 if g["cf"] else 1.0
+                    m4 = {"I": g["mscale"] * mo[0], "X": g["mscale"] * mo[1], "Y": sg * g["mscale"] * mo[2], "Z": sg * g["mscale"] * mo[3]}
+                    _chain_gradients(plan, g["recs"], m4, params, b, grads)
                 for a in order:
                     if ms[a] == P.LT_EMPTY:
                         continue
                     g = gates[ms[a]]
                     lo = jj[(jj >> a) & 1 == 0]
                     hi = lo | (1 << a)
-                    if g["grad"]:
-                        assert lam is not None and grads is not None
-                        mo = _moments(p, l, lo, hi)
-                        sg = -1.0 if g["cf"] else 1.0
-                        m4 = {"I": g["mscale"] * mo[0], "X": g["mscale"] * mo[1], "Y": sg * g["mscale"] * mo[2], "Z": sg * g["mscale"] * mo[3]}
-                        _chain_gradients(plan, g["recs"], m4, params, b, grads)
                     for arr in ([p] if lam is None else [p, l]):
                         x, y = arr[:, lo].copy(), arr[:, hi].copy()
                         arr[:, lo] = x + g["beta"] * y

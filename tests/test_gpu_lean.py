@@ -1,6 +1,5 @@
 """`lean_sweep_kernel` (TMA-staged tiles, persistent CTAs, normalised 2x2) against the CPU oracle, through the C-ABI:
-every compiled (dtype, r, m, direction) instantiation, both tile I/O modes (TMA boxes and cp.async gathers), single and
-double buffering, non-unitary / singular 1-qubit matrices (row flips), and the adjoint gradients."""
+every compiled (dtype, r, m, direction) instantiation, both tile I/O modes (TMA boxes and cp.async gathers), non-unitary / singular 1-qubit matrices (row flips), and the adjoint gradients."""
 
 from __future__ import annotations
 
@@ -59,12 +58,11 @@ def _forward(prog, values, psi0, cfg, dtype, n, B):
 
 
 @pytest.mark.parametrize("inst", [i for i in INSTANCES if not i[3]], ids=lambda i: f"{'c128' if i[0] else 'c64'}-r{i[1]}m{i[2]}")
-@pytest.mark.parametrize("io", ["tma", "gather", "tma2buf"])
+@pytest.mark.parametrize("io", ["tma", "gather"])
 def test_lean_forward_instances(inst, io: str, monkeypatch) -> None:
     c128, r, m, _ = inst
     dtype = torch.complex128 if c128 else torch.complex64
     monkeypatch.setenv("B200SV_TMA", "0" if io == "gather" else "1")
-    monkeypatch.setenv("B200SV_LEAN_NBUF", "2" if io == "tma2buf" else "1")
     n, B = m + 1, 3  # one outer bit: every tile has at most two runs, i.e. is a TMA box
     rng = np.random.default_rng(31 * m + r + len(io))
     prog, names = lean_random_program(n, 90, rng, unitary=not c128)  # complex64: keep the norm O(1)
@@ -81,13 +79,12 @@ def test_lean_forward_instances(inst, io: str, monkeypatch) -> None:
 
 
 @pytest.mark.parametrize("inst", [i for i in INSTANCES if i[3]], ids=lambda i: f"{'c128' if i[0] else 'c64'}-r{i[1]}m{i[2]}")
-@pytest.mark.parametrize("io", ["tma", "gather", "tma2buf"])
+@pytest.mark.parametrize("io", ["tma", "gather"])
 def test_lean_adjoint_instances(inst, io: str, monkeypatch) -> None:
     """ψ, λ walked back and all gradients, through `b200sv_adjoint_plan` directly with this instantiation's geometry."""
     c128, r, m, _ = inst
     dtype = torch.complex128 if c128 else torch.complex64
     monkeypatch.setenv("B200SV_TMA", "0" if io == "gather" else "1")
-    monkeypatch.setenv("B200SV_LEAN_NBUF", "2" if io == "tma2buf" else "1")
     n, B = m + 1, 2
     rng = np.random.default_rng(17 * m + r)
     prog = hea_program(n, 2)

@@ -2,12 +2,22 @@
 """bench.py — BASELINE.json's headline config on B200: expectation + adjoint parameter gradients of a
 20-qubit HEA (depth 8), batch 256 independent parameter sets, complex128 (`configs[1]`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu-baseline] [--cpu-samples 4,8]
 
-One "step" = one full expectation+gradient evaluation of the whole batch: |0..0> init, fused
-forward sweeps, <Z_tot>, λ = Oψ, fused adjoint sweeps that also reduce all 480 gradients.
-Prints ONE JSON line (rank 0).  Multi-GPU (torchrun): every rank evaluates its own 256 parameter
-sets (parameter batches shard trivially: no data-path collective) → "scaling": "weak".
+One "step" = one full expectation+gradient evaluation of the whole batch: |0..0> init, fused forward sweeps, <Z_tot>,
+λ = Oψ, fused adjoint sweeps that also reduce all 480 gradients.  Prints ONE JSON line (rank 0):
+
+* `value`  — evals/s with the parameter table already in HBM, straight through the C-ABI;
+* `e2e`    — the same through the reference-facing plugin: `backend_factory("b200sv", "adjoint")` → `convert` →
+             `embedding_fn` → `expectation(...).sum().backward()` on HOST tensors (H2D of the 480 x 256 angles and D2H of
+             the expectations and all gradients inside the timed region); `e2e.path` says which path was timed;
+* `parity` — BEFORE anything is timed the CUDA result of a few batch elements is compared with the CPU oracle
+             (expectation and all 480 gradients, 1e-10); on a mismatch no value is printed and the exit code is 1;
+* `roofline`, `cpu_baseline`, `clocks`, `gpu_launches` as the contract asks.
+
+Multi-GPU (torchrun): every rank evaluates its own 256 parameter sets (parameter batches shard trivially: no data-path
+collective) → "scaling": "weak"; the line additionally carries `collective` (cfg4 per-GPU share with the gradient
+all-reduce) and `sharded` (one register sharded by its top qubits over the N GPUs, peer-memory sweeps).
 """
 
 from __future__ import annotations
@@ -27,7 +37,8 @@ sys.path.insert(0, str(ROOT))
 
 N_QUBITS, DEPTH, BATCH = 20, 8, 256
 FP64_PEAK_TFLOPS = 33.9  # measured on this pool's B200 with tools/ubench/dmma.cu (16 independent DFMA chains per thread)
-CPU_SAMPLE_BATCH = 4  # parameter sets per CPU step (≈ 10-20 s of host work)
+CPU_SAMPLE_BATCH = 4  # parameter sets per CPU step (≈ 10-30 s of host work)
+PARITY_TOL = 1e-10
 WORKLOAD = ("cfg2: hea(n_qubits=20, depth=8) expectation of total_magnetization + adjoint gradients of 480 parameters, "
             "batch 256 per GPU, complex128")
 METRIC = "expectation+grad evals/s (HEA n=20 depth=8, batch 256, complex128, adjoint)"
@@ -93,9 +104,18 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _cpu_eval(batch: int, threads: int) -> tuple[float, float]:
-    """One expectation+gradient evaluation of hea(20,8) on the CPU oracle (the restated pyqtorch path:
-    einsum per gate + Python adjoint loop).  Returns (seconds, evals/s)."""
+def host_table(rank: int):
+    """The step's inputs: [480, 256] angles, the same generator / seed on every path (device, e2e, CPU legs, tests)."""
+    import torch
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_slots = 3 * N_QUBITS * DEPTH  # 3 rotations per qubit and layer
+    return 2 * torch.pi * torch.rand(n_slots, BATCH, generator=g, dtype=torch.float64)
+
+
+def _cpu_eval(columns: list[int], threads: int, rank: int = 0):
+    """Expectation + all gradients of the given batch elements on the CPU oracle (the restated pyqtorch path: einsum per
+    gate + Python adjoint loop).  Returns (seconds, E [k], grads [480, k])."""
     import torch
 
     from oracle import statevec as oracle
@@ -104,39 +124,57 @@ def _cpu_eval(batch: int, threads: int) -> tuple[float, float]:
     torch.set_num_threads(threads)
     prog = hea_program(N_QUBITS, DEPTH)
     obs = total_magnetization(N_QUBITS)
-    g = torch.Generator().manual_seed(0)
-    values = {nm: 2 * torch.pi * torch.rand(batch, generator=g, dtype=torch.float64) for nm in prog.param_names}
+    table = host_table(rank)
+    values = {nm: table[i, columns].clone() for i, nm in enumerate(prog.param_names)}
     t0 = time.perf_counter()
-    oracle.adjoint_expectation_and_grads(prog, obs, values)
+    e, g = oracle.adjoint_expectation_and_grads(prog, obs, values)
     dt = time.perf_counter() - t0
-    return dt, batch / dt
+    return dt, e, torch.stack([g[nm] for nm in prog.param_names])
 
 
 def run_reference(args) -> None:
-    """Reference arm: the reference's CPU path (restated — pyqtorch is not installable here) on the
-    host cores, same config / metric, each step a bounded sample (batch 1 of the 256)."""
+    """Reference arm: the reference's CPU path (restated — pyqtorch is not installable here) on the host cores, same
+    config / metric, each step a bounded sample of the batch (per-eval throughput)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
     threads = os.cpu_count() or 1
-    sample_batch = CPU_SAMPLE_BATCH
+    k = CPU_SAMPLE_BATCH
+    cols = list(range(k))
     for _ in range(min(args.warmup, 1)):
-        _cpu_eval(sample_batch, threads)
-    ts = [_cpu_eval(sample_batch, threads)[0] for _ in range(args.steps)]
+        _cpu_eval(cols, threads)
+    ts = [_cpu_eval(cols, threads)[0] for _ in range(args.steps)]
     dt = sum(ts) / len(ts)
-    val = sample_batch / dt
+    val = k / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_step": f"{sample_batch} of the 256 parameter sets per step on the host cores (per-eval throughput)"},
+        "config": {"workload": WORKLOAD, "reference_step": f"{k} of the 256 parameter sets per step on the host cores (per-eval throughput)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample_batch} of the 256 parameter sets per step, torch {torch.__version__} einsum-per-gate + adjoint loop (oracle/statevec.py; pyqtorch is not installable here)"},
+                         "sample": f"{k} of the 256 parameter sets per step, torch {torch.__version__} einsum-per-gate + adjoint loop (oracle/statevec.py; pyqtorch is not installable here)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def _qadence_frontend() -> bool:
+    """Make `import qadence` work: /root/reference in the CPU container, the copy under baseline/_ref on a GPU box."""
+    for cand in (Path("/root/reference"), ROOT / "baseline" / "_ref"):
+        if (cand / "qadence" / "__init__.py").exists():
+            for p in (str(cand), str(ROOT / "tests" / "_shims")):
+                if p not in sys.path:
+                    sys.path.insert(0, p)
+            os.environ.setdefault("QADENCE_LOG_LEVEL", "ERROR")
+            try:
+                import qadence  # noqa: F401
+
+                return True
+            except Exception:
+                return False
+    return False
 
 
 def main() -> None:
@@ -146,6 +184,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200sv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-samples", default="4,8", help="batch elements per CPU-baseline evaluation (two sizes: is the per-eval throughput flat?)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the collective / sharded sections at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -179,15 +219,18 @@ def main() -> None:
     cob = engine.CompiledObservable(total_magnetization(N_QUBITS))
     dtype = torch.complex128
     n_slots = len(cp.names)
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_params = (2 * torch.pi * torch.rand(n_slots, BATCH, generator=g, dtype=torch.float64)).pin_memory()
+    host_params = host_table(rank).pin_memory()
+    assert host_params.shape == (n_slots, BATCH)
     S = BATCH * (1 << N_QUBITS) * 16  # bytes of one state
 
     seg = cp.segments[0]
     fwd = cp.device_plan(seg, dtype, False, dev)
     adj = cp.device_plan(seg, dtype, True, dev)
     coef = cob.pauli.coef({}, dev)
-    launches_per_step = 1 + (1 + fwd.n_sweeps) + 1 + 1 + (1 + adj.n_sweeps + 1)  # init, resolve+fwd sweeps, <O>, λ=Oψ, resolve+adj sweeps+grad
+    n_lean_f = int((fwd.plan.sweeps["io_mode"] != 0).sum())
+    n_lean_a = int((adj.plan.sweeps["io_mode"] != 0).sum())
+    # our kernels per step: init, resolve + forward sweeps, <O>, λ = Oψ, resolve + adjoint sweeps + gradient kernel
+    launches_per_step = 1 + (1 + fwd.n_sweeps) + 1 + 1 + (1 + adj.n_sweeps + 1)
     ws_f = fwd.workspace(dtype, BATCH, False).data_ptr()
     ws_a = adj.workspace(dtype, BATCH, True).data_ptr()
 
@@ -196,7 +239,6 @@ def main() -> None:
     psi = torch.empty(BATCH, 1 << N_QUBITS, dtype=dtype, device=dev)
     lam = torch.empty_like(psi)
     grads = torch.zeros(n_slots, BATCH, dtype=torch.float64, device=dev)
-    ones = torch.ones(BATCH, dtype=torch.float64, device=dev)
 
     def device_step():
         st = _stream_ptr(dev)
@@ -229,6 +271,34 @@ def main() -> None:
             ms = float(t.item())
         return ms
 
+    # ---------------- parity gate: CUDA vs the CPU oracle BEFORE anything is timed ----------------
+    cpu_samples = [int(x) for x in args.cpu_samples.split(",") if x.strip()]
+    do_cpu = world == 1 and not args.no_cpu_baseline
+    threads = os.cpu_count() or 1
+    e_dev = device_step()
+    torch.cuda.synchronize(dev)
+    parity = None
+    cpu_runs = []
+    if rank == 0:
+        k0 = cpu_samples[0] if do_cpu else 1
+        cols = list(range(k0))
+        dt, e_cpu, g_cpu = _cpu_eval(cols, threads, rank)
+        err_e = float((e_dev[cols].cpu() - e_cpu).abs().max())
+        err_g = float((grads[:, cols].cpu() - g_cpu).abs().max())
+        parity = {"checked": f"batch elements {cols}: expectation and all {n_slots} gradients vs oracle.adjoint_expectation_and_grads (CPU, einsum per gate)",
+                  "max_abs_err_expectation": err_e, "max_abs_err_gradient": err_g, "tolerance": PARITY_TOL,
+                  "ok": bool(err_e <= PARITY_TOL and err_g <= PARITY_TOL)}
+        cpu_runs.append({"batch_elements": k0, "seconds": dt, "evals_per_s": k0 / dt})
+    ok = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
+    if world > 1:
+        dist.broadcast(ok, 0)
+    if int(ok.item()) == 0:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "error": "parity check against the CPU oracle failed; nothing was timed", "parity": parity}))
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(1)
+
     for _ in range(args.warmup):
         device_step()
     sampler = ClockSampler(local_rank)
@@ -238,19 +308,55 @@ def main() -> None:
     ms_per_step = ms / args.steps
     value = world * BATCH / (ms_per_step * 1e-3)
 
-    # ---------------- end-to-end through the public API, host buffers ----------------
+    # ---------------- end to end through the reference-facing plugin, host buffers ----------------
     names = cp.names
-    d2h_e = torch.empty(BATCH, 1, dtype=torch.float64).pin_memory()
-    d2h_g = torch.empty(n_slots, BATCH, dtype=torch.float64).pin_memory()
+    e2e_path, e2e_err = None, ""
+    if _qadence_frontend():
+        try:
+            from qadence import QuantumCircuit, hea
+            from qadence import total_magnetization as q_total_magnetization
+            from qadence.backends.api import backend_factory
+            from qadence.blocks.utils import parameters
+            from qadence.transpile.block import set_trainable
 
-    def e2e_step():
-        table = host_params.to(dev, non_blocking=True).requires_grad_(True)  # H2D of this step's inputs
-        values = {nm: table[i] for i, nm in enumerate(names)}
-        out = engine.expectation(cp, [cob], values, dtype=dtype, device=dev)
-        out.sum().backward()
-        d2h_e.copy_(out.detach(), non_blocking=True)  # D2H of the results
-        d2h_g.copy_(table.grad, non_blocking=True)
+            block = hea(N_QUBITS, DEPTH)
+            set_trainable(block, value=False)  # the 480 angles are INPUTS of batch 256 (feature parameters), as cfg2 says
+            bk = backend_factory("b200sv", diff_mode="adjoint")
+            conv = bk.convert(QuantumCircuit(N_QUBITS, block), q_total_magnetization(N_QUBITS))
+            qnames = sorted({p.name for p in parameters(block) if not p.is_number}, key=lambda s: int(s.split("_")[-1]))
+            assert len(qnames) == n_slots
 
+            def e2e_step():
+                x = {nm: host_params[i].clone().requires_grad_(True) for i, nm in enumerate(qnames)}  # HOST tensors
+                out = bk.expectation(conv.circuit, conv.observable, conv.embedding_fn(conv.params, x))  # H2D inside
+                out.sum().backward()  # adjoint sweeps; the gradients land on the host tensors (D2H inside)
+                return out, x
+
+            out, x = e2e_step()
+            torch.cuda.synchronize(dev)
+            # qadence's hea and hea_program must mean the same circuit: the plugin path has to reproduce the C-ABI numbers
+            d_e = float((out[:, 0].detach().cpu() - e_dev.cpu()).abs().max())
+            d_g = float(max((x[nm].grad - grads[i].cpu()).abs().max() for i, nm in enumerate(qnames)))
+            if d_e > 1e-10 or d_g > 1e-10:
+                raise RuntimeError(f"plugin path disagrees with the C-ABI path: dE={d_e:.2e} dgrad={d_g:.2e}")
+            e2e_path = ("qadence backend_factory('b200sv', diff_mode='adjoint'): convert -> embedding_fn(host tensors) -> "
+                        "Backend.expectation -> .sum().backward() (front-end: " + ("/root/reference" if Path("/root/reference/qadence").exists() else "baseline/_ref") + ")")
+        except Exception as ex:  # the front-end is optional on a GPU box: fall back to the engine call and SAY so
+            e2e_path = None
+            e2e_err = f": {type(ex).__name__}: {ex}"
+    if e2e_path is None:
+        d2h_e = torch.empty(BATCH, 1, dtype=torch.float64).pin_memory()
+        d2h_g = torch.empty(n_slots, BATCH, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            table = host_params.to(dev, non_blocking=True).requires_grad_(True)  # H2D of this step's inputs
+            values = {nm: table[i] for i, nm in enumerate(names)}
+            out = engine.expectation(cp, [cob], values, dtype=dtype, device=dev)
+            out.sum().backward()
+            d2h_e.copy_(out.detach(), non_blocking=True)  # D2H of the results
+            d2h_g.copy_(table.grad, non_blocking=True)
+
+        e2e_path = "qadence_b200.engine.expectation(...).backward() on a pinned host table (qadence front-end not usable" + e2e_err + ")"
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps) / args.steps
@@ -271,7 +377,6 @@ def main() -> None:
         ev[i + 1].record()
     torch.cuda.synchronize(dev)
     adj_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(adj.n_sweeps)]
-    # forward sweeps (2·S each), for the record
     evf = [torch.cuda.Event(enable_timing=True) for _ in range(fwd.n_sweeps + 1)]
     evf[0].record()
     for s in range(fwd.n_sweeps):
@@ -279,8 +384,20 @@ def main() -> None:
         evf[s + 1].record()
     torch.cuda.synchronize(dev)
     fwd_ms = [evf[i].elapsed_time(evf[i + 1]) for i in range(fwd.n_sweeps)]
-    # a light sweep (one round: three merged rotations) shows the memory path alone: the state is streamed
-    # through shared memory exactly like in the heavy sweeps, with 3 instead of ~10 merged 2x2 per tile
+    # the other kernels of the step, each alone (init, <O>, λ = Oψ)
+    small = {}
+    for nm, fn in (("zero_state", lambda: lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st)),
+                   ("pauli_expectation", lambda: engine.pauli_expectation(cob.pauli, coef, psi)),
+                   ("pauli_apply", lambda: engine.pauli_apply(cob.pauli, coef, psi, out=lam))):
+        fn()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            fn()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        small[nm] = a0.elapsed_time(a1) / 3
+    # a light sweep (one round: three merged rotations) shows the memory path alone
     from qadence_b200.program import OpKind, ProgramBuilder
 
     lb = ProgramBuilder(N_QUBITS)
@@ -288,7 +405,7 @@ def main() -> None:
         lb.rot(OpKind.RX, q, cp.names[q]).rot(OpKind.RY, q, cp.names[q + 20])
     lcp = engine.CompiledProgram(lb.build())
     lplan = lcp.device_plan(lcp.segments[0], dtype, False, dev)
-    ltab = ptable[: max(1, len(lcp.names))] if False else engine.pack_params(lcp.names, {nm: ptable[cp.slot_of[nm]] for nm in lcp.names}, BATCH, dev)
+    ltab = engine.pack_params(lcp.names, {nm: ptable[cp.slot_of[nm]] for nm in lcp.names}, BATCH, dev)
     lws = lplan.workspace(dtype, BATCH, False).data_ptr()
     for _ in range(2):
         cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ltab.data_ptr(), C.byref(lplan.struct), 0, lplan.n_sweeps, 0, lws, st), "light")
@@ -307,21 +424,41 @@ def main() -> None:
     achieved = 4 * S / (adj_avg * 1e-3) / 1e9
     fwd_achieved = 2 * S / (fwd_avg * 1e-3) / 1e9
 
-    # FP64 pipe view of the same step: every merged 2x2 costs 8 FP64 instructions per amplitude going forward and
-    # 24 going backward (un-apply on psi and lambda + the four gradient moments), see DESIGN.md §4.1
+    # FP64 pipe view: a merged (normalised) 2x2 costs 6 FP64 instructions per amplitude going forward and 18 going backward
+    # (un-apply on psi and lambda + the gradient moments), see DESIGN.md §4.1
     n_chain_f = int((fwd.plan.rounds["mslot"] >= 0).sum()) + int((fwd.plan.rounds["mslot4"] >= 0).sum())
     n_chain_a = int((adj.plan.rounds["mslot"] >= 0).sum()) + int((adj.plan.rounds["mslot4"] >= 0).sum())
     fp64_instr = (6 * n_chain_f + 18 * n_chain_a) * float(BATCH) * float(1 << N_QUBITS)
     fp64_tflops = 2 * fp64_instr / (ms_per_step * 1e-3) / 1e12
 
+    # ---------------- multi-GPU sections (N > 1): what a collective / a sharded register costs ----------------
+    multi = {}
+    if world > 1 and not args.no_multi:
+        from tools import multi_gpu_sections
+
+        multi = multi_gpu_sections.run(rank, world, dev, steps=max(2, min(args.steps, 3)))
+
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            dt, v = _cpu_eval(CPU_SAMPLE_BATCH, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{CPU_SAMPLE_BATCH} of the 256 parameter sets (one full expectation+adjoint eval of that sub-batch, {dt:.1f} s), einsum-per-gate restatement of the pyqtorch path (oracle/statevec.py)"}
+        if do_cpu:
+            for k in cpu_samples[1:]:
+                dt, _, _ = _cpu_eval(list(range(k)), threads, rank)
+                cpu_runs.append({"batch_elements": k, "seconds": dt, "evals_per_s": k / dt})
+            best = max(cpu_runs, key=lambda r: r["batch_elements"])
+            cpu = {"value": best["evals_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{best['batch_elements']} of the 256 parameter sets (one full expectation+adjoint evaluation of that sub-batch, {best['seconds']:.1f} s), einsum-per-gate restatement of the pyqtorch path (oracle/statevec.py); the per-eval throughput at the other sample sizes is in `runs`",
+                   "runs": cpu_runs}
+        traffic, traffic_src = None, "no ncu --set full capture of THIS build (profiles/r02_traffic.json absent)"
+        tpath = ROOT / "profiles" / "r02_traffic.json"
+        if tpath.exists():
+            tj = json.loads(tpath.read_text())
+            stamp = ROOT / "qadence_b200" / "lib" / "libb200sv.so.srchash"
+            if stamp.exists() and tj.get("build_hash") == stamp.read_text().strip():
+                traffic, traffic_src = tj["adjoint_sweep_dram_bytes"], tj["source"]
+            else:
+                traffic_src = f"profiles/r02_traffic.json is of build {str(tj.get('build_hash', '?'))[:12]}, not of the one benched"
         n_gates = len(prog.ops)
+        hbm_bytes_step = (2 * fwd.n_sweeps + 4 * adj.n_sweeps + 4) * S
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,31 +466,39 @@ def main() -> None:
             "config": {
                 "workload": WORKLOAD,
                 "l2": "inputs larger than L2 (state 4 GiB per GPU)", "gates": n_gates, "params": n_slots,
-                "fwd_sweeps": fwd.n_sweeps, "adj_sweeps": adj.n_sweeps,
+                "fwd_sweeps": fwd.n_sweeps, "adj_sweeps": adj.n_sweeps, "lean_sweeps": [n_lean_f, n_lean_a],
                 "gates_per_s": world * n_gates * BATCH / (ms_per_step * 1e-3),
                 "parallelism": f"batch-sharded x{world}",
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+            "parity": parity,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "path": e2e_path,
                     "h2d_bytes_per_step": n_slots * BATCH * 8, "d2h_bytes_per_step": BATCH * 8 + n_slots * BATCH * 8},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "sweep_kernel<double,3,true,false> (adjoint sweep: psi+lambda read+write, gradient moments reduced)",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("lean_sweep_kernel<double, r=%d, m=%d, adjoint> (psi + lambda read and written once, gradient moments reduced)" % (adj.plan.cfg.r, adj.plan.cfg.m)) if n_lean_a else "sweep_kernel<double, adjoint>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 17.134e9, "traffic_source": "profiles/r01h_final_build.md: dram__bytes_read 8.592 GB + dram__bytes_write 8.541 GB for one adjoint sweep (ncu --set full)",
-                         "peak_source": peak_src, "bytes_per_launch": 4 * S, "avg_launch_ms": adj_avg,
-                         "forward_sweep": {"achieved": fwd_achieved, "frac": fwd_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": fwd_avg},
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "bytes_per_launch": 4 * S, "avg_launch_ms": adj_avg, "launch_ms": adj_ms,
+                         "forward_sweep": {"achieved": fwd_achieved, "frac": fwd_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": fwd_avg, "launch_ms": fwd_ms},
                          "light_sweep": {"what": "same kernel, one round of three merged 2x2 (6 gates) per sweep", "achieved": light_achieved,
                                          "frac": light_achieved / peak, "bytes_per_launch": 2 * S, "avg_launch_ms": light_ms},
-                         "fp64_pipe": {"what": "whole step: FP64 instructions of the merged 2x2 applications and gradient moments (counted from the plan) vs the DFMA rate measured by tools/ubench/dmma.cu",
+                         "other_kernels_ms": {**small, "frac_of_hbm": {"zero_state": S / (small["zero_state"] * 1e-3) / 1e9 / peak,
+                                                                        "pauli_expectation": S / (small["pauli_expectation"] * 1e-3) / 1e9 / peak,
+                                                                        "pauli_apply": 2 * S / (small["pauli_apply"] * 1e-3) / 1e9 / peak}},
+                         "fp64_pipe": {"what": "whole step: FP64 instructions of the normalised merged 2x2 applications (6 per amplitude forward, 12 backward) and gradient moments (6), counted from the plan, vs the DFMA rate measured by tools/ubench/dmma.cu",
                                        "merged_2x2_fwd": n_chain_f, "merged_2x2_adj": n_chain_a, "achieved": fp64_tflops, "peak": FP64_PEAK_TFLOPS,
                                        "unit": "TFLOP/s", "frac": fp64_tflops / FP64_PEAK_TFLOPS,
                                        "floor_ms_per_step": 2 * fp64_instr / (FP64_PEAK_TFLOPS * 1e12) * 1e3},
-                         "step": {"what": "algorithmic HBM bytes of the whole step (2S per forward sweep, 4S per adjoint sweep, S init, S <O>, 2S lambda=O psi): the tile-search planner trades bandwidth fraction per sweep for FEWER sweeps, i.e. fewer bytes per step",
-                                  "hbm_bytes_per_step": (2 * fwd.n_sweeps + 4 * adj.n_sweeps + 4) * S,
-                                  "hbm_floor_ms_per_step": (2 * fwd.n_sweeps + 4 * adj.n_sweeps + 4) * S / (peak * 1e9) * 1e3,
+                         "step": {"what": "algorithmic HBM bytes of the whole step (2S per forward sweep, 4S per adjoint sweep, S init, S <O>, 2S lambda = O psi)",
+                                  "hbm_bytes_per_step": hbm_bytes_step, "hbm_floor_ms_per_step": hbm_bytes_step / (peak * 1e9) * 1e3,
+                                  "frac": hbm_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak,
                                   "rounds_fwd": int(fwd.plan.sweeps["n_rounds"].sum()), "rounds_adj": int(adj.plan.sweeps["n_rounds"].sum())},
-                         "note": "complex128 sweeps with ~20 merged 2x2 per tile are FP64-pipe/issue bound on B200, not HBM bound (an FP64 instruction holds the issue port 2 cycles; DMMA runs at the same pipe rate), see DESIGN.md §4.1 and profiles/r01_fp64_microbench.md"},
+                         "note": ("what the counters say (profiles/r02_*.md): the heavy sweeps sit at neither roof. With ~20 merged 2x2 per tile the FP64 floor of a "
+                                  "sweep is ~2x its HBM floor, and the kernel reaches about half of the FP64 pipe: 4 warps per scheduler (register-limited) leave "
+                                  "dependency and shared-memory latencies exposed (issue slots ~60 % busy; an FP64 instruction takes two of them)")},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            **multi,
         }
         print(json.dumps(line))
     if world > 1:

@@ -234,7 +234,7 @@ class CompiledProgram:
         if key not in seg._plans:
             tc = cfg or TileConfig.default(dtype == torch.complex128, adjoint)
             plan = build_plan(seg.gates, self.n_qubits, self.slot_of, tc)
-            if (cfg is None and not adjoint and dtype == torch.complex128 and tc.m == 11 and self.n_qubits > 12
+            if (cfg is None and not adjoint and dtype == torch.complex128 and tc.m in (10, 11) and self.n_qubits > 12
                     and "B200SV_TILE_FWD_C128" not in os.environ and int((plan.sweeps["n_gen"] > 0).sum()) > 0):
                 # sweeps with generic-phase entries (controlled / diagonal gates, e.g. a QFT) run 17 % faster with
                 # 2^12-amplitude tiles; pure rotation + CNOT sweeps do not care (profiles/r01_multi_gpu.md)

@@ -98,7 +98,10 @@ class TileConfig:
         # measured on B200 (profiles/r01_tile_geometry.md): 64-byte runs (low = 2 for 16-byte amplitudes) already
         # stream at ~80 % of the HBM roofline, and every forced low bit costs a "hard" bit, i.e. more sweeps
         if dtype_is_c128:
-            return TileConfig(m=11, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3, adjoint=True)
+            # forward: 2^10-amplitude tiles with 64-thread CTAs (7 per SM) beat 2^11 / 128 threads (3 per SM, the tile
+            # alignment slack costs the fourth) although cfg2 then needs 9 sweeps instead of 8: 9 x 3.17 ms vs 8 x 3.87 ms
+            # (profiles/r02_lean_kernel.md)
+            return TileConfig(m=10, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3, adjoint=True)
         return TileConfig(m=12, r=4, low=2, fold=4) if not adjoint else TileConfig(m=11, r=3, low=2, fold=4, adjoint=True)
 
 

@@ -303,6 +303,29 @@ int b200sv_permute_bits(const void* in, void* out, int dtype, int n_qubits, int6
 int b200sv_apply_plan_peers(void* const* peer_states, int n_peers, int rank, int dtype, int n_total, const double* params,
                             const b200sv_plan* plan, int first_sweep, int last_sweep, void* workspace, void* stream);
 
+/* The adjoint counterpart: sweeps [first_sweep, last_sweep) walked backwards on psi AND lambda, both sharded the same way
+ * (`peer_lams[r]` = the lambda shard of rank r).  Every rank accumulates into ITS `grads` (double[n_rows], batch 1) the
+ * contributions 2 Re<lambda| dU |psi> of the tiles it processes; the caller all-reduces (SUM) the gradient vector over the
+ * ranks and puts a cross-GPU barrier on the stream between two sweeps.  Replaces
+ * pyqtorch.differentiation.AdjointExpectation.backward for a register that does not fit one GPU. */
+int b200sv_adjoint_plan_peers(void* const* peer_states, void* const* peer_lams, int n_peers, int rank, int dtype, int n_total,
+                              const double* params, double* grads, const b200sv_plan* plan, int first_sweep, int last_sweep,
+                              void* workspace, void* stream);
+
+/* Pauli-sum observable on a sharded register: out[0] += this rank's part of Re<psi| sum_t coef_t P_t |psi> (rows of its own
+ * shard; the partner amplitudes psi[i ^ xmask] of terms with X / Y on global qubits are read from the peer shards).  The
+ * caller all-reduces (SUM) `out`.  `coef` is `double[n_rows][1][2]`.  Replaces pyq.Observable.expectation
+ * (backends/pyqtorch/backend.py:208,249) on a sharded state. */
+int b200sv_pauli_expectation_peers(void* const* peer_states, int n_peers, int rank, int dtype, int n_total,
+                                   const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, double* out,
+                                   void* stream);
+
+/* out_local = alpha * (sum_t coef_t P_t psi) restricted to this rank's rows: lambda = O psi of the adjoint pass on a sharded
+ * register (out_local must not be one of the psi shards; barrier before — psi final everywhere — and after). */
+int b200sv_pauli_apply_peers(void* const* peer_states, int n_peers, int rank, void* out_local, int dtype, int n_total,
+                             const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, double alpha_re,
+                             double alpha_im, void* stream);
+
 /* Device memory that other processes of the box can map (cudaMalloc + CUDA IPC); `handle64` is 64 opaque bytes to ship to
  * the peers, who call b200sv_ipc_open (enables peer access lazily) and b200sv_ipc_close. */
 int b200sv_ipc_alloc(int64_t bytes, void** ptr, void* handle64);

@@ -39,6 +39,9 @@ EXPORTS = [
     "b200sv_bit_reverse",
     "b200sv_permute_bits",
     "b200sv_apply_plan_peers",
+    "b200sv_adjoint_plan_peers",
+    "b200sv_pauli_expectation_peers",
+    "b200sv_pauli_apply_peers",
     "b200sv_ipc_alloc",
     "b200sv_ipc_open",
     "b200sv_ipc_close",
@@ -112,6 +115,9 @@ def load() -> C.CDLL:
         "b200sv_bit_reverse": [vp, vp, i32, i32, i64, vp],
         "b200sv_permute_bits": [vp, vp, i32, i32, i64, vp, vp],
         "b200sv_apply_plan_peers": [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp],
+        "b200sv_adjoint_plan_peers": [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp],
+        "b200sv_pauli_expectation_peers": [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp],
+        "b200sv_pauli_apply_peers": [vp, i32, i32, vp, i32, i32, vp, i32, i32, vp, f64, f64, vp],
         "b200sv_ipc_alloc": [i64, vp, vp],
         "b200sv_ipc_open": [vp, vp],
         "b200sv_ipc_close": [vp],

@@ -133,38 +133,44 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
   return 0;
 }
 
-// forward sweeps [first, last) of a plan over the FULL index space of a register sharded over `n_peers` GPUs
-// (peer-memory addressing, see PeerTable in sweep.cuh); the caller separates sweeps by a cross-GPU barrier
-template <typename real>
-int run_plan_peers(void* const* peer_states, int n_peers, int rank, int n_total, const double* params, const b200sv_plan* plan,
-                   int first, int last, void* workspace, cudaStream_t st) {
+// sweeps [first, last) of a plan over the FULL index space of a register sharded over `n_peers` GPUs (peer-memory
+// addressing, see PeerTable in sweep.cuh), forward or adjoint; the caller separates sweeps by a cross-GPU barrier.  In the
+// adjoint direction every rank accumulates the gradient contributions of ITS tiles; the caller all-reduces `grads`.
+template <typename real, bool ADJ>
+int run_plan_peers(void* const* peer_states, void* const* peer_lams, int n_peers, int rank, int n_total, const double* params,
+                   double* grads, const b200sv_plan* plan, int first, int last, void* workspace, cudaStream_t st) {
   if (first >= last) return 0;
   int g = 0;
   while ((1 << g) < n_peers) ++g;
   if ((1 << g) != n_peers || n_peers > 16 || rank < 0 || rank >= n_peers) return B200SV_E_ARG;
+  for (int i = 0; i < n_peers; ++i)
+    if (!peer_states[i] || (ADJ && !peer_lams[i])) return B200SV_E_ARG;
   const Workspace<real> ws = carve_workspace<real>(workspace, plan, 1);
   const int x_first = plan->sweeps_host[first].first_exec;
   const int x_count = plan->sweeps_host[last - 1].first_exec + plan->sweeps_host[last - 1].n_exec - x_first;
   if (x_count > 0) {
     resolve_kernel<real><<<(unsigned)((x_count + 127) / 128), 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab,
-                                                                          x_first, x_count, 1ll, +1, 0);
+                                                                          x_first, x_count, 1ll, ADJ ? -1 : +1, ADJ ? 1 : 0);
     LAUNCH_CK();
+    if (ADJ) CK(cudaMemsetAsync(ws.mom + (size_t)x_first * 4, 0, (size_t)x_count * 4 * sizeof(double), st));
   }
-  for (int s = first; s < last; ++s) {
+  for (int k = 0; k < last - first; ++k) {
+    const int s = ADJ ? last - 1 - k : first + k;
     const b200sv_sweep& sw = plan->sweeps_host[s];
     if (sw.m < sw.r || sw.m - sw.r > 8 || sw.m > 12 || sw.n_outer != n_total - sw.m) return B200SV_E_ARG;
     PeerTable pt{};
-    for (int i = 0; i < n_peers; ++i) pt.p[i] = peer_states[i];
+    for (int i = 0; i < n_peers; ++i) { pt.p[i] = peer_states[i]; pt.pl[i] = ADJ ? peer_lams[i] : nullptr; }
     pt.n_local = n_total - g;
     const long long tiles = 1ll << sw.n_outer;
     const long long per_rank = (tiles + n_peers - 1) / n_peers;
     pt.tile_offset = per_rank * rank;
     pt.n_tiles = pt.tile_offset >= tiles ? 0 : (pt.tile_offset + per_rank > tiles ? tiles - pt.tile_offset : per_rank);
     const bool gen = sw.n_gen > 0;
+    void* lam0 = ADJ ? peer_lams[rank] : nullptr;
     int rc = B200SV_E_ARG;
-#define B200SV_LAUNCH_PEER(RR)                                                                                                           \
-  rc = gen ? launch_sweep<real, RR, false, true, true>(peer_states[rank], nullptr, params, nullptr, plan, ws, s, n_total, 1, 0, +1, st, &pt) \
-           : launch_sweep<real, RR, false, false, true>(peer_states[rank], nullptr, params, nullptr, plan, ws, s, n_total, 1, 0, +1, st, &pt)
+#define B200SV_LAUNCH_PEER(RR)                                                                                                            \
+  rc = gen ? launch_sweep<real, RR, ADJ, true, true>(peer_states[rank], lam0, params, grads, plan, ws, s, n_total, 1, 0, ADJ ? -1 : +1, st, &pt) \
+           : launch_sweep<real, RR, ADJ, false, true>(peer_states[rank], lam0, params, grads, plan, ws, s, n_total, 1, 0, ADJ ? -1 : +1, st, &pt)
     switch (sw.r) {
       case 3: B200SV_LAUNCH_PEER(3); break;
       case 4: B200SV_LAUNCH_PEER(4); break;
@@ -172,6 +178,11 @@ int run_plan_peers(void* const* peer_states, int n_peers, int rank, int n_total,
     }
 #undef B200SV_LAUNCH_PEER
     if (rc) return rc;
+  }
+  if (ADJ && x_count > 0) {
+    gradient_kernel<real><<<(unsigned)((x_count + 127) / 128), 128, 0, st>>>(plan->gates, plan->exec_leader, params, plan->consts, ws.xtab,
+                                                                           ws.mom, grads, x_first, x_count, 1ll);
+    LAUNCH_CK();
   }
   return 0;
 }
@@ -549,11 +560,13 @@ __device__ __forceinline__ void single_z_weight(const SingleZ& sz, unsigned long
 }
 
 // E[b] += Re sum_i conj(psi_i) sum_t c_t (-1)^{popc(i&z_t)} psi[i^x_t]
-template <typename c2>
+// PEER: psi is this rank's shard of a register sharded by its top qubits; the partner amplitude psi[i ^ x] of a term with
+// X / Y factors on global qubits lives in another rank's shard and is read through NVLink peer memory (pt.p[owner]).
+template <typename c2, bool PEER = false>
 __global__ void __launch_bounds__(EXP_THREADS)
 pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b200sv_pterm* __restrict__ terms,
                     int T, int n_single, const double* __restrict__ coef, long long coef_ld, double* __restrict__ out,
-                    unsigned long long index_hi, long long blocks_per_state) {
+                    unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
   __shared__ double red[32];
@@ -591,7 +604,13 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
       const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
       if (tm.x == 0ull) wr += sg * tm.cr;
       else {
-        const c2 q = p[i ^ (long long)tm.x];
+        c2 q;
+        if constexpr (PEER) {
+          const unsigned long long j = gi ^ tm.x;
+          q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
+        } else {
+          q = p[i ^ (long long)tm.x];
+        }
         const double cr = sg * tm.cr, ci = sg * tm.ci;
         sr += cr * (double)q.x - ci * (double)q.y;
         si += cr * (double)q.y + ci * (double)q.x;
@@ -605,12 +624,12 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
 }
 
 // out = alpha * (sum_t c_t P_t psi) + beta * acc
-template <typename c2>
+template <typename c2, bool PEER = false>
 __global__ void __launch_bounds__(256)
 pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
                    const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
                    long long coef_ld, double ar, double ai, double br, double bi,
-                   unsigned long long index_hi, long long blocks_per_state) {
+                   unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
   const long long b = blockIdx.x / blocks_per_state;
@@ -646,7 +665,13 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
       const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
       if (tm.x == 0ull) { wr += sg * tm.cr; wi += sg * tm.ci; }
       else {
-        const c2 q = p[i ^ (long long)tm.x];
+        c2 q;
+        if constexpr (PEER) {
+          const unsigned long long j = gi ^ tm.x;
+          q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
+        } else {
+          q = p[i ^ (long long)tm.x];
+        }
         const double cr = sg * tm.cr, ci = sg * tm.ci;
         sr += cr * (double)q.x - ci * (double)q.y;
         si += cr * (double)q.y + ci * (double)q.x;
@@ -1017,9 +1042,9 @@ int b200sv_pauli_expectation(const void* psi, int dtype, int n, int64_t batch, c
   const long long grid = bps * batch;
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (dtype == B200SV_C128)
-    pauli_expect_kernel<double2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps);
+    pauli_expect_kernel<double2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps, PeerTable{});
   else if (dtype == B200SV_C64)
-    pauli_expect_kernel<float2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps);
+    pauli_expect_kernel<float2><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, n_single, coef, coef_ld, out, index_hi, bps, PeerTable{});
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;
@@ -1037,9 +1062,9 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (br == 0.0 && bi == 0.0) acc = nullptr;
   if (dtype == B200SV_C128)
-    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps, PeerTable{});
   else if (dtype == B200SV_C64)
-    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps);
+    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps, PeerTable{});
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;
@@ -1140,7 +1165,7 @@ int b200sv_apply_dense(const void* psi, void* out, int dtype, int n, int64_t bat
 
 int b200sv_sample(const void* psi, int dtype, int n, int64_t batch, double* probs, double* tree,
                   const double* uniforms, int64_t n_shots, int64_t* out_idx, void* stream) {
-  if (!psi || !probs || !tree || !uniforms || !out_idx || batch <= 0 || n_shots <= 0 || n > 34) return B200SV_E_ARG;
+  if (!psi || !probs || !tree || !uniforms || !out_idx || batch <= 0 || n_shots <= 0 || n < 0 || n > 34) return B200SV_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
   const int chunk = (int)(N < 256 ? N : 256);
@@ -1181,6 +1206,7 @@ int b200sv_permute_bits(const void* in, void* out, int dtype, int n, int64_t bat
 }
 
 int b200sv_bit_reverse(const void* in, void* out, int dtype, int n, int64_t batch, void* stream) {
+  if (n < 0 || n > 40) return B200SV_E_ARG;
   int32_t perm[64];
   for (int j = 0; j < n; ++j) perm[j] = n - 1 - j;
   return b200sv_permute_bits(in, out, dtype, n, batch, perm, stream);
@@ -1284,16 +1310,93 @@ int b200sv_apply_plan_peers(void* const* peer_states, int n_peers, int rank, int
                             const b200sv_plan* plan, int first_sweep, int last_sweep, void* workspace, void* stream) {
   if (!peer_states || !plan || n_total < 1 || n_total > 48 || first_sweep < 0 || last_sweep > plan->n_sweeps) return B200SV_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B200SV_C128) return run_plan_peers<double>(peer_states, n_peers, rank, n_total, params, plan, first_sweep, last_sweep, workspace, st);
-  if (dtype == B200SV_C64) return run_plan_peers<float>(peer_states, n_peers, rank, n_total, params, plan, first_sweep, last_sweep, workspace, st);
+  if (!workspace) return B200SV_E_ARG;
+  if (dtype == B200SV_C128) return run_plan_peers<double, false>(peer_states, nullptr, n_peers, rank, n_total, params, nullptr, plan, first_sweep, last_sweep, workspace, st);
+  if (dtype == B200SV_C64) return run_plan_peers<float, false>(peer_states, nullptr, n_peers, rank, n_total, params, nullptr, plan, first_sweep, last_sweep, workspace, st);
   return B200SV_E_ARG;
+}
+
+int b200sv_adjoint_plan_peers(void* const* peer_states, void* const* peer_lams, int n_peers, int rank, int dtype, int n_total,
+                              const double* params, double* grads, const b200sv_plan* plan, int first_sweep, int last_sweep,
+                              void* workspace, void* stream) {
+  if (!peer_states || !peer_lams || !plan || !grads || !workspace || n_total < 1 || n_total > 48 || first_sweep < 0 ||
+      last_sweep > plan->n_sweeps)
+    return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200SV_C128) return run_plan_peers<double, true>(peer_states, peer_lams, n_peers, rank, n_total, params, grads, plan, first_sweep, last_sweep, workspace, st);
+  if (dtype == B200SV_C64) return run_plan_peers<float, true>(peer_states, peer_lams, n_peers, rank, n_total, params, grads, plan, first_sweep, last_sweep, workspace, st);
+  return B200SV_E_ARG;
+}
+
+static int peer_table(void* const* peer_states, int n_peers, int rank, int n_total, PeerTable* pt) {
+  int g = 0;
+  while ((1 << g) < n_peers) ++g;
+  if (!peer_states || (1 << g) != n_peers || n_peers > 16 || rank < 0 || rank >= n_peers || n_total <= g || n_total > 48) return B200SV_E_ARG;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_states[i]) return B200SV_E_ARG;
+    pt->p[i] = peer_states[i];
+  }
+  pt->n_local = n_total - g;
+  return 0;
+}
+
+int b200sv_pauli_expectation_peers(void* const* peer_states, int n_peers, int rank, int dtype, int n_total,
+                                   const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, double* out,
+                                   void* stream) {
+  PeerTable pt{};
+  if (int rc = peer_table(peer_states, n_peers, rank, n_total, &pt)) return rc;
+  if (!out || !coef) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms, n_single)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = pt.n_local;
+  const long long N = 1ll << n;
+  const long long per = EXP_THREADS * EXP_PER_THREAD;
+  const long long bps = (N + per - 1) / per;
+  if (bps > 2147483647ll) return B200SV_E_ARG;
+  const unsigned long long index_hi = (unsigned long long)rank << n;
+  if (dtype == B200SV_C128)
+    pauli_expect_kernel<double2, true><<<(unsigned)bps, EXP_THREADS, 0, st>>>((const double2*)peer_states[rank], n, 1, terms, n_terms, n_single, coef, 1, out, index_hi, bps, pt);
+  else if (dtype == B200SV_C64)
+    pauli_expect_kernel<float2, true><<<(unsigned)bps, EXP_THREADS, 0, st>>>((const float2*)peer_states[rank], n, 1, terms, n_terms, n_single, coef, 1, out, index_hi, bps, pt);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_pauli_apply_peers(void* const* peer_states, int n_peers, int rank, void* out_local, int dtype, int n_total,
+                             const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, double alpha_re,
+                             double alpha_im, void* stream) {
+  PeerTable pt{};
+  if (int rc = peer_table(peer_states, n_peers, rank, n_total, &pt)) return rc;
+  if (!out_local || !coef) return B200SV_E_ARG;
+  for (int i = 0; i < n_peers; ++i)
+    if (peer_states[i] == out_local) return B200SV_E_ARG;  // out of place
+  if (int rc = check_terms(n_terms, n_single)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = pt.n_local;
+  const long long N = 1ll << n;
+  const long long bps = (N + 1023) / 1024;
+  if (bps > 2147483647ll) return B200SV_E_ARG;
+  const unsigned long long index_hi = (unsigned long long)rank << n;
+  if (dtype == B200SV_C128)
+    pauli_apply_kernel<double2, true><<<(unsigned)bps, 256, 0, st>>>((const double2*)peer_states[rank], (double2*)out_local, nullptr, n, 1, terms, n_terms, n_single, coef, 1, alpha_re, alpha_im, 0.0, 0.0, index_hi, bps, pt);
+  else if (dtype == B200SV_C64)
+    pauli_apply_kernel<float2, true><<<(unsigned)bps, 256, 0, st>>>((const float2*)peer_states[rank], (float2*)out_local, nullptr, n, 1, terms, n_terms, n_single, coef, 1, alpha_re, alpha_im, 0.0, 0.0, index_hi, bps, pt);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
 }
 
 int b200sv_ipc_alloc(int64_t bytes, void** ptr, void* handle64) {
   if (bytes <= 0 || !ptr || !handle64) return B200SV_E_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CK(cudaMalloc(ptr, (size_t)bytes));
-  CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
+  const cudaError_t e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), *ptr);
+  if (e != cudaSuccess) {  // do not leak the allocation when the handle cannot be made
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return (int)e;
+  }
   return 0;
 }
 int b200sv_ipc_open(const void* handle64, void** ptr) {

@@ -447,6 +447,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // hazard; sweeps are separated by a cross-GPU barrier on the stream.
 struct PeerTable {
   void* p[16];            // state buffers of ranks 0..n_peers-1 (p[rank] is the local one)
+  void* pl[16];           // adjoint: the lambda shards of the same ranks
   int n_local;            // index bits below this are the offset inside a shard
   long long tile_offset;  // this GPU processes tiles [tile_offset, tile_offset + n_tiles) of the sweep
   long long n_tiles;
@@ -461,7 +462,6 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
              const ExecGate<real>* __restrict__ xtab, double* __restrict__ mom_g, int sweep_idx,
              int n, long long batch, unsigned long long index_hi, int dir_dbg, long long tiles_per_cta, int nbuf,
              const PeerTable peers) {
-  static_assert(!(PEER && ADJ), "peer-memory sweeps are forward only");
   constexpr int dir = ADJ ? -1 : +1;  // the adjoint kernel always walks backwards, the plain one forwards
   const int dbg = dir_dbg & 0xff;  // timing experiments only (B200SV_DBG): 1 = skip math, 2 = skip rounds
   using c2 = typename C2<real>::type;
@@ -496,6 +496,10 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
   const unsigned long long local_mask = PEER ? ((1ull << peers.n_local) - 1ull) : ~0ull;
   auto gaddr = [&](c2* base_ptr, unsigned long long idx) -> c2* {  // basis index -> address (through the peer table)
     if constexpr (PEER) return reinterpret_cast<c2*>(peers.p[idx >> peers.n_local]) + (idx & local_mask);
+    else return base_ptr + idx;
+  };
+  auto laddr = [&](c2* base_ptr, unsigned long long idx) -> c2* {  // the same for lambda
+    if constexpr (PEER) return reinterpret_cast<c2*>(peers.pl[idx >> peers.n_local]) + (idx & local_mask);
     else return base_ptr + idx;
   };
   const long long tile_first = (long long)blockIdx.x * tiles_per_cta;
@@ -557,7 +561,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
       const int e = i * nt + tid;
       const long long g = off + (long long)(t_lo[e & 63] + t_hi[e >> 6]);
       cp_async<sizeof(c2)>(dst + swz<real>(e), gaddr(psi_g, (unsigned long long)g));
-      if constexpr (ADJ) cp_async<sizeof(c2)>(dst + tile + swz<real>(e), lam_g + g);
+      if constexpr (ADJ) cp_async<sizeof(c2)>(dst + tile + swz<real>(e), laddr(lam_g, (unsigned long long)g));
     }
     cp_async_commit();
   };
@@ -784,7 +788,7 @@ sweep_kernel(typename C2<real>::type* __restrict__ psi_g, typename C2<real>::typ
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int e = i * nt + tid;
-        lam_g[state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6])] = tile_lam[swz<real>(e)];
+        *laddr(lam_g, (unsigned long long)(state_off + (long long)(cta_base + t_lo[e & 63] + t_hi[e >> 6]))) = tile_lam[swz<real>(e)];
       }
     }
   }

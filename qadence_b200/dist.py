@@ -377,7 +377,7 @@ class PeerShards:
         from . import cabi
 
         lib = cabi.load()
-        self.rank, self.world, self.device, self.dtype = rank, world, device, dtype
+        self.rank, self.world, self.device, self.dtype, self.group = rank, world, device, dtype, group
         elem = 16 if dtype == torch.complex128 else 8
         self.nbytes = (1 << n_local) * elem
         ptr = C.c_void_p()
@@ -393,16 +393,24 @@ class PeerShards:
             gathered = [mine]
         self._opened: list[int] = []
         ptrs = []
-        for r in range(world):
-            if r == rank:
-                ptrs.append(self.local_ptr)
-                continue
-            hb = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
-            p = C.c_void_p()
+        try:
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self.local_ptr)
+                    continue
+                hb = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
+                p = C.c_void_p()
+                with torch.cuda.device(device):
+                    cabi.check(lib.b200sv_ipc_open(hb, C.byref(p)), "ipc_open")
+                self._opened.append(int(p.value))
+                ptrs.append(int(p.value))
+        except Exception:  # do not leak the mappings opened so far nor the local allocation
             with torch.cuda.device(device):
-                cabi.check(lib.b200sv_ipc_open(hb, C.byref(p)), "ipc_open")
-            self._opened.append(int(p.value))
-            ptrs.append(int(p.value))
+                for q in self._opened:
+                    lib.b200sv_ipc_close(q)
+                lib.b200sv_ipc_free(self.local_ptr)
+            self.local_ptr, self._opened = None, []
+            raise
         self.ptrs = (C.c_void_p * world)(*ptrs)
         real = torch.as_tensor(_RawDeviceArray(self.local_ptr, self.nbytes // 8), device=device)
         pair = real.view(-1, 2) if dtype == torch.complex128 else real.view(torch.float32).view(-1, 2)
@@ -416,12 +424,12 @@ class PeerShards:
             return
         torch.cuda.synchronize(self.device)
         if self.world > 1:
-            dist.barrier()
+            dist.barrier(group=self.group)
         with torch.cuda.device(self.device):
             for p in self._opened:
                 lib.b200sv_ipc_close(p)
             if self.world > 1:
-                dist.barrier()
+                dist.barrier(group=self.group)
             lib.b200sv_ipc_free(self.local_ptr)
         self.local_ptr, self.state, self._opened = None, None, []
 
@@ -463,10 +471,15 @@ class PeerShardedSimulator:
         self.device = engine._dev(device)
         self.names = program.param_names
         self.slot_of = {nm: i for i, nm in enumerate(self.names)}
-        cfg = TileConfig.default(dtype == torch.complex128, False)
-        # (2^12-amplitude tiles, B200SV_TILE_FWD_C128=12,4,2, are 15 % faster up to n = 31 but slowed one straddling sweep of
-        #  the 36-qubit run from ~0.4 s to 1.9 s — see profiles/r01_multi_gpu.md; the batch default 2^11 is kept)
+        fold = 3 if dtype == torch.complex128 else 4
+        # 2^11-amplitude tiles, generic kernels (`lean=False`: uncontrolled diagonal gates on global qubits stay free
+        # "external diagonals" instead of asking for their qubit as a tile bit, and the NVLink traffic stays what
+        # profiles/r01_multi_gpu.md measured).  (2^12 tiles are 15 % faster up to n = 31 but slowed one straddling sweep of the
+        # 36-qubit run from ~0.4 s to 1.9 s.)
+        cfg = TileConfig(m=11 if dtype == torch.complex128 else 12, r=4, low=2, fold=fold, lean=False)
         self.plan = DevicePlan(build_plan(list(program.ops), self.n, self.slot_of, cfg, packer="greedy"), self.device)
+        self._plan_adj: DevicePlan | None = None
+        self._lam: PeerShards | None = None
         self.shards = PeerShards(self.n_local, dtype, rank, world, self.device, group)
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.time_sweeps = False  # diagnostics: per-sweep CUDA-event times (incl. the barrier) in `sweep_ms`
@@ -516,5 +529,78 @@ class PeerShardedSimulator:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
+    # ---- observables and adjoint gradients on the sharded register -------------------------------
+    def _compiled(self, obs: PauliSum):
+        from . import engine
+
+        if obs.n_qubits != self.n:
+            raise ValueError("observable and register sizes differ")
+        return engine.CompiledPauliSum.build(obs)
+
+    def expectation(self, values: Mapping[str, Tensor] | None, obs: PauliSum, run: bool = True) -> Tensor:
+        """Re<ψ|O|ψ> of ANY Pauli-sum observable (constant coefficients): every rank sums over the rows of its shard — partner
+        amplitudes of X / Y factors on global qubits are read from the peer shards over NVLink — then one all-reduce of a
+        scalar.  `run=False` reuses the state left by the last `run`."""
+        from . import cabi, engine
+
+        if run:
+            self.run(values)
+        cps = self._compiled(obs)
+        if cps.is_parametric:
+            raise NotImplementedError("parametric observable coefficients are not supported on a sharded register")
+        dev = self.device
+        coef = cps.coef({}, dev)
+        cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+        out = torch.zeros(1, dtype=torch.float64, device=dev)
+        rc = cabi.load().b200sv_pauli_expectation_peers(self.shards.ptrs, self.world, self.rank, engine._DT[self.dtype], self.n,
+                                                        cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), out.data_ptr(),
+                                                        engine._stream_ptr(dev))
+        cabi.check(rc, "pauli_expectation_peers")
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def expectation_and_grads(self, values: Mapping[str, Tensor] | None, obs: PauliSum) -> tuple[Tensor, Tensor]:
+        """(E [1], dE/dθ [n_params]) by the adjoint method on the sharded register: λ = Oψ into a second set of peer-mapped
+        shards, then the sweeps walked backwards on ψ and λ (`b200sv_adjoint_plan_peers`, one barrier per sweep); every
+        rank reduces the gradient moments of its own tiles and ONE all-reduce sums the `[n_params]` vector."""
+        from . import cabi, engine
+        from .engine import DevicePlan
+        from .plan import TileConfig, build_plan
+
+        lib = cabi.load()
+        dev = self.device
+        e = self.expectation(values, obs, run=True)
+        if self._lam is None:
+            self._lam = PeerShards(self.n_local, self.dtype, self.rank, self.world, dev, self.group)
+        if self._plan_adj is None:
+            fold = 3 if self.dtype == torch.complex128 else 4
+            cfg = TileConfig(m=10 if self.dtype == torch.complex128 else 11, r=3, low=2, fold=fold, adjoint=True, lean=False)
+            self._plan_adj = DevicePlan(build_plan(list(self.program.ops), self.n, self.slot_of, cfg, packer="greedy"), dev)
+        cps = self._compiled(obs)
+        coef = cps.coef({}, dev)
+        cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+        st = engine._stream_ptr(dev)
+        rc = lib.b200sv_pauli_apply_peers(self.shards.ptrs, self.world, self.rank, self._lam.state.data_ptr(), engine._DT[self.dtype], self.n,
+                                          cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), 1.0, 0.0, st)
+        cabi.check(rc, "pauli_apply_peers")
+        self._barrier()  # every λ shard is complete before a sweep reads it through the peer table
+        ptable = engine.pack_params(self.names, values or {}, 1, dev)
+        grads = torch.zeros(max(1, len(self.names)), 1, dtype=torch.float64, device=dev)
+        dp = self._plan_adj
+        ws = dp.workspace(self.dtype, 1, True).data_ptr()
+        for s in range(dp.n_sweeps - 1, -1, -1):
+            rc = lib.b200sv_adjoint_plan_peers(self.shards.ptrs, self._lam.ptrs, self.world, self.rank, engine._DT[self.dtype], self.n,
+                                               ptable.data_ptr(), grads.data_ptr(), C.byref(dp.struct), s, s + 1, ws, st)
+            cabi.check(rc, "adjoint_plan_peers")
+            self._barrier()
+        g = grads[:, 0].clone()
+        if self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        return e, g
+
     def close(self) -> None:
+        if self._lam is not None:
+            self._lam.close()
+            self._lam = None
         self.shards.close()

@@ -83,6 +83,69 @@ def test_rank_bit_addressing_with_peer_buffers_on_one_device(world: int) -> None
     assert (got - want).abs().max().item() < 1e-12
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_expectation_and_adjoint_gradients_on_one_device(world: int) -> None:
+    """`b200sv_pauli_expectation_peers`, `b200sv_pauli_apply_peers` and `b200sv_adjoint_plan_peers` with `world` psi and
+    lambda shards on THIS device (the "ranks" take turns on one stream): a general Pauli-sum observable with X / Y factors
+    on GLOBAL qubits, and the adjoint gradients of every parameter, against the single-device engine path."""
+    import ctypes as C
+
+    from qadence_b200 import cabi, engine
+    from qadence_b200.engine import DevicePlan, _DT, _stream_ptr
+    from qadence_b200.plan import TileConfig, build_plan
+    from qadence_b200.program import PauliSum, PauliTerm
+
+    n = 16
+    g = world.bit_length() - 1
+    n_local = n - g
+    prog = _program(n)
+    gen = torch.Generator().manual_seed(9)
+    values = {nm: (6.28 * torch.rand(1, generator=gen, dtype=torch.float64)).requires_grad_(True) for nm in prog.param_names}
+    obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)]
+                   + [PauliTerm(0.7, (), ((0, "X"), (n - 1, "Y"))), PauliTerm(-0.4, (), ((1, "Y"), (5, "Z"))), PauliTerm(0.3, (), ((0, "Z"), (1, "Z")))])
+    dev = torch.device("cuda:0")
+    cp = engine.CompiledProgram(prog)
+    want = engine.expectation(cp, [engine.CompiledObservable(obs)], values, device=dev)
+    want.sum().backward()
+    want_g = torch.stack([values[nm].grad.reshape(()) for nm in prog.param_names])
+
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    fplan = DevicePlan(build_plan(list(prog.ops), n, slot_of, TileConfig(m=11, r=4, low=2, fold=3, lean=False), packer="greedy"), dev)
+    aplan = DevicePlan(build_plan(list(prog.ops), n, slot_of, TileConfig(m=10, r=3, low=2, fold=3, adjoint=True, lean=False), packer="greedy"), dev)
+    psi = [torch.zeros(1, 1 << n_local, dtype=torch.complex128, device=dev) for _ in range(world)]
+    lam = [torch.zeros(1, 1 << n_local, dtype=torch.complex128, device=dev) for _ in range(world)]
+    psi[0][0, 0] = 1.0
+    pp = (C.c_void_p * world)(*[t.data_ptr() for t in psi])
+    pl = (C.c_void_p * world)(*[t.data_ptr() for t in lam])
+    detached = {k: v.detach() for k, v in values.items()}
+    tab = engine.pack_params(prog.param_names, detached, 1, dev)
+    lib = cabi.load()
+    st = _stream_ptr(dev)
+    dt = _DT[torch.complex128]
+    wsf = fplan.workspace(torch.complex128, 1, False)
+    for s in range(fplan.n_sweeps):
+        for rank in range(world):
+            assert lib.b200sv_apply_plan_peers(pp, world, rank, dt, n, tab.data_ptr(), C.byref(fplan.struct), s, s + 1, wsf.data_ptr(), st) == 0
+    cps = engine.CompiledPauliSum.build(obs)
+    coef = torch.view_as_real(cps.coef({}, dev).to(torch.complex128).contiguous())
+    e = torch.zeros(1, dtype=torch.float64, device=dev)
+    for rank in range(world):  # the all-reduce of the per-rank parts
+        assert lib.b200sv_pauli_expectation_peers(pp, world, rank, dt, n, cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, coef.data_ptr(), e.data_ptr(), st) == 0
+    assert abs(e.item() - want.item()) < 1e-11
+    for rank in range(world):
+        assert lib.b200sv_pauli_apply_peers(pp, world, rank, lam[rank].data_ptr(), dt, n, cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, coef.data_ptr(), 1.0, 0.0, st) == 0
+    grads = [torch.zeros(len(prog.param_names), 1, dtype=torch.float64, device=dev) for _ in range(world)]
+    wsa = [aplan.workspace(torch.complex128, 1, True).clone() for _ in range(world)]  # one workspace per "rank" (moment accumulators)
+    for s in range(aplan.n_sweeps - 1, -1, -1):
+        for rank in range(world):
+            rc = lib.b200sv_adjoint_plan_peers(pp, pl, world, rank, dt, n, tab.data_ptr(), grads[rank].data_ptr(), C.byref(aplan.struct), s, s + 1, wsa[rank].data_ptr(), st)
+            assert rc == 0
+    got_g = sum(gr[:, 0] for gr in grads).cpu()
+    assert (got_g - want_g).abs().max().item() < 1e-10
+    back = torch.cat([t.reshape(-1) for t in psi])
+    assert abs(back[0].item() - 1.0) < 1e-10 and back[1:].abs().max().item() < 1e-10  # psi walked back to |0...0>
+
+
 def test_traffic_model_counts_global_bits() -> None:
     from qadence_b200.dist import peer_traffic
     from qadence_b200.plan import TileConfig, build_plan

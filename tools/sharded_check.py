@@ -37,6 +37,7 @@ ap.add_argument("--depth", type=int, default=1)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--peer", action="store_true", help="fuse the exchanges into the sweeps (NVLink peer-memory addressing)")
+ap.add_argument("--grad", action="store_true", help="(with --peer) also expectation of a general Pauli sum + adjoint gradients of every parameter on the sharded register; with --verify compared with the single-GPU engine")
 args = ap.parse_args()
 rank, world = qdist.init_from_env("nccl")
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -84,6 +85,35 @@ if args.verify:
     if world > 1:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
     err = float(e.item())
+grad_info = None
+if args.grad and args.peer:
+    from qadence_b200.program import PauliSum, PauliTerm
+
+    obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.7, (), ((0, "X"), (n - 1, "Y"))), PauliTerm(-0.4, (), ((1, "Y"), (n // 2, "Z")))])
+    e_sh, g_sh = sim.expectation_and_grads(values, obs)  # warm-up (lambda shards, adjoint plan)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e_sh, g_sh = sim.expectation_and_grads(values, obs)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    grad_info = {"expectation": float(e_sh.item()), "n_params": int(g_sh.numel()), "ms_expectation_and_grads": float(t.item()),
+                 "adjoint_sweeps": sim._plan_adj.n_sweeps}
+    if args.verify:
+        err_e = err_g = 0.0
+        if rank == 0:
+            leaf = {k: v.clone().requires_grad_(True) for k, v in values.items()}
+            ref = engine.expectation(engine.CompiledProgram(prog), [engine.CompiledObservable(obs)], leaf, device=dev)
+            ref.sum().backward()
+            ref_g = torch.stack([leaf[nm].grad.reshape(()) for nm in prog.param_names]).to(dev)
+            err_e = abs(float(ref.item()) - float(e_sh.item()))
+            err_g = float((ref_g - g_sh).abs().max().item())
+        grad_info.update({"abs_err_expectation_vs_single_gpu": err_e, "max_abs_err_gradient_vs_single_gpu": err_g})
 if rank == 0:
     S_local = (1 << sim.n_local) * 16
     n_sweeps = sim.n_sweeps()
@@ -92,7 +122,7 @@ if rank == 0:
         "mode": "peer-memory sweeps" if args.peer else "all-to-all exchanges",
         "exchanges": sim.stats["exchanges"], "nvlink_bytes_sent_per_rank": sim.stats["nvlink_bytes_per_rank_per_direction"] if args.peer else sim.bytes_sent,
         "global_bits_per_sweep": sim.stats.get("global_bits_per_sweep"), "sweep_ms_rank0": sweep_ms,
-        "local_sweep_bytes": 2 * S_local * n_sweeps, "norm": norm, "total_magnetization": mag, "max_abs_err_vs_single_gpu": err,
+        "local_sweep_bytes": 2 * S_local * n_sweeps, "norm": norm, "total_magnetization": mag, "max_abs_err_vs_single_gpu": err, "grad": grad_info,
     }))
 if args.peer:
     del st

@@ -516,7 +516,6 @@ struct SingleZ {
 
 constexpr int MAX_TERMS_SMEM = 1024;
 constexpr int EXP_THREADS = 256;
-constexpr int EXP_PER_THREAD = 8;
 
 __device__ __forceinline__ void resolve_terms(TermS* sh, const b200sv_pterm* terms, int T,
                                               const double* coef, long long coef_ld, long long b,
@@ -559,6 +558,37 @@ __device__ __forceinline__ void single_z_weight(const SingleZ& sz, unsigned long
   wr = sz.c0r - 2.0 * ar; wi = sz.c0i - 2.0 * ai;
 }
 
+// Index decomposition of the streaming Pauli kernels: i = blk * 2^14 + g * 2^11 + k * 2^8 + tid  (g, k < 8).  The single-Z
+// part of a Pauli sum is additive over index bits, w(i) = c0 + d(tid) + d(k << 8) + d(g << 11) + d(blk << 14 | index_hi) with
+// d(x) = -2 * sum_{bits set in x} c_bit: the four pieces are computed once per CTA (tables in shared memory), so a
+// total_magnetization-like observable costs three additions per amplitude instead of a loop over the set bits.
+constexpr int PK_K = 8, PK_G = 8, PK_TILE = EXP_THREADS * PK_K * PK_G;
+
+struct DiagTables {
+  double kr[PK_K], ki[PK_K], gr[PK_G], gi[PK_G], br, bi;
+};
+
+__device__ __forceinline__ void diag_tables(const SingleZ& sz, DiagTables* dt, long long blk, unsigned long long index_hi, int n_single,
+                                            double& tr, double& ti) {
+  tr = 0.0; ti = 0.0;
+  if (n_single > 0) {
+    double wr, wi;
+    single_z_weight(sz, (unsigned long long)threadIdx.x, wr, wi);
+    tr = wr - sz.c0r; ti = wi - sz.c0i;
+  }
+  if (threadIdx.x < PK_K + PK_G + 1) {
+    const int t = threadIdx.x;
+    unsigned long long x = t < PK_K ? ((unsigned long long)t << 8) : t < PK_K + PK_G ? ((unsigned long long)(t - PK_K) << 11)
+                                                                                     : (((unsigned long long)blk << 14) | index_hi);
+    double wr = 0.0, wi = 0.0;
+    if (n_single > 0) single_z_weight(sz, x, wr, wi);
+    else { wr = sz.c0r; wi = sz.c0i; }
+    if (t < PK_K) { dt->kr[t] = wr - sz.c0r; dt->ki[t] = wi - sz.c0i; }
+    else if (t < PK_K + PK_G) { dt->gr[t - PK_K] = wr - sz.c0r; dt->gi[t - PK_K] = wi - sz.c0i; }
+    else { dt->br = wr; dt->bi = wi; }  // includes c0 once
+  }
+}
+
 // E[b] += Re sum_i conj(psi_i) sum_t c_t (-1)^{popc(i&z_t)} psi[i^x_t]
 // PEER: psi is this rank's shard of a register sharded by its top qubits; the partner amplitude psi[i ^ x] of a term with
 // X / Y factors on global qubits lives in another rank's shard and is read through NVLink peer memory (pt.p[owner]).
@@ -569,55 +599,65 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
                     unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
+  __shared__ DiagTables dt;
   __shared__ double red[32];
   const long long b = blockIdx.x / blocks_per_state;
   const long long blk = blockIdx.x % blocks_per_state;
   resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
   T -= n_single;
+  double tr, ti;
+  diag_tables(sz, &dt, blk, index_hi, n_single, tr, ti);
+  __syncthreads();
   const long long N = 1ll << n;
   const c2* p = psi + (b << n);
   double acc = 0.0;
-  const long long base = blk * (long long)(EXP_THREADS * EXP_PER_THREAD);
-  double w0r = 0.0, w0i = 0.0;  // single-Z weight of this thread's k = 0 index
-  if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
-  // all of the thread's amplitudes are requested before the first one is used: the kernel is a pure stream (1·S bytes) and
-  // needs EXP_PER_THREAD independent 16-byte loads in flight per thread to fill the HBM pipe
-  c2 av[EXP_PER_THREAD];
+  const long long base = blk * (long long)PK_TILE + threadIdx.x;
+  const double wt = tr + dt.br;
+#pragma unroll 1
+  for (int g = 0; g < PK_G; ++g) {
+    const long long gbase = base + (long long)g * (EXP_THREADS * PK_K);
+    if (gbase >= N) break;
+    // all of the group's amplitudes are requested before the first one is used: the kernel is a pure stream (1·S bytes)
+    // and needs several independent 16-byte loads in flight per thread to fill the HBM pipe
+    c2 av[PK_K];
 #pragma unroll
-  for (int k = 0; k < EXP_PER_THREAD; ++k) {
-    const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
-    av[k].x = 0; av[k].y = 0;
-    if (i < N) av[k] = __ldcs(p + i);
-  }
-#pragma unroll
-  for (int k = 0; k < EXP_PER_THREAD; ++k) {
-    const long long i = base + (long long)k * EXP_THREADS + threadIdx.x;
-    if (i >= N) break;
-    const c2 a = av[k];
-    const unsigned long long gi = (unsigned long long)i | index_hi;
-    double wr = w0r;             // diagonal weight (k only changes the bits above log2(EXP_THREADS))
-    if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * EXP_THREADS, kr, ki); wr += kr - sz.c0r; }
-    double sr = 0.0, si = 0.0;   // off-diagonal sum
-    for (int t = 0; t < T; ++t) {
-      const TermS tm = sh[t];
-      const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
-      if (tm.x == 0ull) wr += sg * tm.cr;
-      else {
-        c2 q;
-        if constexpr (PEER) {
-          const unsigned long long j = gi ^ tm.x;
-          q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
-        } else {
-          q = p[i ^ (long long)tm.x];
-        }
-        const double cr = sg * tm.cr, ci = sg * tm.ci;
-        sr += cr * (double)q.x - ci * (double)q.y;
-        si += cr * (double)q.y + ci * (double)q.x;
-      }
+    for (int k = 0; k < PK_K; ++k) {
+      const long long i = gbase + (long long)k * EXP_THREADS;
+      av[k].x = 0; av[k].y = 0;
+      if (i < N) av[k] = __ldcs(p + i);
     }
-    const double ax = a.x, ay = a.y;
-    acc += wr * (ax * ax + ay * ay) + (ax * sr + ay * si);
+    const double wg = wt + dt.gr[g];
+#pragma unroll
+    for (int k = 0; k < PK_K; ++k) {
+      const long long i = gbase + (long long)k * EXP_THREADS;
+      if (i >= N) break;
+      const c2 a = av[k];
+      double wr = wg + dt.kr[k];  // diagonal weight of the single-Z terms
+      double sr = 0.0, si = 0.0;  // off-diagonal sum
+      if (T > 0) {
+        const unsigned long long gi = (unsigned long long)i | index_hi;
+        for (int t = 0; t < T; ++t) {
+          const TermS tm = sh[t];
+          const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
+          if (tm.x == 0ull) wr += sg * tm.cr;
+          else {
+            c2 q;
+            if constexpr (PEER) {
+              const unsigned long long j = gi ^ tm.x;
+              q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
+            } else {
+              q = p[i ^ (long long)tm.x];
+            }
+            const double cr = sg * tm.cr, ci = sg * tm.ci;
+            sr += cr * (double)q.x - ci * (double)q.y;
+            si += cr * (double)q.y + ci * (double)q.x;
+          }
+        }
+      }
+      const double ax = a.x, ay = a.y;
+      acc += wr * (ax * ax + ay * ay) + (ax * sr + ay * si);
+    }
   }
   acc = block_reduce_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(&out[b], acc);
@@ -625,68 +665,78 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
 
 // out = alpha * (sum_t c_t P_t psi) + beta * acc
 template <typename c2, bool PEER = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(EXP_THREADS)
 pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
                    const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
                    long long coef_ld, double ar, double ai, double br, double bi,
                    unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
+  __shared__ DiagTables dt;
   const long long b = blockIdx.x / blocks_per_state;
   const long long blk = blockIdx.x % blocks_per_state;
   resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
   T -= n_single;
+  double tr, ti;
+  diag_tables(sz, &dt, blk, index_hi, n_single, tr, ti);
+  __syncthreads();
   const long long N = 1ll << n;
   const c2* p = psi + (b << n);
-  const long long base = blk * (long long)(256 * 4);
-  double w0r = 0.0, w0i = 0.0;
-  if (n_single > 0) single_z_weight(sz, ((unsigned long long)(base + threadIdx.x)) | index_hi, w0r, w0i);
-  c2 av[4], zv[4];  // loads first (memory-level parallelism), see pauli_expect_kernel
+  const long long base = blk * (long long)PK_TILE + threadIdx.x;
+  const double wtr = tr + dt.br, wti = ti + dt.bi;
+#pragma unroll 1
+  for (int g = 0; g < PK_G; ++g) {
+    const long long gbase = base + (long long)g * (EXP_THREADS * PK_K);
+    if (gbase >= N) break;
+    c2 av[PK_K], zv[PK_K];  // loads first (memory-level parallelism), see pauli_expect_kernel
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long i = base + (long long)k * 256 + threadIdx.x;
-    av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0;
-    if (i < N) {
-      av[k] = p[i];
-      if (acc != nullptr) zv[k] = acc[(b << n) + i];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const long long i = base + (long long)k * 256 + threadIdx.x;
-    if (i >= N) break;
-    const unsigned long long gi = (unsigned long long)i | index_hi;
-    const c2 a = av[k];
-    double wr = w0r, wi = w0i, sr = 0.0, si = 0.0;
-    if (n_single > 0) { double kr, ki; single_z_weight(sz, (unsigned long long)k * 256, kr, ki); wr += kr - sz.c0r; wi += ki - sz.c0i; }
-    for (int t = 0; t < T; ++t) {
-      const TermS tm = sh[t];
-      const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
-      if (tm.x == 0ull) { wr += sg * tm.cr; wi += sg * tm.ci; }
-      else {
-        c2 q;
-        if constexpr (PEER) {
-          const unsigned long long j = gi ^ tm.x;
-          q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
-        } else {
-          q = p[i ^ (long long)tm.x];
-        }
-        const double cr = sg * tm.cr, ci = sg * tm.ci;
-        sr += cr * (double)q.x - ci * (double)q.y;
-        si += cr * (double)q.y + ci * (double)q.x;
+    for (int k = 0; k < PK_K; ++k) {
+      const long long i = gbase + (long long)k * EXP_THREADS;
+      av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0;
+      if (i < N) {
+        av[k] = __ldcs(p + i);
+        if (acc != nullptr) zv[k] = acc[(b << n) + i];
       }
     }
-    sr += wr * (double)a.x - wi * (double)a.y;
-    si += wr * (double)a.y + wi * (double)a.x;
-    double rr = ar * sr - ai * si, ri = ar * si + ai * sr;
-    if (acc != nullptr) {
-      const c2 z = zv[k];
-      rr += br * (double)z.x - bi * (double)z.y;
-      ri += br * (double)z.y + bi * (double)z.x;
+    const double wgr = wtr + dt.gr[g], wgi = wti + dt.gi[g];
+#pragma unroll
+    for (int k = 0; k < PK_K; ++k) {
+      const long long i = gbase + (long long)k * EXP_THREADS;
+      if (i >= N) break;
+      const c2 a = av[k];
+      double wr = wgr + dt.kr[k], wi = wgi + dt.ki[k], sr = 0.0, si = 0.0;
+      if (T > 0) {
+        const unsigned long long gi = (unsigned long long)i | index_hi;
+        for (int t = 0; t < T; ++t) {
+          const TermS tm = sh[t];
+          const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
+          if (tm.x == 0ull) { wr += sg * tm.cr; wi += sg * tm.ci; }
+          else {
+            c2 q;
+            if constexpr (PEER) {
+              const unsigned long long j = gi ^ tm.x;
+              q = reinterpret_cast<const c2*>(pt.p[j >> pt.n_local])[j & ((1ull << pt.n_local) - 1ull)];
+            } else {
+              q = p[i ^ (long long)tm.x];
+            }
+            const double cr = sg * tm.cr, ci = sg * tm.ci;
+            sr += cr * (double)q.x - ci * (double)q.y;
+            si += cr * (double)q.y + ci * (double)q.x;
+          }
+        }
+      }
+      sr += wr * (double)a.x - wi * (double)a.y;
+      si += wr * (double)a.y + wi * (double)a.x;
+      double rr = ar * sr - ai * si, ri = ar * si + ai * sr;
+      if (acc != nullptr) {
+        const c2 z = zv[k];
+        rr += br * (double)z.x - bi * (double)z.y;
+        ri += br * (double)z.y + bi * (double)z.x;
+      }
+      c2 o; o.x = rr; o.y = ri;
+      __stcs(out + (b << n) + i, o);
     }
-    c2 o; o.x = rr; o.y = ri;
-    out[(b << n) + i] = o;
   }
 }
 
@@ -1037,7 +1087,7 @@ int b200sv_pauli_expectation(const void* psi, int dtype, int n, int64_t batch, c
   if (int rc = check_terms(n_terms, n_single)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
-  const long long per = EXP_THREADS * EXP_PER_THREAD;
+  const long long per = PK_TILE;
   const long long bps = (N + per - 1) / per;
   const long long grid = bps * batch;
   if (grid > 2147483647ll) return B200SV_E_ARG;
@@ -1057,7 +1107,7 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
   if (int rc = check_terms(n_terms, n_single)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const long long N = 1ll << n;
-  const long long bps = (N + 1023) / 1024;
+  const long long bps = (N + PK_TILE - 1) / PK_TILE;
   const long long grid = bps * batch;
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (br == 0.0 && bi == 0.0) acc = nullptr;
@@ -1350,7 +1400,7 @@ int b200sv_pauli_expectation_peers(void* const* peer_states, int n_peers, int ra
   cudaStream_t st = (cudaStream_t)stream;
   const int n = pt.n_local;
   const long long N = 1ll << n;
-  const long long per = EXP_THREADS * EXP_PER_THREAD;
+  const long long per = PK_TILE;
   const long long bps = (N + per - 1) / per;
   if (bps > 2147483647ll) return B200SV_E_ARG;
   const unsigned long long index_hi = (unsigned long long)rank << n;
@@ -1375,7 +1425,7 @@ int b200sv_pauli_apply_peers(void* const* peer_states, int n_peers, int rank, vo
   cudaStream_t st = (cudaStream_t)stream;
   const int n = pt.n_local;
   const long long N = 1ll << n;
-  const long long bps = (N + 1023) / 1024;
+  const long long bps = (N + PK_TILE - 1) / PK_TILE;
   if (bps > 2147483647ll) return B200SV_E_ARG;
   const unsigned long long index_hi = (unsigned long long)rank << n;
   if (dtype == B200SV_C128)

@@ -12,6 +12,8 @@
 #include <mutex>
 #include <type_traits>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (NVTX v3): ranges cost nothing unless a tool injects itself
+
 #include "b200sv.h"
 #include "sweep.cuh"
 #include "lean.cuh"
@@ -31,6 +33,21 @@ using namespace b200sv;
   } while (0)
 
 namespace {
+
+// One NVTX range per sweep launch (B200SV_NVTX=1): "b200sv fwd sweep 3 lean-tma m10 r4 rounds 6" — SURVEY.md §5's tracing hook.
+struct SweepRange {
+  bool on;
+  SweepRange(const char* dir, int s, const b200sv_sweep& sw, const char* kind) {
+    static const bool enabled = [] { const char* e = getenv("B200SV_NVTX"); return e && atoi(e) != 0; }();
+    on = enabled;
+    if (on) {
+      char name[160];
+      snprintf(name, sizeof(name), "b200sv %s sweep %d %s m%d r%d rounds %d entries %d", dir, s, kind, sw.m, sw.r, sw.n_rounds, sw.n_exec);
+      nvtxRangePushA(name);
+    }
+  }
+  ~SweepRange() { if (on) nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // sweep launchers
@@ -109,6 +126,7 @@ int launch_sweep(void* psi, void* lam, const double* params, double* grads, cons
                  const PeerTable* peers = nullptr) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
+  SweepRange nvtx_range(ADJ ? "adj" : "fwd", s, sw, PEER ? "generic-peer" : "generic");
   static const int persistent = [] { const char* e = getenv("B200SV_PERSISTENT"); return e ? atoi(e) : B200SV_PERSISTENT_DEFAULT; }();
   const int nbuf = persistent == 1 ? 2 : 1;  // 1: persistent + double buffer, 2: persistent, single buffer (table reuse only)
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
@@ -277,6 +295,7 @@ int launch_lean(void* psi, void* lam, const b200sv_plan* plan, const Workspace<r
                 uint64_t index_hi, cudaStream_t st) {
   using c2 = typename C2<real>::type;
   const b200sv_sweep& sw = plan->sweeps_host[s];
+  SweepRange nvtx_range(ADJ ? "adj" : "fwd", s, sw, sw.io_mode == B200SV_IO_LEAN_TMA ? "lean-tma" : "lean-gather");
   static const int dbg_flags = [] { const char* e = getenv("B200SV_DBG"); return e ? (atoi(e) & 0xff) : 0; }();
   static const int occ_env = [] { const char* e = getenv("B200SV_LEAN_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const bool tma = sw.io_mode == B200SV_IO_LEAN_TMA;

@@ -310,7 +310,7 @@ class QubitShardedSimulator:
 
         lib = cabi.load()
         values = values or {}
-        st = self.zero_state(dtype) if state is None else state
+        st = self.zero_state(dtype) if state is None else state.clone()  # never evolve the caller's tensor in place
         ptable = engine.pack_params(self.names, values, 1, self.device)
         self.bytes_sent = 0
         for i, step in enumerate(self.layout.steps):
@@ -494,7 +494,7 @@ class PeerShardedSimulator:
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)
 
-    def run(self, values: Mapping[str, Tensor] | None = None) -> Tensor:
+    def run(self, values: Mapping[str, Tensor] | None = None, ptable: Tensor | None = None) -> Tensor:
         """Returns the `[1, 2^n_local]` local shard (a view of the IPC buffer, standard layout) of U|0…0>."""
         from . import cabi, engine
 
@@ -503,7 +503,9 @@ class PeerShardedSimulator:
         cabi.check(lib.b200sv_init_zero_state(st.data_ptr(), engine._DT[self.dtype], self.n_local, 1, engine._stream_ptr(self.device)), "init")
         if self.rank != 0:
             st[0, 0] = 0
-        ptable = engine.pack_params(self.names, values or {}, 1, self.device)
+        if ptable is None:
+            ptable = engine.pack_params(self.names, values or {}, 1, self.device)
+        ptable = ptable.detach().contiguous()
         ws = self.plan.workspace(self.dtype, 1, False).data_ptr()
         self._barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(self.plan.n_sweeps + 1)] if self.time_sweeps else None
@@ -537,6 +539,43 @@ class PeerShardedSimulator:
             raise ValueError("observable and register sizes differ")
         return engine.CompiledPauliSum.build(obs)
 
+    def sample(self, values: Mapping[str, Tensor] | None, n_shots: int, uniforms: Tensor | None = None, seed: int = 0,
+               run: bool = True) -> Tensor:
+        """`n_shots` basis indices (int64, the same tensor on every rank) drawn from |ψ|² of the sharded register
+        ("all-gather of the per-rank mass"): the ranks all-gather the probability mass of their shards, every
+        shot's uniform picks its rank from the cumulative masses, the owning rank draws the index inside its shard with the
+        ordinary inverse-CDF sampler (`b200sv_sample`) on the rescaled uniform, and one all-reduce assembles the indices.
+        `uniforms` ([n_shots], in [0, 1)) must be the same on every rank (default: a generator seeded with `seed`)."""
+        from . import engine
+
+        if run:
+            self.run(values)
+        dev = self.device
+        st = self.shards.state
+        if uniforms is None:
+            uniforms = torch.rand(n_shots, dtype=torch.float64, generator=torch.Generator().manual_seed(seed))
+        u = uniforms.to(device=dev, dtype=torch.float64).reshape(-1)
+        mass = engine.dot(st, st).real.reshape(1).clone()
+        masses = [torch.empty_like(mass) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(masses, mass, group=self.group)
+        else:
+            masses = [mass]
+        cum = torch.cumsum(torch.cat(masses), 0)
+        v = u * cum[-1]
+        owner = torch.clamp(torch.searchsorted(cum, v, right=True), max=self.world - 1)
+        lo = torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), cum[:-1]])
+        mine = owner == self.rank
+        out = torch.zeros(n_shots, dtype=torch.int64, device=dev)
+        k = int(mine.sum().item())
+        if k > 0:
+            local_u = torch.clamp((v[mine] - lo[self.rank]) / masses[self.rank], min=0.0, max=1.0 - 2.0**-53)
+            idx = engine.sample_indices(st, local_u.reshape(1, -1)).reshape(-1)
+            out[mine] = idx + (self.rank << self.n_local)
+        if self.world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
     def expectation(self, values: Mapping[str, Tensor] | None, obs: PauliSum, run: bool = True) -> Tensor:
         """Re<ψ|O|ψ> of ANY Pauli-sum observable (constant coefficients): every rank sums over the rows of its shard — partner
         amplitudes of X / Y factors on global qubits are read from the peer shards over NVLink — then one all-reduce of a
@@ -560,7 +599,7 @@ class PeerShardedSimulator:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
 
-    def expectation_and_grads(self, values: Mapping[str, Tensor] | None, obs: PauliSum) -> tuple[Tensor, Tensor]:
+    def expectation_and_grads(self, values: Mapping[str, Tensor] | None, obs: PauliSum, ptable: Tensor | None = None) -> tuple[Tensor, Tensor]:
         """(E [1], dE/dθ [n_params]) by the adjoint method on the sharded register: λ = Oψ into a second set of peer-mapped
         shards, then the sweeps walked backwards on ψ and λ (`b200sv_adjoint_plan_peers`, one barrier per sweep); every
         rank reduces the gradient moments of its own tiles and ONE all-reduce sums the `[n_params]` vector."""
@@ -570,7 +609,11 @@ class PeerShardedSimulator:
 
         lib = cabi.load()
         dev = self.device
-        e = self.expectation(values, obs, run=True)
+        if ptable is None:
+            ptable = engine.pack_params(self.names, values or {}, 1, dev)
+        ptable = ptable.detach().contiguous()
+        self.run(ptable=ptable)
+        e = self.expectation(None, obs, run=False)
         if self._lam is None:
             self._lam = PeerShards(self.n_local, self.dtype, self.rank, self.world, dev, self.group)
         if self._plan_adj is None:
@@ -585,7 +628,6 @@ class PeerShardedSimulator:
                                           cps.terms(dev).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), 1.0, 0.0, st)
         cabi.check(rc, "pauli_apply_peers")
         self._barrier()  # every λ shard is complete before a sweep reads it through the peer table
-        ptable = engine.pack_params(self.names, values or {}, 1, dev)
         grads = torch.zeros(max(1, len(self.names)), 1, dtype=torch.float64, device=dev)
         dp = self._plan_adj
         ws = dp.workspace(self.dtype, 1, True).data_ptr()
@@ -604,3 +646,62 @@ class PeerShardedSimulator:
             self._lam.close()
             self._lam = None
         self.shards.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# `Configuration(shard="qubits")`: the qadence adapter's entry points for one register sharded over the process group
+# ---------------------------------------------------------------------------------------------------
+_SIMULATORS: dict = {}
+
+
+def _simulator(program: Program, dtype: torch.dtype, device: torch.device, group=None) -> "PeerShardedSimulator":
+    key = (id(program), dtype, device, id(group))
+    if key not in _SIMULATORS:
+        if not dist.is_initialized():
+            raise RuntimeError('Configuration(shard="qubits") needs an initialised torch.distributed process group (one process per GPU)')
+        if any(op.kind >= OpKind.MATK for op in program.ops):
+            raise NotImplementedError("a qubit-sharded register runs circuits of simple gates (rotations, controlled gates, SWAP, constant 1-qubit matrices)")
+        _SIMULATORS[key] = PeerShardedSimulator(program, dist.get_rank(group), dist.get_world_size(group), device, group, dtype)
+    return _SIMULATORS[key]
+
+
+class _ShardedExpectation(torch.autograd.Function):
+    """E(θ) of a Pauli-sum observable on the sharded register; backward = the adjoint sweeps over peer memory."""
+
+    @staticmethod
+    def forward(ctx, table: Tensor, sim: "PeerShardedSimulator", obs: PauliSum) -> Tensor:  # type: ignore[override]
+        if table.requires_grad:
+            e, g = sim.expectation_and_grads(None, obs, ptable=table)
+            ctx.save_for_backward(g)
+        else:
+            sim.run(ptable=table)
+            e = sim.expectation(None, obs, run=False)
+        return e.reshape(1, 1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout: Tensor):  # type: ignore[override]
+        (g,) = ctx.saved_tensors
+        return (gout.reshape(()) * g).reshape(-1, 1), None, None
+
+
+def sharded_expectation(program: Program, observables: Sequence[PauliSum], values: Mapping[str, Tensor], dtype: torch.dtype = torch.complex128,
+                        device: torch.device | str | None = None, group=None) -> Tensor:
+    """`[1, n_obs]` expectation values of `program` on a register sharded by its top qubits over `group`, differentiable
+    w.r.t. the entries of `values` (batch size 1: the GPUs are spent on ONE state).  Every rank must make the same call."""
+    from . import engine
+
+    dev = engine._dev(device)
+    sim = _simulator(program, dtype, dev, group)
+    table = engine.pack_params(sim.names, values, 1, dev)
+    if table.shape[1] != 1:
+        raise ValueError("a qubit-sharded register takes a batch of one parameter set")
+    return torch.cat([_ShardedExpectation.apply(table, sim, obs) for obs in observables], dim=1)
+
+
+def sharded_sample(program: Program, values: Mapping[str, Tensor], n_shots: int, dtype: torch.dtype = torch.complex128,
+                   device: torch.device | str | None = None, group=None, seed: int = 0) -> Tensor:
+    from . import engine
+
+    sim = _simulator(program, dtype, engine._dev(device), group)
+    return sim.sample(values, n_shots, seed=seed)

@@ -504,6 +504,7 @@ class _RunState(torch.autograd.Function):
         return psi
 
     @staticmethod
+    @torch.autograd.function.once_differentiable  # no double-backward rule for the wavefunction: create_graph=True raises instead of returning silent zeros
     def backward(ctx, g: Tensor):
         ptable, psi = ctx.saved_tensors
         lam = g.detach().to(psi.dtype).contiguous().clone()

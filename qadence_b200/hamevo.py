@@ -211,15 +211,21 @@ def adjoint_generator_params(op: Op, compiled: Any, psi: Tensor, lam: Tensor, va
         accumulate(1.0)
         back(1.0)
         return psi, lam
+    # composite Gauss–Legendre rule: panels of phase <= KRYLOV_RHO_PER_STEP each (the integrand oscillates with the phase
+    # t‖H‖, so a single rule capped at a fixed order would under-resolve long evolutions), (phase + 8) nodes per panel
     rho = (_norm_bound(op, compiled, values) or 1.0) * float(t.abs().max())
-    k = int(min(96, max(8, np.ceil(rho) + 8)))
+    panels = max(1, int(np.ceil(rho / KRYLOV_RHO_PER_STEP)))
+    k = int(max(8, np.ceil(rho / panels) + 8))
     nodes, weights = np.polynomial.legendre.leggauss(k)
     nodes, weights = 0.5 * (nodes + 1.0), 0.5 * weights  # on [0, 1]
     at = 1.0
-    for s_, w_ in zip(nodes[::-1], weights[::-1]):
-        back(at - float(s_))
-        at = float(s_)
-        accumulate(float(w_))
+    for pnl in range(panels - 1, -1, -1):  # walking back from s = 1 to s = 0
+        lo, width = pnl / panels, 1.0 / panels
+        for s_, w_ in zip(nodes[::-1], weights[::-1]):
+            pos = lo + width * float(s_)
+            back(at - pos)
+            at = pos
+            accumulate(float(w_) * width)
     back(at)
     return psi, lam
 

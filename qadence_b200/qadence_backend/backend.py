@@ -333,6 +333,15 @@ class Backend(BackendInterface):
             if endianness != self.native_endianness and state is not None:
                 raise NotImplementedError("little-endian initial density matrices are not supported")
             out = density.expectation(nat.density, [o.native.lifted for o in observable], values, state, dtype=nat.dtype, device=nat._device)
+        elif self.config.shard == "qubits":
+            from qadence_b200 import dist as qdist
+
+            if state is not None:
+                raise NotImplementedError("a qubit-sharded register starts from |0...0>")
+            obs = [o.native.compiled.obs for o in observable]
+            if any(o.native.compiled.pauli is None for o in observable):
+                raise NotImplementedError("a qubit-sharded register takes Pauli-sum observables")
+            out = qdist.sharded_expectation(nat.compiled.program, obs, values, dtype=nat.dtype, device=nat._device)
         else:
             out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, state,
                                      dtype=nat.dtype, device=nat._device)

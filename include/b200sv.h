@@ -260,6 +260,15 @@ int b200sv_scal(const double* a, void* x, int dtype, int n_qubits, int64_t batch
 int b200sv_lincomb(const double* c, const void* V, int K, void* out, int dtype, int n_qubits,
                    int64_t batch, void* stream);
 
+/* One Lanczos step after the matvec (Krylov HamEvo), fused into three passes over the state, per batch element b:
+ *     w <- w - beta_prev[b] v_prev   (v_prev may be NULL: first step);   a = Re<v, w>;   w <- w - a v;
+ *     c = <v, w> (one re-orthogonalisation pass);   v_next = (w - c v) / b,  b = sqrt(||w||^2 - |c|^2)  written over w;
+ *     alpha[b] = a + Re c,  beta[b] = b   (b = 0 and v_next = 0 when the Krylov space is exhausted).
+ * `acc` is a scratch of 4 doubles per batch element that the caller zeroes before the call.  Replaces nine batched BLAS-1
+ * launches (dot / axpy / scal / copy) and the torch glue between them per step of hamevo.krylov_expm. */
+int b200sv_lanczos_step(void* w, const void* v, const void* v_prev, const double* beta_prev, double* acc, double* alpha,
+                        double* beta, int dtype, int n_qubits, int64_t batch, void* stream);
+
 /* Krylov plumbing: y_b = exp(-i t_b T_b) e_1 for the batched real symmetric tridiagonal T_b built by
  * Lanczos (diagonal alpha[j][b], off-diagonal beta[j][b], j < m <= 64), by scaled Taylor series on
  * the device (no dense eigendecomposition, no host round trip), plus the a-posteriori error estimate

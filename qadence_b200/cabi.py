@@ -33,6 +33,7 @@ EXPORTS = [
     "b200sv_axpy",
     "b200sv_scal",
     "b200sv_lincomb",
+    "b200sv_lanczos_step",
     "b200sv_tridiag_expm",
     "b200sv_apply_dense",
     "b200sv_sample",
@@ -109,6 +110,7 @@ def load() -> C.CDLL:
         "b200sv_axpy": [vp, vp, vp, i32, i32, i64, vp],
         "b200sv_scal": [vp, vp, i32, i32, i64, vp],
         "b200sv_lincomb": [vp, vp, i32, vp, i32, i32, i64, vp],
+        "b200sv_lanczos_step": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
         "b200sv_tridiag_expm": [vp, vp, vp, i32, i64, vp, vp, vp],
         "b200sv_apply_dense": [vp, vp, i32, i32, i64, vp, vp, i32, vp],
         "b200sv_sample": [vp, i32, i32, i64, vp, vp, vp, i64, vp, vp],

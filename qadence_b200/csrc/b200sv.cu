@@ -866,6 +866,104 @@ __global__ void lincomb_kernel(const double* __restrict__ c, const c2* __restric
   }
 }
 
+// ---- fused Lanczos step (Krylov HamEvo): three passes over the state instead of nine BLAS-1 calls ---------------------
+// acc[b] = {a, c_re, c_im, n2} accumulators of this step (zeroed by the caller once for all steps)
+//   lanczos_a:    w <- w - beta_prev[b] * v_prev (if any);  a  += Re <v, w>
+//   lanczos_orth: w <- w - a * v;                            c  += <v, w>,  n2 += ||w||^2
+//   lanczos_next: v_next = (w - c v) / b,  b = sqrt(n2 - |c|^2)  (v is normalised);  alpha = a + Re c,  beta = b
+__device__ __forceinline__ void block_reduce_add(double v, double* sh, double* dst) {
+  const double t = block_reduce_sum(v, sh);
+  if (threadIdx.x == 0) atomicAdd(dst, t);
+}
+
+template <typename c2>
+__global__ void __launch_bounds__(256)
+lanczos_a_kernel(c2* __restrict__ w, const c2* __restrict__ v, const c2* __restrict__ vprev, const double* __restrict__ beta_prev,
+                 double* __restrict__ acc, int n, long long blocks_per_state) {
+  __shared__ double red[32];
+  const long long b = blockIdx.x / blocks_per_state, blk = blockIdx.x % blocks_per_state;
+  const long long N = 1ll << n, base = (b << n) + blk * 2048ll;
+  const double bp = (vprev != nullptr) ? beta_prev[b] : 0.0;
+  double a = 0.0;
+  c2 wv[8], vv[8], pv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = blk * 2048ll + k * 256 + threadIdx.x;
+    wv[k].x = 0; wv[k].y = 0; vv[k] = wv[k]; pv[k] = wv[k];
+    if (i < N) { wv[k] = w[base + k * 256 + threadIdx.x]; vv[k] = v[base + k * 256 + threadIdx.x]; if (vprev != nullptr) pv[k] = vprev[base + k * 256 + threadIdx.x]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = blk * 2048ll + k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const double wr = (double)wv[k].x - bp * (double)pv[k].x, wi = (double)wv[k].y - bp * (double)pv[k].y;
+    a += (double)vv[k].x * wr + (double)vv[k].y * wi;
+    if (vprev != nullptr) { c2 o; o.x = wr; o.y = wi; w[base + k * 256 + threadIdx.x] = o; }
+  }
+  block_reduce_add(a, red, acc + 4 * b);
+}
+
+template <typename c2>
+__global__ void __launch_bounds__(256)
+lanczos_orth_kernel(c2* __restrict__ w, const c2* __restrict__ v, double* __restrict__ acc, int n, long long blocks_per_state) {
+  __shared__ double red[32];
+  const long long b = blockIdx.x / blocks_per_state, blk = blockIdx.x % blocks_per_state;
+  const long long N = 1ll << n, base = (b << n) + blk * 2048ll;
+  const double a = acc[4 * b];
+  double cr = 0.0, ci = 0.0, n2 = 0.0;
+  c2 wv[8], vv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = blk * 2048ll + k * 256 + threadIdx.x;
+    wv[k].x = 0; wv[k].y = 0; vv[k] = wv[k];
+    if (i < N) { wv[k] = w[base + k * 256 + threadIdx.x]; vv[k] = v[base + k * 256 + threadIdx.x]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = blk * 2048ll + k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const double vr = vv[k].x, vi = vv[k].y;
+    const double wr = (double)wv[k].x - a * vr, wi = (double)wv[k].y - a * vi;
+    cr += vr * wr + vi * wi;  // conj(v) * w
+    ci += vr * wi - vi * wr;
+    n2 += wr * wr + wi * wi;
+    c2 o; o.x = wr; o.y = wi;
+    w[base + k * 256 + threadIdx.x] = o;
+  }
+  block_reduce_add(cr, red, acc + 4 * b + 1);
+  block_reduce_add(ci, red, acc + 4 * b + 2);
+  block_reduce_add(n2, red, acc + 4 * b + 3);
+}
+
+template <typename c2>
+__global__ void __launch_bounds__(256)
+lanczos_next_kernel(c2* __restrict__ w, const c2* __restrict__ v, const double* __restrict__ acc, double* __restrict__ alpha,
+                    double* __restrict__ beta, int n, long long blocks_per_state) {
+  const long long b = blockIdx.x / blocks_per_state, blk = blockIdx.x % blocks_per_state;
+  const long long N = 1ll << n, base = (b << n) + blk * 2048ll;
+  const double a = acc[4 * b], cr = acc[4 * b + 1], ci = acc[4 * b + 2], n2 = acc[4 * b + 3];
+  const double al = a + cr;
+  double b2 = n2 - (cr * cr + ci * ci);
+  if (b2 < 0.0) b2 = 0.0;
+  double bb = sqrt(b2);
+  const double scale = fabs(al) > 1.0 ? fabs(al) : 1.0;
+  const bool tiny = bb <= 1e-14 * scale;  // invariant subspace reached: the basis ends here
+  const double inv = tiny ? 0.0 : 1.0 / bb;
+  if (tiny) bb = 0.0;
+  if (blk == 0 && threadIdx.x == 0) { alpha[b] = al; beta[b] = bb; }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const long long i = blk * 2048ll + k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const c2 wv = w[base + k * 256 + threadIdx.x], vv = v[base + k * 256 + threadIdx.x];
+    const double vr = vv.x, vi = vv.y;
+    c2 o;
+    o.x = ((double)wv.x - (cr * vr - ci * vi)) * inv;
+    o.y = ((double)wv.y - (cr * vi + ci * vr)) * inv;
+    w[base + k * 256 + threadIdx.x] = o;
+  }
+}
+
 // ---- batched tridiagonal exponential (Lanczos small problem) -----------------------------------
 constexpr int TRI_MAX = 64;
 __global__ void tridiag_expm_kernel(const double* __restrict__ alpha, const double* __restrict__ beta,
@@ -1202,6 +1300,27 @@ int b200sv_lincomb(const double* c, const void* V, int K, void* out, int dtype, 
   if (dtype == B200SV_C128) lincomb_kernel<double2><<<grid_for(total, 256), 256, 0, st>>>(c, (const double2*)V, K, (double2*)out, n, batch);
   else if (dtype == B200SV_C64) lincomb_kernel<float2><<<grid_for(total, 256), 256, 0, st>>>(c, (const float2*)V, K, (float2*)out, n, batch);
   else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_lanczos_step(void* w, const void* v, const void* v_prev, const double* beta_prev, double* acc, double* alpha,
+                        double* beta, int dtype, int n, int64_t batch, void* stream) {
+  if (!w || !v || !acc || !alpha || !beta || (v_prev && !beta_prev) || n < 0 || n > 40 || batch <= 0 || w == v) return B200SV_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + 2047) / 2048;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (dtype == B200SV_C128) {
+    lanczos_a_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)w, (const double2*)v, (const double2*)v_prev, beta_prev, acc, n, bps);
+    lanczos_orth_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)w, (const double2*)v, acc, n, bps);
+    lanczos_next_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((double2*)w, (const double2*)v, acc, alpha, beta, n, bps);
+  } else if (dtype == B200SV_C64) {
+    lanczos_a_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)w, (const float2*)v, (const float2*)v_prev, beta_prev, acc, n, bps);
+    lanczos_orth_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)w, (const float2*)v, acc, n, bps);
+    lanczos_next_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((float2*)w, (const float2*)v, acc, alpha, beta, n, bps);
+  } else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;
 }

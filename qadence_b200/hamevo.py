@@ -47,7 +47,7 @@ def _matvec(op: Op, compiled: Any, values: Mapping[str, Tensor], n: int, device:
     g = op.generator
     if isinstance(g, PauliSum):
         coef = compiled.coef(values, device)
-        return lambda v: E.pauli_apply(compiled, coef, v)
+        return lambda v, out=None: E.pauli_apply(compiled, coef, v, out=out)  # the Lanczos loop writes straight into its basis
     if isinstance(g, Program):
         def mv(v: Tensor) -> Tensor:
             tab = E.pack_params(compiled.names, values, v.shape[0], device)
@@ -129,7 +129,7 @@ def _td_step(compiled: Any, coef: Tensor, state: Tensor, dt: Tensor, sign: float
                                             sign, 0, E._stream_ptr(state.device))
         cabi.check(rc, "diag_evolve")
         return state
-    return krylov_expm(lambda v: E.pauli_apply(compiled, coef, v), state, sign * dt)
+    return krylov_expm(lambda v, out=None: E.pauli_apply(compiled, coef, v, out=out), state, sign * dt)
 
 
 def evolve_time_dependent(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
@@ -273,30 +273,30 @@ def krylov_expm(matvec: Callable[[Tensor], Tensor], psi: Tensor, t: Tensor, tol:
     E.scal((1.0 / safe).to(torch.complex128), V[0])
     alphas = torch.zeros(m_max, B, dtype=torch.float64, device=dev)
     betas = torch.zeros(m_max, B, dtype=torch.float64, device=dev)
+    acc = torch.zeros(m_max, B, 4, dtype=torch.float64, device=dev)  # per-step accumulators of b200sv_lanczos_step
+    lib = cabi.load()
+    n_q = int(N).bit_length() - 1
+    import inspect
+
+    takes_out = "out" in inspect.signature(matvec).parameters
     y = None
     converged = False
     m = 0
     for j in range(m_max):
-        w = matvec(V[j])
-        a = E.dot(V[j], w).real
-        E.axpy((-a).to(torch.complex128), V[j], w)
-        if j > 0:
-            E.axpy((-betas[j - 1]).to(torch.complex128), V[j - 1], w)
-        # one extra local re-orthogonalisation pass keeps the recurrence accurate to ~1e-15
-        c = E.dot(V[j], w)
-        E.axpy(-c, V[j], w)
-        a = a + c.real
-        b = torch.sqrt(E.dot(w, w).real)
-        alphas[j] = a
+        if takes_out:
+            matvec(V[j], out=V[j + 1])
+        else:
+            V[j + 1].copy_(matvec(V[j]))
+        # the rest of the step (three-term recurrence, one re-orthogonalisation pass, normalisation, alpha / beta) in three
+        # fused passes over the state: no host arithmetic, no synchronisation
+        rc = lib.b200sv_lanczos_step(V[j + 1].data_ptr(), V[j].data_ptr(), V[j - 1].data_ptr() if j > 0 else None,
+                                     betas[j - 1].data_ptr() if j > 0 else None, acc[j].data_ptr(), alphas[j].data_ptr(), betas[j].data_ptr(),
+                                     E._DT[psi.dtype], n_q, B, E._stream_ptr(dev))
+        cabi.check(rc, "lanczos_step")
         m = j + 1
-        tiny = b <= 1e-14 * torch.clamp(a.abs(), min=1.0)
-        betas[j] = torch.where(tiny, torch.zeros_like(b), b)
-        inv = torch.where(tiny, torch.zeros_like(b), 1.0 / torch.where(tiny, torch.ones_like(b), b))
-        V[j + 1].copy_(w)
-        E.scal(inv.to(torch.complex128), V[j + 1])
         if m >= min(8, m_max) and (m % 8 == 0 or m == m_max or m == N):
             y, err = _small_expm(alphas[:m], betas[:m], t)
-            if float(err.max()) < tol or m == N:
+            if float(err.max()) < tol or m == N:  # the only host synchronisation: once every 8 steps
                 converged = True
                 break
     if not converged:

@@ -83,6 +83,24 @@ def cfg3():
 
 
 ms3 = timeit(cfg3, reps=3, warm=1)
+# matvec count of one evaluation (the Krylov propagator's only state-sized kernel besides the fused Lanczos step)
+_calls = {"pauli_apply": 0, "lanczos_step": 0}
+_orig_apply = engine.pauli_apply
+
+
+def _counting_apply(*a, **k):
+    _calls["pauli_apply"] += 1
+    return _orig_apply(*a, **k)
+
+
+engine.pauli_apply = _counting_apply
+cfg3()
+torch.cuda.synchronize()
+engine.pauli_apply = _orig_apply
+n_matvec = _calls["pauli_apply"] - 1  # one call is lambda = O psi ... (expectation only: no lambda) -> kept as an upper bound
+S3 = B * (1 << n) * 16
+# per Lanczos step: matvec 2S + lanczos_a 4S + lanczos_orth 3S + lanczos_next 3S algorithmic bytes
+bytes_per_step = 12 * S3
 psi = engine.run(cp3, v3, device=dev)
 norm_err = float((engine.dot(psi, psi).real - 1).abs().max())
 # parity of a batch slice against the dense-matrix oracle (n = 12 -> 4096 x 4096 expm is feasible for a few elements)
@@ -92,6 +110,9 @@ sl = {k: v[:2] for k, v in v3.items()}
 want = oracle.run(prog3, sl)
 err = float((psi[:2].cpu() - want).abs().max())
 out["cfg3"] = {"n": n, "batch": B, "ms": ms3, "hamevo_applications_per_s": 3 * B / (ms3 * 1e-3), "generator_terms": len(h_rx.terms),
+               "matvecs_per_evaluation": n_matvec, "ms_per_lanczos_step": ms3 / max(1, n_matvec), "matvecs_per_s": n_matvec * B / (ms3 * 1e-3),
+               "hbm_frac_of_the_lanczos_steps": (bytes_per_step * n_matvec / (ms3 * 1e-3) / 1e9) / 6542.1,
+               "note": "state 64 MiB: a Lanczos step is four kernels over 12 S = 768 MiB of algorithmic traffic; the state and the Krylov basis of the last steps are partly L2-resident (126 MB)",
                "norm_err": norm_err, "max_abs_err_vs_dense_expm_oracle(first 2 batch elements)": err}
 
 # ---- cfg4: feature map (RX(x) per qubit here) + hea(16, 12), 512 per GPU ----

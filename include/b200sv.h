@@ -239,6 +239,18 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
                        int64_t coef_ld, double alpha_re, double alpha_im, double beta_re,
                        double beta_im, uint64_t index_hi, void* stream);
 
+/* The diagonal part of a Pauli sum as a table: out[r][i] = sum_t coef[row_t][r] (-1)^{popc(i & zmask_t)} (complex, `rows` = 1
+ * or the batch; all terms must have xmask == 0), and the matvec that consumes it:
+ *     out = alpha * (diag[b][i] psi_i + sum_{X/Y terms t} coef_t P_t psi) + beta * acc.
+ * The Krylov propagator computes the table once per evolution: a Rydberg generator (66 N_iN_j + detunings + 12 drive terms,
+ * analog/hamiltonian_terms.py:16-72) then costs 12 instead of 90 terms per amplitude and matvec.  Same replaced call site
+ * as b200sv_pauli_apply. */
+int b200sv_pauli_diagonal(const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, int64_t coef_ld,
+                          int n_qubits, int64_t rows, double* out, uint64_t index_hi, void* stream);
+int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dtype, int n_qubits, int64_t batch,
+                            const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld, const double* diag,
+                            int64_t diag_ld, double alpha_re, double alpha_im, double beta_re, double beta_im, void* stream);
+
 /* psi[b][i] *= exp(-i t[b] d_b(i)), d_b(i) = sum_t coef[row_t][b] (-1)^{popc(i & zmask_t)} evaluated
  * on the fly from the index bits (all terms must have xmask == 0).  The diagonal Rydberg interaction
  * sum_{i<j} C6/r^6 N_i N_j of analog blocks (analog/hamiltonian_terms.py:16-45) takes this path.

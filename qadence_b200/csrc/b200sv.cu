@@ -688,7 +688,11 @@ __global__ void __launch_bounds__(EXP_THREADS)
 pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
                    const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
                    long long coef_ld, double ar, double ai, double br, double bi,
-                   unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
+                   unsigned long long index_hi, long long blocks_per_state, const PeerTable pt,
+                   const double* __restrict__ diag = nullptr, long long diag_ld = 1) {
+  // diag (optional): precomputed complex weights [diag_ld][2^n] of ALL diagonal terms of the sum (b200sv_pauli_diagonal); the
+  // term list then holds only the X / Y terms — the Krylov matvec of a Rydberg Hamiltonian (66 ZZ + 12 Z + 12 X terms)
+  // evaluates 12 terms per amplitude instead of 90
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
   __shared__ DiagTables dt;
@@ -709,13 +713,16 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
     const long long gbase = base + (long long)g * (EXP_THREADS * PK_K);
     if (gbase >= N) break;
     c2 av[PK_K], zv[PK_K];  // loads first (memory-level parallelism), see pauli_expect_kernel
+    double2 dv[PK_K];
+    const double2* dg = diag ? reinterpret_cast<const double2*>(diag) + ((diag_ld == 1 ? 0 : b) << n) : nullptr;
 #pragma unroll
     for (int k = 0; k < PK_K; ++k) {
       const long long i = gbase + (long long)k * EXP_THREADS;
-      av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0;
+      av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0; dv[k].x = 0.0; dv[k].y = 0.0;
       if (i < N) {
         av[k] = __ldcs(p + i);
         if (acc != nullptr) zv[k] = acc[(b << n) + i];
+        if (dg != nullptr) dv[k] = dg[i];
       }
     }
     const double wgr = wtr + dt.gr[g], wgi = wti + dt.gi[g];
@@ -724,7 +731,7 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
       const long long i = gbase + (long long)k * EXP_THREADS;
       if (i >= N) break;
       const c2 a = av[k];
-      double wr = wgr + dt.kr[k], wi = wgi + dt.ki[k], sr = 0.0, si = 0.0;
+      double wr = wgr + dt.kr[k] + dv[k].x, wi = wgi + dt.ki[k] + dv[k].y, sr = 0.0, si = 0.0;
       if (T > 0) {
         const unsigned long long gi = (unsigned long long)i | index_hi;
         for (int t = 0; t < T; ++t) {
@@ -756,6 +763,32 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
       c2 o; o.x = rr; o.y = ri;
       __stcs(out + (b << n) + i, o);
     }
+  }
+}
+
+// out[r][i] = sum_t coef_t(r) (-1)^{popc(i & z_t)}  (all terms diagonal): the weight table b200sv_pauli_apply_diag consumes
+__global__ void __launch_bounds__(256)
+pauli_diagonal_kernel(const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef, long long coef_ld,
+                      int n, double2* __restrict__ out, unsigned long long index_hi, long long blocks_per_state) {
+  __shared__ TermS sh[MAX_TERMS_SMEM];
+  __shared__ SingleZ sz;
+  const long long r = blockIdx.x / blocks_per_state, blk = blockIdx.x % blocks_per_state;
+  resolve_terms(sh, terms, T, coef, coef_ld, r, &sz, n_single);
+  __syncthreads();
+  T -= n_single;
+  const long long N = 1ll << n;
+  for (int k = 0; k < 4; ++k) {
+    const long long i = blk * 1024ll + k * 256 + threadIdx.x;
+    if (i >= N) break;
+    const unsigned long long gi = (unsigned long long)i | index_hi;
+    double wr = sz.c0r, wi = sz.c0i;
+    if (n_single > 0) single_z_weight(sz, gi, wr, wi);
+    for (int t = 0; t < T; ++t) {
+      const TermS tm = sh[t];
+      const double sg = (__popcll(gi & tm.z) & 1) ? -1.0 : 1.0;
+      wr += sg * tm.cr; wi += sg * tm.ci;
+    }
+    out[(r << n) + i] = make_double2(wr, wi);
   }
 }
 
@@ -1232,6 +1265,41 @@ int b200sv_pauli_apply(const void* psi, void* out, const void* acc, int dtype, i
     pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps, PeerTable{});
   else if (dtype == B200SV_C64)
     pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, n_single, coef, coef_ld, ar, ai, br, bi, index_hi, bps, PeerTable{});
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_pauli_diagonal(const b200sv_pterm* terms, int n_terms, int n_single, const double* coef, int64_t coef_ld, int n,
+                          int64_t rows, double* out, uint64_t index_hi, void* stream) {
+  if (!out || !coef || n < 0 || n > 40 || rows <= 0 || (coef_ld != 1 && coef_ld != rows)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms, n_single)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + 1023) / 1024;
+  const long long grid = bps * rows;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  pauli_diagonal_kernel<<<(unsigned)grid, 256, 0, st>>>(terms, n_terms, n_single, coef, coef_ld, n, (double2*)out, index_hi, bps);
+  LAUNCH_CK();
+  return 0;
+}
+
+int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dtype, int n, int64_t batch,
+                            const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld, const double* diag,
+                            int64_t diag_ld, double ar, double ai, double br, double bi, void* stream) {
+  if (!psi || !out || psi == out || !diag || batch <= 0 || (coef_ld != 1 && coef_ld != batch) || (diag_ld != 1 && diag_ld != batch)) return B200SV_E_ARG;
+  if (n_terms > 0 && (!terms || !coef)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms, 0)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + PK_TILE - 1) / PK_TILE;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (br == 0.0 && bi == 0.0) acc = nullptr;
+  if (dtype == B200SV_C128)
+    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+  else if (dtype == B200SV_C64)
+    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;

@@ -135,6 +135,15 @@ class CompiledPauliSum:
     def n_terms(self) -> int:
         return len(self.ps.terms)
 
+    def split_diagonal(self) -> "tuple[CompiledPauliSum, CompiledPauliSum] | None":
+        """(diagonal part, X / Y part) as two compiled sums, or None when either is empty (cached).  Used by the Krylov
+        matvec: the diagonal part is tabulated once per evolution (`b200sv_pauli_diagonal`)."""
+        if not hasattr(self, "_split"):
+            dg = [t for t in self.ps.terms if all(p[1] == "Z" for p in t.paulis)]
+            off = [t for t in self.ps.terms if not all(p[1] == "Z" for p in t.paulis)]
+            self._split = (CompiledPauliSum.build(PauliSum(self.ps.n_qubits, dg)), CompiledPauliSum.build(PauliSum(self.ps.n_qubits, off))) if dg and off else None
+        return self._split
+
     @property
     def is_parametric(self) -> bool:
         return any(len(nm) > 0 for nm in self.names)
@@ -362,6 +371,31 @@ def pauli_apply(cps: CompiledPauliSum, coef: Tensor, psi: Tensor, out: Tensor | 
         float(np.real(alpha)), float(np.imag(alpha)), float(np.real(beta)), float(np.imag(beta)), index_hi, _stream_ptr(dev),
     )
     cabi.check(rc, "pauli_apply")
+    return out
+
+
+def pauli_diagonal(cps: CompiledPauliSum, coef: Tensor, device: torch.device) -> Tensor:
+    """[rows, 2^n] complex128 table of a DIAGONAL Pauli sum, rows = coef.shape[1] (1 or the batch)."""
+    n = cps.ps.n_qubits
+    rows = int(coef.shape[1])
+    out = torch.empty(rows, 1 << n, 2, dtype=torch.float64, device=device)
+    cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+    rc = cabi.load().b200sv_pauli_diagonal(cps.terms(device).data_ptr(), cps.n_terms, cps.n_single, cf.data_ptr(), rows, n, rows, out.data_ptr(), 0,
+                                           _stream_ptr(device))
+    cabi.check(rc, "pauli_diagonal")
+    return out
+
+
+def pauli_apply_diag(off: CompiledPauliSum, coef_off: Tensor, diag: Tensor, psi: Tensor, out: Tensor | None = None) -> Tensor:
+    """out = diag ⊙ ψ + Σ_{X/Y terms} coef_t P_t ψ  (the Krylov matvec with a tabulated diagonal)."""
+    n = off.ps.n_qubits
+    B = psi.shape[0]
+    dev = psi.device
+    out = torch.empty_like(psi) if out is None else out
+    cf = torch.view_as_real(coef_off.detach().to(torch.complex128).contiguous())
+    rc = cabi.load().b200sv_pauli_apply_diag(psi.data_ptr(), out.data_ptr(), 0, _DT[psi.dtype], n, B, off.terms(dev).data_ptr(), off.n_terms, cf.data_ptr(),
+                                             coef_off.shape[1], diag.data_ptr(), diag.shape[0], 1.0, 0.0, 0.0, 0.0, _stream_ptr(dev))
+    cabi.check(rc, "pauli_apply_diag")
     return out
 
 

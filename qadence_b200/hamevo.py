@@ -46,8 +46,7 @@ def _time(op: Op, values: Mapping[str, Tensor], batch: int, device: torch.device
 def _matvec(op: Op, compiled: Any, values: Mapping[str, Tensor], n: int, device: torch.device) -> Callable[[Tensor], Tensor]:
     g = op.generator
     if isinstance(g, PauliSum):
-        coef = compiled.coef(values, device)
-        return lambda v, out=None: E.pauli_apply(compiled, coef, v, out=out)  # the Lanczos loop writes straight into its basis
+        return _pauli_matvec(compiled, compiled.coef(values, device), values, device)
     if isinstance(g, Program):
         def mv(v: Tensor) -> Tensor:
             tab = E.pack_params(compiled.names, values, v.shape[0], device)
@@ -66,6 +65,22 @@ def _matvec(op: Op, compiled: Any, values: Mapping[str, Tensor], n: int, device:
         mat = torch.as_tensor(np.asarray(g, dtype=np.complex128))
         mat = mat.reshape(mat.shape[-2], mat.shape[-1])
     return lambda v: E.apply_dense(v, mat, bits)
+
+
+def _pauli_matvec(compiled: Any, coef: Tensor, values: Mapping[str, Tensor] | None, device: torch.device,
+                  coefs_split: "tuple[Tensor, Tensor] | None" = None) -> Callable[..., Tensor]:
+    """ψ ↦ Hψ for a Pauli-sum generator (the Lanczos loop passes `out=` and writes straight into its basis).  A generator
+    with both diagonal and X / Y terms — every Rydberg Hamiltonian — gets its diagonal tabulated ONCE
+    (`b200sv_pauli_diagonal`); each matvec then evaluates only the X / Y terms per amplitude (`b200sv_pauli_apply_diag`)."""
+    split = compiled.split_diagonal() if compiled.ps.n_qubits <= 26 else None  # the table is 2^n complex numbers per row
+    if split is None:
+        return lambda v, out=None: E.pauli_apply(compiled, coef, v, out=out)
+    dg, off = split
+    if coefs_split is None:
+        coefs_split = (dg.coef(values or {}, device), off.coef(values or {}, device))
+    table = E.pauli_diagonal(dg, coefs_split[0], device)
+    coef_off = coefs_split[1]
+    return lambda v, out=None: E.pauli_apply_diag(off, coef_off, table, v, out=out)
 
 
 def generator_apply(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int) -> Tensor:

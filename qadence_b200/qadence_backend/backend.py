@@ -31,7 +31,7 @@ from qadence.types import BackendName, Endianness, Engine, ParamDictType
 
 from .. import density, engine
 from ..embedding import ParamTable, UnsupportedExpression, compile_expressions, make_embedding_fn
-from ..program import Program
+from ..program import OpKind, Program
 from .config import Configuration, default_passes
 from .convert_ops import convert_block, convert_observable, convert_readout_noise
 
@@ -40,6 +40,44 @@ logger = getLogger(__name__)
 _REPLACE = "b200sv" not in BackendName.list()
 _NAME, _ENGINE = ("pyqtorch", "torch") if _REPLACE else ("b200sv", "b200sv")
 _DTYPES = {"complex128": torch.complex128, "complex64": torch.complex64}
+
+
+def dropout_ops(program: Program, prob: float, mode: str, values: Any) -> set[int]:
+    """Indices of the ops one forward pass of a quantum-dropout circuit skips (arXiv:2310.04120, what the reference gets
+    from `pyq.DropoutQuantumCircuit`, backends/pyqtorch/backend.py:127-141; pyqtorch is absent here, so the three modes are
+    restated from its documented behaviour — parity unpinned, like §4.3's noise):
+      rotational_dropout     every parametric rotation whose parameter is trainable is dropped with probability `prob`;
+      entangling_dropout     every controlled gate is dropped with probability `prob`;
+      canonical_fwd_dropout  rotational dropout, and a dropped rotation takes the entangling gates that follow it on its
+                             qubit (up to that qubit's next rotation) with it.
+    Draws from torch's global generator (`torch.manual_seed` makes a training run reproducible)."""
+    rot = (OpKind.RX, OpKind.RY, OpKind.RZ, OpKind.PHASE)
+
+    def trainable(op: Any) -> bool:
+        if not isinstance(op.param, str):
+            return False
+        if isinstance(values, ParamTable):
+            return op.param not in values.nograd
+        v = values.get(op.param) if hasattr(values, "get") else None
+        return bool(isinstance(v, Tensor) and v.requires_grad)
+
+    ops = list(program.ops)
+    coins = torch.bernoulli(torch.full((len(ops),), float(prob))).bool().tolist() if ops else []
+    drop: set[int] = set()
+    if mode == "entangling_dropout":
+        return {i for i, op in enumerate(ops) if op.controls and coins[i]}
+    for i, op in enumerate(ops):
+        if op.kind in rot and not op.controls and trainable(op) and coins[i]:
+            drop.add(i)
+            if mode == "canonical_fwd_dropout":
+                q = op.targets[0]
+                for j in range(i + 1, len(ops)):
+                    nxt = ops[j]
+                    if nxt.kind in rot and not nxt.controls and q in nxt.targets:
+                        break
+                    if nxt.controls and (q in nxt.targets or q in nxt.controls):
+                        drop.add(j)
+    return drop
 
 
 class NativeCircuit:
@@ -57,6 +95,24 @@ class NativeCircuit:
         self.dtype = dtype
         self._device = device
         self.readout_noise = readout_noise
+        self.dropout_prob = 0.0  # quantum dropout (pyqtorch `DropoutQuantumCircuit`): set by `Backend.circuit`
+        self.dropout_mode = "rotational_dropout"
+        self._dropped: dict = {}  # dropped-op index tuple -> CompiledProgram (bounded cache)
+
+    def compiled_for_call(self, training: bool, values: Any) -> "engine.CompiledProgram":
+        """The program this call executes: the full one, or — quantum dropout, training mode only — one with a fresh random
+        subset of its gates removed (`dropout_ops`)."""
+        if not training or self.dropout_prob <= 0.0 or self.compiled is None:
+            return self.compiled
+        drop = dropout_ops(self.program, self.dropout_prob, str(getattr(self.dropout_mode, "value", self.dropout_mode)), values)
+        if not drop:
+            return self.compiled
+        key = tuple(sorted(drop))
+        if key not in self._dropped:
+            if len(self._dropped) >= 64:
+                self._dropped.pop(next(iter(self._dropped)))
+            self._dropped[key] = engine.CompiledProgram(Program(self.program.n_qubits, [op for i, op in enumerate(self.program.ops) if i not in drop]))
+        return self._dropped[key]
 
     @property
     def density(self) -> density.CompiledDensityProgram:
@@ -244,11 +300,14 @@ class Backend(BackendInterface):
             circuit = transpile(*passes)(circuit)
         if self.config.noise:  # noise set in the configuration (pyqtorch/backend.py:118-127)
             set_noise(circuit, self.config.noise)
-        if self.config.dropout_probability:
-            raise NotImplementedError("b200sv does not implement quantum dropout (`dropout_probability` must be 0)")
         ops = convert_block(circuit.block, n_qubits=circuit.n_qubits, config=self.config)
         readout = convert_readout_noise(circuit.n_qubits, self.config.noise) if self.config.noise else None
         native = NativeCircuit(Program(circuit.n_qubits, ops), _DTYPES[self.config.dtype], self.config.device, readout)
+        if self.config.dropout_probability:  # pyqtorch/backend.py:127-141: a DropoutQuantumCircuit instead of a QuantumCircuit
+            if native.is_noisy:
+                raise NotImplementedError("quantum dropout of a circuit with digital noise is not supported")
+            native.dropout_prob = float(self.config.dropout_probability)
+            native.dropout_mode = self.config.dropout_mode or "rotational_dropout"
         return ConvertedCircuit(native=native, abstract=circuit, original=original)
 
     def _set_block_and_readout_noises(self, circuit: ConvertedCircuit, noise: NoiseHandler | None) -> None:
@@ -299,7 +358,7 @@ class Backend(BackendInterface):
             if endianness != self.native_endianness:
                 out = _reverse_density(out)
         else:
-            out = engine.run(nat.compiled, param_values, state, dtype=nat.dtype, device=nat._device)
+            out = engine.run(nat.compiled_for_call(circuit.training, param_values), param_values, state, dtype=nat.dtype, device=nat._device)
             if endianness != self.native_endianness:
                 if out.requires_grad:  # keep the autograd edge of a differentiable wavefunction: a torch gather, not the kernel
                     idx = torch.tensor([int(format(i, f"0{n}b")[::-1], 2) for i in range(2**n)], device=out.device)
@@ -343,7 +402,7 @@ class Backend(BackendInterface):
                 raise NotImplementedError("a qubit-sharded register takes Pauli-sum observables")
             out = qdist.sharded_expectation(nat.compiled.program, obs, values, dtype=nat.dtype, device=nat._device)
         else:
-            out = engine.expectation(nat.compiled, [o.native.compiled for o in observable], values, state,
+            out = engine.expectation(nat.compiled_for_call(circuit.training, values), [o.native.compiled for o in observable], values, state,
                                      dtype=nat.dtype, device=nat._device)
         dev = _result_device(self.config, pc, po, state)
         return out if dev is None else out.to(dev)

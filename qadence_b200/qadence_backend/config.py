@@ -45,8 +45,10 @@ class Configuration(BackendConfiguration):
     """`NoiseHandler` applied at conversion time (pyqtorch/config.py:62): digital noise on every primitive block — the
     circuit then runs as a density matrix (qadence_b200/density.py) — and/or readout noise for `sample`."""
     dropout_probability: float = 0.0
-    """Quantum dropout is not supported: a non-zero value raises at conversion time."""
+    """Quantum dropout probability (0 means no dropout), as in pyqtorch/config.py:69-72: while the converted circuit is in
+    training mode every `run` / `expectation` executes a fresh random sub-circuit (`qadence_backend.backend.dropout_ops`)."""
     dropout_mode: object = None
+    """`DropoutMode` / its string value: "rotational_dropout" (default), "entangling_dropout", "canonical_fwd_dropout"."""
     n_eqs: int | None = None
     shift_prefac: float = 0.5
     gap_step: float = 1.0

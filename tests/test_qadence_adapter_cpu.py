@@ -496,8 +496,44 @@ def test_pyqtorch_configuration_dicts_are_accepted(oracle_device) -> None:
            "shift_prefac": 0.5, "gap_step": 1.0, "lb": None, "ub": None, "dropout_probability": 0.0, "dropout_mode": "rotational"}
     model = QuantumModel(QuantumCircuit(2, chain(RX(0, "x"), CNOT(0, 1))), total_magnetization(2), backend="b200sv", configuration=cfg)
     assert model.expectation({"x": torch.tensor([0.2, 0.4])}).shape == (2, 1)
-    with pytest.raises(NotImplementedError, match="dropout"):
-        QuantumModel(QuantumCircuit(1, RX(0, "x")), backend="b200sv", configuration={"dropout_probability": 0.1})
+
+
+@pytest.mark.parametrize("mode", ["rotational_dropout", "entangling_dropout", "canonical_fwd_dropout"])
+def test_quantum_dropout(oracle_device, mode: str) -> None:
+    """`dropout_probability > 0` (pyqtorch/backend.py:127-141): in training mode every call executes a random sub-circuit,
+    in eval mode the full circuit; a dropped trainable rotation gets no gradient in that pass."""
+    from qadence_b200.qadence_backend.backend import dropout_ops
+
+    n = 3
+    circ = QuantumCircuit(n, chain(feature_map(n, param="x"), hea(n, 2)))
+    torch.manual_seed(0)
+    model = QuantumModel(circ, total_magnetization(n), backend="b200sv", diff_mode=DiffMode.ADJOINT,
+                         configuration={"dropout_probability": 0.5, "dropout_mode": mode})
+    plain = QuantumModel(circ, total_magnetization(n), backend="b200sv", diff_mode=DiffMode.ADJOINT)
+    plain.load_state_dict(model.state_dict())
+    assert model._circuit.native.dropout_prob == 0.5
+    x = {"x": torch.tensor([0.3, 0.8])}
+    model.eval()
+    assert torch.allclose(model.expectation(x), plain.expectation(x), atol=1e-12)  # eval mode: the full circuit
+    model.train()
+    outs = {tuple(model.expectation(x).detach().flatten().round(decimals=9).tolist()) for _ in range(12)}
+    assert len(outs) > 1  # different sub-circuits in different passes
+    # the mask: only the gate classes of the mode are ever dropped, and only trainable rotations
+    prog = model._circuit.native.program
+    vals = model.embedding_fn(model._params, x)
+    seen: set[int] = set()
+    for _ in range(20):
+        seen |= dropout_ops(prog, 0.5, mode, vals)
+    for i in seen:
+        op = prog.ops[i]
+        if mode == "entangling_dropout":
+            assert op.controls
+        elif mode == "rotational_dropout":
+            assert not op.controls and isinstance(op.param, str)
+    assert seen
+    e = model.expectation(x)
+    e.sum().backward()
+    assert any(p.grad is not None for p in model.parameters())
 
 
 @pytest.mark.parametrize("dtype", [torch.complex64, torch.complex128])

@@ -274,6 +274,8 @@ def hamevo_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = Fal
     """ψ ← exp(−i t G) ψ with a dense exponential (block_to_tensor.py:409-440; see `expm_i` for the one deviation)."""
     if op.tsym:
         return hamevo_td_apply(op, state, values, n, dagger)
+    if op.steps > 0 and isinstance(op.generator, PauliSum):
+        return hamevo_trotter_apply(op, state, values, n, dagger)
     batch = state.shape[-1]
     t = _value(values, op.param, batch).to(CDTYPE)
     gen_depends_on_batch = _generator_is_batched(op, values, batch)
@@ -285,6 +287,36 @@ def hamevo_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = Fal
     flat = from_pyq_shape(state)  # [B, dim]
     out = torch.einsum("bij,bj->bi", U, flat)
     return to_pyq_shape(out, n)
+
+
+def hamevo_trotter_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = False) -> torch.Tensor:
+    """The b200sv extension `algo_hevo="trotter"` restated with dense exponentials (the reference has no Trotter option:
+    its AlgoHEvo values EXP / EIG / RK4, types.py:301-309, are all the exact propagator): `op.steps` Strang steps
+    e^{-iD dt/2} e^{-iK dt} e^{-iD dt/2} of H = D + K, D = the all-Z terms, K = the rest."""
+    batch = state.shape[-1]
+    t = _value(values, op.param, batch).to(CDTYPE)
+    g = op.generator
+    D = PauliSum(g.n_qubits, [tm for tm in g.terms if all(p[1] == "Z" for p in tm.paulis)])
+    K = PauliSum(g.n_qubits, [tm for tm in g.terms if not all(p[1] == "Z" for p in tm.paulis)])
+    bsz = batch if _generator_is_batched(op, values, batch) else 1
+    GD = generator_dense(D, n, values, op.targets, bsz).expand(batch, -1, -1) if D.terms else None
+    GK = generator_dense(K, n, values, op.targets, bsz).expand(batch, -1, -1) if K.terms else None
+    k = max(1, int(op.steps))
+    sign = 1j if dagger else -1j
+    dt = t / k
+    half = expm_i(GD, 0.5 * dt, sign) if GD is not None else None
+    full = expm_i(GD, dt, sign) if GD is not None else None
+    drive = expm_i(GK, dt, sign) if GK is not None else None
+    flat = from_pyq_shape(state)
+
+    def mul(U, v):
+        return v if U is None else torch.einsum("bij,bj->bi", U, v)
+
+    flat = mul(half, flat)
+    for s_ in range(k):
+        flat = mul(drive, flat)
+        flat = mul(full if s_ < k - 1 else half, flat)
+    return to_pyq_shape(flat, n)
 
 
 def _generator_is_batched(op: Op, values, batch: int) -> bool:

@@ -245,9 +245,83 @@ def adjoint_generator_params(op: Op, compiled: Any, psi: Tensor, lam: Tensor, va
     return psi, lam
 
 
+def trotter_parts(compiled: Any):
+    """(diagonal part, drive part, {qubit: ([X term indices], [Y term indices])}) of a Pauli-sum generator whose non-diagonal
+    terms are all single-qubit X / Y terms (the drive of a neutral-atom Hamiltonian), else None."""
+    dg = [t for t in compiled.ps.terms if all(p[1] == "Z" for p in t.paulis)]
+    off = [t for t in compiled.ps.terms if not all(p[1] == "Z" for p in t.paulis)]
+    if any(len(t.paulis) != 1 or t.paulis[0][1] not in ("X", "Y") for t in off):
+        return None
+    if not hasattr(compiled, "_trotter"):
+        cd = E.CompiledPauliSum.build(PauliSum(compiled.ps.n_qubits, dg)) if dg else None
+        co = E.CompiledPauliSum.build(PauliSum(compiled.ps.n_qubits, off)) if off else None
+        per_q: dict = {}
+        if co is not None:
+            for i, t in enumerate(co.ps.terms):
+                q, axis = t.paulis[0]
+                per_q.setdefault(q, ([], []))[0 if axis == "X" else 1].append(i)
+        prog = None
+        if per_q:
+            from .program import ProgramBuilder
+
+            b = ProgramBuilder(compiled.ps.n_qubits)
+            for q in sorted(per_q):  # exp(-i θ (cos φ X + sin φ Y)) = RZ(φ) RX(2θ) RZ(-φ): applied right to left
+                b.RZ(q, f"__trot_nphi_{q}").RX(q, f"__trot_th_{q}").RZ(q, f"__trot_phi_{q}")
+            prog = E.CompiledProgram(b.build())
+        compiled._trotter = (cd, co, per_q, prog)
+    return compiled._trotter
+
+
+def evolve_trotter(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
+    """ψ ← [e^{-i D dt/2} Π_q e^{-i K_q dt} e^{-i D dt/2}]^k ψ, k = op.steps, dt = t / k: second-order Trotter (Strang) splitting
+    of H = D + Σ_q K_q into its diagonal part D (all-Z strings: `b200sv_diag_evolve`, evaluated on the fly) and the single-qubit
+    drive terms K_q = a_q X_q + b_q Y_q (exact per step: one fused sweep of merged rotations).  Time-symmetric, so the
+    dagger is the same sequence with −t.  Error O(t dt² ‖[D, K]‖)."""
+    parts = trotter_parts(compiled)
+    if parts is None:
+        raise NotImplementedError('algo_hevo="trotter" needs a generator whose non-diagonal terms are single-qubit X / Y terms')
+    cd, co, per_q, prog = parts
+    dev = psi.device
+    B = psi.shape[0]
+    k = max(1, int(op.steps))
+    dt = _time(op, values, B, dev) * ((-1.0 if dagger else 1.0) / k)
+
+    def diag(frac: float) -> None:
+        if cd is None:
+            return
+        coef = cd.coef(values, dev)
+        cf = torch.view_as_real(coef.detach().to(torch.complex128).contiguous())
+        tt = (frac * dt).contiguous()
+        rc = cabi.load().b200sv_diag_evolve(psi.data_ptr(), E._DT[psi.dtype], n, B, cd.terms(dev).data_ptr(), cd.n_terms, cd.n_single, cf.data_ptr(),
+                                            coef.shape[1], tt.data_ptr(), B, 1.0, 0, E._stream_ptr(dev))
+        cabi.check(rc, "diag_evolve (trotter)")
+
+    table = None
+    if prog is not None:
+        coef = co.coef(values, dev).real  # [T_off, 1 or B]; Hermitian generator: real coefficients
+        vals = {}
+        zero = torch.zeros(coef.shape[1], dtype=torch.float64, device=dev)
+        for q, (xs, ys) in per_q.items():
+            a = coef[xs].sum(0) if xs else zero
+            bq = coef[ys].sum(0) if ys else zero
+            phi = torch.atan2(bq, a)
+            vals[f"__trot_phi_{q}"], vals[f"__trot_nphi_{q}"] = phi, -phi
+            vals[f"__trot_th_{q}"] = 2.0 * dt * torch.sqrt(a * a + bq * bq)
+        table = E.pack_params(prog.names, vals, B, dev)
+    out = psi
+    diag(0.5)
+    for s_ in range(k):
+        if prog is not None:
+            out = E._run_segments(prog, out, table, {})
+        diag(1.0 if s_ < k - 1 else 0.5)
+    return out
+
+
 def evolve(op: Op, compiled: Any, psi: Tensor, values: Mapping[str, Tensor], n: int, dagger: bool = False) -> Tensor:
     if op.tsym:
         return evolve_time_dependent(op, compiled, psi, values, n, dagger)
+    if op.steps > 0 and isinstance(op.generator, PauliSum):
+        return evolve_trotter(op, compiled, psi, values, n, dagger)
     dev = psi.device
     B = psi.shape[0]
     t = _time(op, values, B, dev)

@@ -129,7 +129,8 @@ class Op:
     generator: Any = None  # HAMEVO: PauliSum | Program | np.ndarray [2^k,2^k] | str (key of a matrix value)
     label: str = ""  # reference op name, for diagnostics only
     tsym: str = ""  # HAMEVO with a time-dependent generator: name of the time symbol; `param` is then the DURATION
-    steps: int = 0  # ... and the number of integration steps (Configuration.n_steps_hevo)
+    steps: int = 0  # ... and the number of integration steps (Configuration.n_steps_hevo); with an empty `tsym`: the number of
+    #                 second-order Trotter steps of a constant generator (Configuration.algo_hevo = "trotter"), 0 = exact
     # digital noise channels applied right after this op, in order: ((protocol name, (probabilities...)), ...) — what the
     # reference hands to pyqtorch gates as `noise=` (backends/pyqtorch/convert_ops.py:206-208,354-372); see density.py
     noise: tuple = ()
@@ -141,7 +142,9 @@ class Op:
         if self.noise:
             d["noise"] = [[str(nm), [float(x) for x in pr]] for nm, pr in self.noise]
         if self.tsym:
-            d["tsym"], d["steps"] = self.tsym, self.steps
+            d["tsym"] = self.tsym
+        if self.steps:
+            d["steps"] = self.steps
         if self.param is not None:
             if isinstance(self.param, str):
                 d["p"] = self.param

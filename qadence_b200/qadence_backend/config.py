@@ -28,9 +28,13 @@ def default_passes(config: "Configuration") -> list[Callable]:
 class Configuration(BackendConfiguration):
     # ---- options shared with the pyqtorch backend (same names / defaults) ----
     algo_hevo: str = "krylov"
-    """HamEvo algorithm: diagonal generators are exponentiated on the fly, everything else uses the
-    matrix-free Lanczos–Krylov propagator converged to 1e-13 (the reference's `EXP` is a dense
-    `matrix_exp`; results agree to the parity tolerance)."""
+    """HamEvo algorithm.  "krylov" (default; the reference's "EXP" / "EIG" / "RK4" are accepted and mean the same exact
+    propagator): diagonal generators are exponentiated on the fly, everything else uses the matrix-free Lanczos–Krylov
+    propagator converged to 1e-13 (the reference's `EXP` is a dense `matrix_exp`; results agree to the parity tolerance).
+    "trotter": second-order (Strang) splitting of a Pauli-sum generator into its diagonal part (Rydberg interaction,
+    detunings — `b200sv_diag_evolve`) and its single-qubit drive terms (one fused sweep of rotations per step),
+    `n_steps_hevo` steps; error O(t·dt²), i.e. NOT within the 1e-10 parity tolerance — an explicit speed / accuracy knob for
+    neutral-atom programs whose generator norm makes the Krylov space large."""
     ode_solver: object = None
     """Accepted for compatibility (pyqtorch `SolverType`): time-dependent generators always use the exponential-midpoint
     propagator with `n_steps_hevo` steps."""

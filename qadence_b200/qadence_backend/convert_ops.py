@@ -140,7 +140,13 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
             generator = m
         else:
             generator = convert_generator(gen, n_qubits, config)
-        return [Op(OpKind.HAMEVO, tuple(qs), (), param=names[0], generator=generator, label="HamEvo")]
+        steps = 0
+        if str(getattr(config, "algo_hevo", "")).lower() == "trotter":  # second-order Trotter splitting (hamevo.evolve_trotter)
+            from ..program import PauliSum
+
+            if isinstance(generator, PauliSum):
+                steps = max(1, int(config.n_steps_hevo))
+        return [Op(OpKind.HAMEVO, tuple(qs), (), param=names[0], generator=generator, label="HamEvo", steps=steps)]
 
     if isinstance(block, MatrixBlock):
         m = block.matrix.detach().to(torch.complex128).numpy()

@@ -785,3 +785,16 @@ def test_noisy_expectation_is_differentiable_in_ad_and_adjoint_mode(oracle_devic
         hi = value(vals["th"] + (1e-6 if nm == "th" else 0), vals["ph"] + (1e-6 if nm == "ph" else 0))
         lo = value(vals["th"] - (1e-6 if nm == "th" else 0), vals["ph"] - (1e-6 if nm == "ph" else 0))
         assert abs(float(gi) - (hi - lo) / 2e-6) < 1e-7, nm
+
+
+def test_algo_hevo_trotter_reaches_the_converted_program() -> None:
+    """`Configuration(algo_hevo="trotter", n_steps_hevo=k)` marks Pauli-sum HamEvo ops for the Trotter propagator (Op.steps = k);
+    the default and the reference's own AlgoHEvo names keep the exact one (steps = 0)."""
+    from qadence_b200.program import OpKind
+
+    block = HamEvo(add(0.7 * kron(Z(0), Z(1)), 0.3 * X(0), 0.2 * Y(1)), 0.9)
+    for cfg, want in (({}, 0), ({"algo_hevo": "EXP"}, 0), ({"algo_hevo": "trotter", "n_steps_hevo": 25}, 25)):
+        bk = backend_factory("b200sv", diff_mode=None, configuration=cfg)
+        ops = bk.convert(QuantumCircuit(2, block)).circuit.native.program.ops
+        evo = [o for o in ops if o.kind == OpKind.HAMEVO]
+        assert len(evo) == 1 and evo[0].steps == want, (cfg, evo[0].steps)

@@ -93,11 +93,20 @@ def _counting_apply(*a, **k):
     return _orig_apply(*a, **k)
 
 
+_orig_apply_diag = engine.pauli_apply_diag
+
+
+def _counting_apply_diag(*a, **k):
+    _calls["pauli_apply"] += 1
+    return _orig_apply_diag(*a, **k)
+
+
 engine.pauli_apply = _counting_apply
+engine.pauli_apply_diag = _counting_apply_diag
 cfg3()
 torch.cuda.synchronize()
-engine.pauli_apply = _orig_apply
-n_matvec = _calls["pauli_apply"] - 1  # one call is lambda = O psi ... (expectation only: no lambda) -> kept as an upper bound
+engine.pauli_apply, engine.pauli_apply_diag = _orig_apply, _orig_apply_diag
+n_matvec = _calls["pauli_apply"]  # Krylov matvecs of the two non-diagonal HamEvo (the all-Z one is a single elementwise kernel)
 S3 = B * (1 << n) * 16
 # per Lanczos step: matvec 2S + lanczos_a 4S + lanczos_orth 3S + lanczos_next 3S algorithmic bytes
 bytes_per_step = 12 * S3

@@ -253,6 +253,57 @@ def hamevo_td_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = 
     return to_pyq_shape(flat, n)
 
 
+def lindblad_apply(op: Op, state: torch.Tensor, values, n: int) -> torch.Tensor:
+    """`HamEvo(generator, t, noise_operators=[L_k])` on a vectorised density matrix (the doubled register of
+    qadence_b200/density.py: first n/2 qubits = row index of ρ, last n/2 = column index): the reference hands the jump
+    operators to pyqtorch's Lindblad master-equation solver (backends/pyqtorch/convert_ops.py:249-267) and pins the result
+    only against qutip `mesolve` to 6e-2 (tests/backends/pyq/test_time_dependent_generator.py:68-126).  Restated with the
+    exact semigroup: vec(ρ) ← exp(t 𝓛) vec(ρ) on the FULL register, 𝓛 = −i (H ⊗ 1 − 1 ⊗ Hᵀ) + Σ_k [L_k ⊗ L_k* − ½ (L_k†L_k ⊗ 1 +
+    1 ⊗ (L_k†L_k)ᵀ)]; time-dependent generators: `op.steps` exponential-midpoint steps, as `hamevo_td_apply`."""
+    from scipy.linalg import expm
+
+    n0 = n // 2
+    sup = list(op.targets[: len(op.targets) // 2])
+    d = 2**n0
+    batch = state.shape[-1]
+    eye_state = to_pyq_shape(torch.eye(d, dtype=CDTYPE), n0)
+    eye = np.eye(d)
+    diss = np.zeros((d * d, d * d), dtype=np.complex128)
+    for L in op.jumps:
+        Lt = torch.as_tensor(np.asarray(L), dtype=CDTYPE)[:, :, None]
+        Lf = from_pyq_shape(apply_operator(eye_state, Lt, sup)).T.numpy()  # the jump operator on the whole register
+        LL = Lf.conj().T @ Lf
+        diss += np.kron(Lf, Lf.conj()) - 0.5 * (np.kron(LL, eye) + np.kron(eye, LL.T))
+
+    def liouvillian(H: np.ndarray) -> np.ndarray:
+        return -1j * (np.kron(H, eye) - np.kron(eye, H.T)) + diss
+
+    t = _value(values, op.param, batch).to(torch.float64).numpy()
+    flat = from_pyq_shape(state).numpy().copy()  # [B, d*d]
+    if op.tsym:
+        steps = max(1, op.steps)
+        frozen = [type(tt)(1.0 + 0j, (), tt.paulis) for tt in op.generator.terms]
+        dense = []
+        for term in frozen:
+            tmp = eye_state
+            for q, p_ in term.paulis:
+                tmp = apply_operator(tmp, _PAULI[p_][:, :, None], [q])
+            dense.append(from_pyq_shape(tmp).T.numpy())
+        dt = t / steps
+        for k in range(steps):
+            coefs = td_coefficients(op.generator, op.tsym, torch.as_tensor((k + 0.5) * dt), values, batch)
+            for b in range(batch):
+                H = sum(complex(c[b]) * m for c, m in zip(coefs, dense))
+                flat[b] = expm(dt[b] * liouvillian(H)) @ flat[b]
+    else:
+        bsz = batch if _generator_is_batched(op, values, batch) else 1
+        sub = Op(op.kind, tuple(sup), (), param=op.param, generator=op.generator)
+        G = generator_dense(sub.generator, n0, values, sup, bsz).numpy()
+        for b in range(batch):
+            flat[b] = expm(t[b] * liouvillian(G[b if bsz > 1 else 0])) @ flat[b]
+    return to_pyq_shape(torch.as_tensor(flat, dtype=CDTYPE), n)
+
+
 def expm_i(G: torch.Tensor, t: torch.Tensor, sign: complex) -> torch.Tensor:
     """exp(sign·t·G) for batched G [B, d, d], t [B] (sign = ∓i).
 
@@ -272,6 +323,10 @@ def expm_i(G: torch.Tensor, t: torch.Tensor, sign: complex) -> torch.Tensor:
 
 def hamevo_apply(op: Op, state: torch.Tensor, values, n: int, dagger: bool = False) -> torch.Tensor:
     """ψ ← exp(−i t G) ψ with a dense exponential (block_to_tensor.py:409-440; see `expm_i` for the one deviation)."""
+    if op.jumps:
+        if dagger:
+            raise ValueError("a Lindblad evolution has no inverse")
+        return lindblad_apply(op, state, values, n)
     if op.tsym:
         return hamevo_td_apply(op, state, values, n, dagger)
     if op.steps > 0 and isinstance(op.generator, PauliSum):

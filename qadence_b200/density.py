@@ -182,6 +182,12 @@ def vectorise(prog: Program) -> tuple[Program, list[str]]:
     needs: set[str] = set()
     out: list[Op] = []
     for op in prog.ops:
+        if op.kind == OpKind.HAMEVO and op.jumps:
+            # Lindblad evolution: ONE op on the row + column copies of the support; the generator stays the n-qubit one and
+            # `hamevo.evolve_lindblad` builds exp(t·𝓛) on those 2k qubits
+            out.append(Op(OpKind.HAMEVO, tuple(op.targets) + tuple(q + n for q in op.targets), (), param=op.param,
+                          generator=op.generator, label="HamEvo[Lindblad]", tsym=op.tsym, steps=op.steps, jumps=op.jumps))
+            continue
         out.extend(_lift_op(op, n2, 0, False, needs))
         out.extend(_lift_op(op, n2, n, True, needs))
         if op.noise:

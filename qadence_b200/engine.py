@@ -234,7 +234,8 @@ class CompiledProgram:
         if run:
             self.segments.append(Segment(gates=run))
         self.invertible = all(
-            all(_is_unitary_simple(o) for o in s.gates) if s.gates is not None else s.op.kind in (OpKind.HAMEVO, OpKind.MATK)
+            all(_is_unitary_simple(o) for o in s.gates) if s.gates is not None
+            else (s.op.kind in (OpKind.HAMEVO, OpKind.MATK) and not s.op.jumps)  # a Lindblad evolution is a semigroup: no inverse walk
             for s in self.segments
         )
 

@@ -134,6 +134,10 @@ class Op:
     # digital noise channels applied right after this op, in order: ((protocol name, (probabilities...)), ...) — what the
     # reference hands to pyqtorch gates as `noise=` (backends/pyqtorch/convert_ops.py:206-208,354-372); see density.py
     noise: tuple = ()
+    # HAMEVO only: Lindblad jump operators L_k, dense [2^k, 2^k] matrices on `targets` (targets[0] = MSB) — the reference's
+    # `HamEvo(..., noise_operators=[...])` (backends/pyqtorch/convert_ops.py:249-267); the op then evolves a density matrix
+    # under dρ/dt = −i[H, ρ] + Σ_k (L_k ρ L_k† − ½{L_k†L_k, ρ}) (density.py / hamevo.evolve_lindblad)
+    jumps: tuple = ()
 
     def to_json(self) -> dict:
         d: dict[str, Any] = {"kind": int(self.kind), "t": list(self.targets), "c": list(self.controls)}
@@ -141,6 +145,8 @@ class Op:
             d["label"] = self.label
         if self.noise:
             d["noise"] = [[str(nm), [float(x) for x in pr]] for nm, pr in self.noise]
+        if self.jumps:
+            d["jumps"] = [{"shape": list(np.shape(m)), "re": np.real(m).ravel().tolist(), "im": np.imag(m).ravel().tolist()} for m in self.jumps]
         if self.tsym:
             d["tsym"] = self.tsym
         if self.steps:
@@ -204,6 +210,7 @@ class Op:
             tsym=d.get("tsym", ""),
             steps=int(d.get("steps", 0)),
             noise=tuple((str(nm), tuple(float(x) for x in pr)) for nm, pr in d.get("noise", [])),
+            jumps=tuple(mat(x) for x in d.get("jumps", [])),
         )
 
 
@@ -251,7 +258,8 @@ class Program:
 
     @property
     def is_noisy(self) -> bool:
-        return any(op.noise for op in self.iter_ops())
+        # (a Lindblad HAMEVO already lifted to vec(ρ) — 2k targets for 2^k-dimensional jump operators — is an ordinary linear op)
+        return any(op.noise or (op.jumps and 2 ** len(op.targets) == np.shape(op.jumps[0])[0]) for op in self.iter_ops())
 
     def n_gates(self) -> int:
         return sum(1 for _ in self.iter_ops())

@@ -125,10 +125,11 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
 
     if isinstance(block, TimeEvolutionBlock):
         gen = block.generator
+        jumps = _convert_jumps(block)
         if getattr(gen, "is_time_dependent", False):
-            return [_convert_time_dependent(block, n_qubits, config)]
-        if len(getattr(block, "noise_operators", None) or []) > 0:
-            raise NotImplementedError("b200sv: Lindblad `noise_operators` of HamEvo (analog noise) are not supported")
+            op = _convert_time_dependent(block, n_qubits, config)
+            op.jumps = jumps
+            return [op]
         names = config.get_param_name(block)
         if isinstance(gen, sympy.Basic):  # symbolic matrix generator: looked up in param_values (convert_ops.py:231-232)
             generator: Any = names[1]
@@ -142,11 +143,13 @@ def convert_block(block: Any, n_qubits: int | None = None, config: Any = None) -
             generator = convert_generator(gen, n_qubits, config)
         steps = 0
         if str(getattr(config, "algo_hevo", "")).lower() == "trotter":  # second-order Trotter splitting (hamevo.evolve_trotter)
-            from ..program import PauliSum
-
             if isinstance(generator, PauliSum):
                 steps = max(1, int(config.n_steps_hevo))
-        return [Op(OpKind.HAMEVO, tuple(qs), (), param=names[0], generator=generator, label="HamEvo", steps=steps)]
+        if jumps:
+            steps = 0  # the Lindblad propagator is always the exact exponential (hamevo.evolve_lindblad)
+            if not isinstance(generator, (np.ndarray, str, PauliSum)):
+                raise NotImplementedError("b200sv: a HamEvo with `noise_operators` needs a Pauli-like or matrix generator")
+        return [Op(OpKind.HAMEVO, tuple(qs), (), param=names[0], generator=generator, label="HamEvo", steps=steps, jumps=jumps)]
 
     if isinstance(block, MatrixBlock):
         m = block.matrix.detach().to(torch.complex128).numpy()
@@ -222,6 +225,24 @@ def _convert_time_dependent(block: Any, n_qubits: int, config: Any) -> Op:
         dur = float(_numeric(duration))
     return Op(OpKind.HAMEVO, tuple(block.qubit_support), (), param=dur, generator=ps, label="HamEvo(t)",
               tsym=times.pop(), steps=int(config.n_steps_hevo))
+
+
+def _convert_jumps(block: Any) -> tuple:
+    """`HamEvo.noise_operators` → dense jump operators on the HamEvo's qubit support (backends/pyqtorch/convert_ops.py:249-256;
+    the constructor, operations/ham_evo.py:157-170, already rejects parametric operators and supports outside the generator's)."""
+    ops = getattr(block, "noise_operators", None) or []
+    if len(ops) == 0:
+        return ()
+    from qadence.blocks.block_to_tensor import block_to_tensor
+
+    qs = tuple(block.qubit_support)
+    if len(qs) > 5:
+        raise NotImplementedError("b200sv: `noise_operators` are supported on HamEvo blocks of up to 5 qubits (dense superoperator)")
+    out = []
+    for nb in ops:
+        m = block_to_tensor(nb, {}, qubit_support=qs, use_full_support=False)
+        out.append(m.detach().to(torch.complex128).reshape(m.shape[-2], m.shape[-1]).numpy())
+    return tuple(out)
 
 
 def _scale_symbols(block: Any) -> set:

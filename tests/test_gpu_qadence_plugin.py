@@ -122,6 +122,52 @@ def test_backend_factory_call_sequence() -> None:
     assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in params.values() if p.requires_grad)
 
 
+def test_lindblad_noise_operators_and_dropout_through_the_plugin() -> None:
+    """`HamEvo(..., noise_operators=[...])` (tests/backends/pyq/test_time_dependent_generator.py:68-126) returns the density
+    matrix of the integrated master equation; expectation = Tr(Oρ).  Quantum dropout: the training-mode circuit equals
+    the oracle on the SAME dropped sub-program, evaluation mode equals the full circuit."""
+    from tests.test_lindblad import integrate_master_equation
+
+    X2, Z2, I2 = np.array([[0, 1], [1, 0]], dtype=complex), np.diag([1.0 + 0j, -1]), np.eye(2)
+    gen = 0.9 * qadence.X(0) + 0.6 * qadence.Z(0) * qadence.Z(1) + 0.3 * qadence.Y(1)
+    block = chain(qadence.RX(0, 0.4), qadence.HamEvo(gen, 1.2, noise_operators=[0.7 * qadence.X(1), 0.4 * qadence.Z(0)]))
+    model = QuantumModel(QuantumCircuit(2, block), total_magnetization(2), backend="b200sv", diff_mode=DiffMode.GPSR)
+    rho = model.run({})
+    assert type(rho).__name__ == "DensityMatrix"
+    H = 0.9 * np.kron(X2, I2) + 0.6 * np.kron(Z2, Z2) + 0.3 * np.kron(I2, np.array([[0, -1j], [1j, 0]]))
+    psi = oracle.run(model.backend.backend.circuit(QuantumCircuit(2, qadence.RX(0, 0.4))).native.program, {})[0].numpy()
+    want = integrate_master_equation(lambda t: H, [0.7 * np.kron(I2, X2), 0.4 * np.kron(Z2, I2)], np.outer(psi, psi.conj()), 1.2)
+    assert np.abs(rho[0].cpu().numpy() - want).max() < 1e-9
+    e = model.expectation({})
+    assert abs(float(e) - np.trace((np.kron(Z2, I2) + np.kron(I2, Z2)) @ want).real) < 1e-9
+
+    n = 4
+    circ = QuantumCircuit(n, chain(feature_map(n, param="x"), hea(n, 2)))
+    model = QuantumModel(circ, total_magnetization(n), backend="b200sv", diff_mode=DiffMode.ADJOINT, configuration={"dropout_probability": 0.5})
+    x = {"x": torch.linspace(-0.5, 0.5, 3, dtype=torch.float64)}
+    nat = model._circuit.native
+    vals = model.embedding_fn(model._params, x)
+    host = {k: torch.as_tensor(v).detach().cpu() for k, v in vals.items()}
+    model.train()
+    torch.manual_seed(3)
+    sub = nat.compiled_for_call(True, vals)
+    torch.manual_seed(3)
+    e_train = model.expectation(x)
+    assert (e_train.detach().cpu() - oracle.expectation(sub.program, [total_magnetization_sum(n)], host)).abs().max() < 1e-10
+    assert len(sub.program.ops) < len(nat.program.ops)
+    e_train.sum().backward()
+    assert any(p.grad is not None for p in model.parameters())
+    model.eval()
+    e_eval = model.expectation(x)
+    assert (e_eval.detach().cpu() - oracle.expectation(nat.program, [total_magnetization_sum(n)], host)).abs().max() < 1e-10
+
+
+def total_magnetization_sum(n: int):
+    from qadence_b200.program import total_magnetization as tm
+
+    return tm(n)
+
+
 def test_replace_mode_in_a_subprocess() -> None:
     """`B200SV_REPLACE_PYQTORCH=1`: `backend="pyqtorch"` (qadence's default) builds the b200sv backend and runs on the GPU."""
     import subprocess

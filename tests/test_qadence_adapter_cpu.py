@@ -329,6 +329,52 @@ def test_time_dependent_hamevo_through_quantum_model(oracle_device, duration: fl
     assert torch.allclose(state, state1)
 
 
+def _noise_ops():
+    from qadence.blocks import MatrixBlock
+
+    return [qadence.I(0) * qadence.I(1), qadence.X(0),
+            MatrixBlock(block_to_tensor(qadence.X(0), qubit_support=(0, 1), use_full_support=True), qubit_support=(0, 1))]
+
+
+@pytest.mark.parametrize("duration", [0.5, 1.0])
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_noisy_time_dependent_hamevo_through_quantum_model(oracle_device, duration: float, which: int) -> None:
+    """Mirror of the reference's tests/backends/pyq/test_time_dependent_generator.py:68-126 (`HamEvo(...,
+    noise_operators=[L])`, a density matrix comes back) with the integrated master equation in place of qutip `mesolve`
+    (not installed here); the reference's acceptance is MIDDLE_ACCEPTANCE = 6e-2, we ask 1e-5."""
+    import sympy
+    from qadence.parameters import Parameter, TimeParameter
+
+    from tests.test_lindblad import integrate_master_equation
+    from tests.test_time_dependent import FY, OMEGA, X as Xm, Y as Ym, I2
+
+    noise_op = _noise_ops()[which]
+    t, x = TimeParameter("t"), Parameter("x", trainable=False)
+    hamevo = qadence.HamEvo(OMEGA * (sympy.sin(FY * t) * qadence.X(0) + x * (t**2) * qadence.Y(1)), "t", noise_operators=[noise_op])
+    values = {"x": torch.tensor(2.0), "duration": torch.tensor(duration)}
+    model = QuantumModel(QuantumCircuit(2, hamevo), backend="b200sv", diff_mode=DiffMode.AD, configuration={"n_steps_hevo": 500})
+    rho = model.run(values=values)
+    assert type(rho).__name__ == "DensityMatrix" and rho.shape == (1, 4, 4)
+    L = block_to_tensor(noise_op, qubit_support=(0, 1), use_full_support=True).squeeze(0).numpy()
+    rho0 = np.zeros((4, 4), dtype=np.complex128)
+    rho0[0, 0] = 1
+    want = integrate_master_equation(lambda s: OMEGA * (np.sin(FY * s) * np.kron(Xm, I2) + 2.0 * s**2 * np.kron(I2, Ym)), [L], rho0, duration)
+    assert np.abs(rho[0].numpy() - want).max() < 1e-5
+    rho1 = qadence.run(hamevo, values=values, backend="b200sv", configuration={"n_steps_hevo": 500})
+    assert torch.allclose(rho, rho1)
+
+
+def test_noisy_constant_hamevo_conversion() -> None:
+    """Constant generator + jump operators: exact semigroup, jump operators as dense matrices on the HamEvo support."""
+    gen = 0.7 * qadence.X(0) + 0.4 * qadence.Z(0) * qadence.Z(2)
+    bk = backend_factory("b200sv", diff_mode=None)
+    conv = bk.convert(QuantumCircuit(3, qadence.HamEvo(gen, 1.3, noise_operators=[qadence.X(2), 0.5 * qadence.Z(0)])))
+    (op,) = conv.circuit.native.program.ops
+    assert op.targets == (0, 2) and len(op.jumps) == 2 and op.jumps[0].shape == (4, 4)
+    assert np.allclose(op.jumps[0], np.kron(np.eye(2), [[0, 1], [1, 0]])) and np.allclose(op.jumps[1], 0.5 * np.kron(np.diag([1, -1]), np.eye(2)))
+    assert conv.circuit.native.is_noisy
+
+
 # ------------------------------------------------------------------------------------------ device-side embedding
 @pytest.fixture(autouse=True)
 def oracle_embedding_device(request: pytest.FixtureRequest, monkeypatch: pytest.MonkeyPatch) -> None:

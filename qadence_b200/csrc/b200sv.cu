@@ -284,9 +284,15 @@ int make_tensor_map(CUtensorMap* out, void* state, int amp_bytes, int64_t batch,
 }
 
 // (real, R, M, ADJ) combinations lean_sweep_kernel is compiled for
+#ifdef B200SV_LEAN_EXPERIMENTAL  // tuning builds only (tools/gpu_call12.sh)
+#define B200SV_LEAN_EXTRA(X) X(double, 5, 11, false) X(double, 5, 10, false) X(double, 4, 9, true)
+#else
+#define B200SV_LEAN_EXTRA(X)
+#endif
 #define B200SV_LEAN_INSTANCES(X)                                                                          \
+  B200SV_LEAN_EXTRA(X)                                                                                    \
   X(double, 4, 11, false) X(double, 5, 12, false) X(double, 4, 10, false)                                 \
-  X(double, 3, 10, true) X(double, 4, 11, true) X(double, 3, 11, true)                                    \
+  X(double, 4, 10, true) X(double, 3, 10, true) X(double, 4, 11, true) X(double, 3, 11, true)             \
   X(float, 4, 12, false) X(float, 5, 12, false) X(float, 4, 11, false)                                    \
   X(float, 3, 11, true) X(float, 4, 12, true) X(float, 4, 11, true)
 

@@ -238,16 +238,30 @@ template <int I, typename F> __device__ __forceinline__ void static_for_down(F&&
 
 // launch geometry per instantiation: CTAs per SM the register allocation targets (threads per CTA = 2^(M-R))
 #ifndef B200SV_LEAN_REGS_FWD_D_R4
-#define B200SV_LEAN_REGS_FWD_D_R4 168  // complex128 forward, r = 4: the tile alignment leaves room for 3 CTAs per SM anyway
+#define B200SV_LEAN_REGS_FWD_D_R4 128  // complex128 forward, r = 4: 8 CTAs of 64 threads (2^10-amplitude tiles, packed layout); measured 26.2 vs 28.1 ms per pass at 168
+#endif
+#ifndef B200SV_LEAN_REGS_64
+#define B200SV_LEAN_REGS_64 128  // 64 data registers (complex128 adjoint r = 3, complex64 r = 4 / adjoint r = 3 ...): 4 CTAs of 128 threads
+#endif
+#ifndef B200SV_LEAN_REGS_ADJ_D_R2
+#define B200SV_LEAN_REGS_ADJ_D_R2 80  // experimental r = 2 adjoint tiles: 6 warps per scheduler
 #endif
 template <typename real, int R, int M, bool ADJ> struct LeanCfg {
   static constexpr int NT = 1 << (M - R);
   static constexpr int DATA_REGS = (1 << R) * (ADJ ? 2 : 1) * (int)(2 * sizeof(real) / 4);
   // registers per thread the kernel may use = 65536 / (NT * MINB), capped at 255
   // registers per thread the kernel may use = 65536 / (NT * MINB), capped at 255
-  static constexpr int REGS_WANTED = DATA_REGS >= 128 ? 255 : (DATA_REGS >= 64 ? ((sizeof(real) == 8 && !ADJ && R == 4) ? B200SV_LEAN_REGS_FWD_D_R4 : 128) : 128);
+  static constexpr int REGS_WANTED = DATA_REGS >= 128 ? 255 : (DATA_REGS >= 64 ? ((sizeof(real) == 8 && !ADJ && R == 4) ? B200SV_LEAN_REGS_FWD_D_R4 : B200SV_LEAN_REGS_64)
+                                                                : ((sizeof(real) == 8 && ADJ && R == 2) ? B200SV_LEAN_REGS_ADJ_D_R2 : 128));
   static constexpr int MINB_RAW = 65536 / (NT * REGS_WANTED);
   static constexpr int MINB = MINB_RAW < 1 ? 1 : MINB_RAW;
+  // Shared-memory layout.  ALIGNED: the tile buffers are aligned to their own size inside the window, so a thread's address is
+  // base | offset and the per-amplitude masks are XOR-ed straight into it (cheapest addressing) — at the price of up to one
+  // tile of slack per CTA.  Packed (tiles first, tables behind, address = base + (offset ^ mask), one more add per access):
+  // taken where the slack would cost resident CTAs (B200: 227 KB per SM, 1 KB reserved per CTA).
+  static constexpr int TILE_BYTES = (1 << M) * 2 * (int)sizeof(real);
+  static constexpr int ALIGNED_SMEM = ((ADJ ? 2 : 1) + 1) * TILE_BYTES + 1024;
+  static constexpr bool ALIGNED = MINB * ALIGNED_SMEM <= 227 * 1024;
 };
 
 template <typename real, int R, bool ADJ> __host__ __device__ inline size_t lean_table_bytes(int n_rounds, int n_exec, int nt) {
@@ -262,17 +276,14 @@ template <typename real, int R, bool ADJ> __host__ __device__ inline size_t lean
 template <typename real, int R, int M, bool ADJ> inline size_t lean_smem_bytes(int n_rounds, int n_exec) {
   const size_t tile_bytes = ((size_t)1 << M) * 2 * sizeof(real);
   const size_t tables = lean_table_bytes<real, R, ADJ>(n_rounds, n_exec, 1 << (M - R));
-  // buffers are aligned to tile_bytes inside the window: one tile of slack, split before / after the buffers; the tables
-  // go into whichever part holds them (the kernel decides from the actual window address)
+  if (!LeanCfg<real, R, M, ADJ>::ALIGNED) return (size_t)(ADJ ? 2 : 1) * tile_bytes + tables;
+  // aligned buffers: one tile of slack, split before / after the buffers; the tables go into whichever part holds them (the
+  // kernel decides from the actual window address)
   size_t slack = tile_bytes;
   while (slack / 2 < tables && slack < 4 * tile_bytes) slack += tile_bytes;
   return (size_t)(ADJ ? 2 : 1) * tile_bytes + slack;
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Warp reduction of the 4 moments of up to R slots at once (transposed butterfly over 4*R values: after the level with
-// lane-bit b only the lanes' own half of the values is kept, so 4R values cost ~4R shuffles instead of 5 * 4R).  On return
-// lane L holds the warp total of value `lean_reduce_index<R>(L)` (or garbage if that is < 0).
 template <int R> __device__ __forceinline__ int lean_reduce_index(int lane) {
   // value kept by a lane after the levels 16, 8, 4, 2 (level 1 leaves both lanes of a pair with the total); -1: padding
   static_assert(4 * R <= 16, "one value per lane pair");
@@ -336,12 +347,14 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
   const int n_rounds = sw.n_rounds, n_exec = sw.n_exec;
   const bool use_tma = A.tg.rank > 0;
 
-  // ---- shared-memory carve-up: tile buffers aligned to TILE_BYTES (so that address = base ^ mask), tables in the slack
+  // ---- shared-memory carve-up (LeanCfg::ALIGNED): buffers aligned to TILE_BYTES with the tables in the slack, or packed
+  constexpr bool ALIGNED = LeanCfg<real, R, M, ADJ>::ALIGNED;
   const unsigned sbase = smem_u32(smem_raw);
-  const unsigned pad = (0u - sbase) & (TILE_BYTES - 1u);
   const unsigned buf_bytes = (unsigned)NSTATE * TILE_BYTES;
   const unsigned tbl_bytes = (unsigned)lean_table_bytes<real, R, ADJ>(n_rounds, n_exec, NT);
-  unsigned char* tbl = (pad >= tbl_bytes) ? smem_raw : smem_raw + pad + buf_bytes;
+  const unsigned pad = ALIGNED ? ((0u - sbase) & (TILE_BYTES - 1u)) : 0u;
+  unsigned char* tbl = (ALIGNED && pad >= tbl_bytes) ? smem_raw : smem_raw + pad + buf_bytes;
+  unsigned char* const tile_ptr = smem_raw + pad;
   const unsigned tile_psi = sbase + pad;
   const unsigned mbar0 = smem_u32(tbl);
   volatile long long* s_tile = reinterpret_cast<volatile long long*>(tbl + 16);  // the tile this CTA works on next (-1: none)
@@ -506,8 +519,9 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
         ms[a] = (int)T[38 + a];
         if (ms[a] != (int)LT_EMPTY) base ^= ro[a] & gt[ms[a]].flipmask;
       }
-      const unsigned la0 = tile_psi | (base & 0xffffu);  // the buffer is TILE_BYTES-aligned: OR == ADD, later XORs stay inside
-      const unsigned sa0 = tile_psi | (base >> 16);
+      // ALIGNED: the buffer is TILE_BYTES-aligned, OR == ADD and the later XORs stay inside; packed: offsets, base added per access
+      const unsigned la0 = ALIGNED ? (tile_psi | (base & 0xffffu)) : (base & 0xffffu);
+      const unsigned sa0 = ALIGNED ? (tile_psi | (base >> 16)) : (base >> 16);
       auto xmask = [&](int j, int sh) {
         unsigned o = 0;
 #pragma unroll
@@ -521,48 +535,106 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const unsigned a = la0 ^ xmask(j, 0);
-        p[j] = lds_c2<c2>(a);
-        if constexpr (ADJ) l[j] = lds_c2<c2>(a + TILE_BYTES);
+#ifdef B200SV_LEAN_DBGX  // timing experiments only (results invalid): bit 4 = no tile traffic in the rounds, bit 8 = no barriers
+        if (A.dbg & 4) {
+          p[j].x = (real)(a & 1023u) * (real)0.001; p[j].y = (real)(j + 1) * (real)0.01;
+          if constexpr (ADJ) { l[j].x = p[j].y; l[j].y = p[j].x; }
+          continue;
+        }
+#endif
+        // plain shared-window accesses (the buffers start the dynamic window): the base folds into the instruction
+        if constexpr (ALIGNED) {
+          p[j] = lds_c2<c2>(a);
+          if constexpr (ADJ) l[j] = lds_c2<c2>(a + TILE_BYTES);
+        } else {
+          p[j] = *reinterpret_cast<const c2*>(tile_ptr + a);
+          if constexpr (ADJ) l[j] = *reinterpret_cast<const c2*>(tile_ptr + a + TILE_BYTES);
+        }
       }
+#ifdef B200SV_LEAN_DBGX
+      if (need_sync && !(A.dbg & 8)) __syncthreads();
+#else
       if (need_sync) __syncthreads();  // every register file is loaded before anyone stores at permuted / re-laid-out addresses
+#endif
 
       if (!(A.dbg & 1)) {
-        if constexpr (!ADJ) {
-          static_for_up<0, R>([&](auto ic) {
-            constexpr int a = decltype(ic)::value;
-            if (ms[a] != (int)LT_EMPTY) RG::template nmat<a>(p, gt[ms[a]].m);
-          });
-        } else {
-          // The chains of one round act on different qubits, so <lambda|P_a|psi> does not care whether the OTHER slots
-          // are already un-applied (their 2x2 commute with P_a and cancel between bra and ket up to the real factor the
-          // resolve kernel tracks): all moments of the round are taken first, from the same registers, and reduced together.
-          bool any = false;
+        // Full rounds (every slot holds a chain — all rounds of an HEA sweep but its first / last) take a straight-line copy of
+        // the body: no per-slot tests, branches and reconvergence points (~70 of ~850 instructions of an adjoint round)
+        bool full = true;
 #pragma unroll
-          for (int a = 0; a < R; ++a) any |= ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN;
-          if (any) {  // uniform across the CTA
-            double mo[4 * R];
+        for (int a = 0; a < R; ++a) {
+          full &= ms[a] != (int)LT_EMPTY;
+          if constexpr (ADJ) full &= (gt[ms[a] != (int)LT_EMPTY ? ms[a] : n_exec].gr & 0xff) == GR_CHAIN;
+        }
+#ifdef B200SV_LEAN_DBGX
+        if (A.dbg & (16 | 32 | 64)) full = false;  // the timing experiments live in the general body; bit 64: general body only
+#endif
+        // measured (cfg2, ms per pass): adjoint r = 3 93.2 -> 89.5 with the straight-line copy; forward r = 4 26.2 -> 27.8 and
+        // adjoint r = 4 85.6 -> 88.4 (the second copy costs registers there): taken for the r <= 3 adjoint instantiations only
+        constexpr bool HAS_FAST = ADJ && R <= 3;
+        if (!HAS_FAST) full = false;
+        auto math = [&](auto fast_tag) {
+          constexpr bool FAST = decltype(fast_tag)::value;
+          if constexpr (!ADJ) {
             static_for_up<0, R>([&](auto ic) {
               constexpr int a = decltype(ic)::value;
-              double m4[4] = {0.0, 0.0, 0.0, 0.0};
-              if (ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN) RG::template moments<a>(p, l, m4);
-              mo[4 * a] = m4[0]; mo[4 * a + 1] = m4[1]; mo[4 * a + 2] = m4[2]; mo[4 * a + 3] = m4[3];
+              if (FAST || ms[a] != (int)LT_EMPTY) RG::template nmat<a>(p, gt[ms[a]].m);
             });
-            const int lane = tid & 31;
-            const double tot = lean_reduce_moments<R>(mo, lane);
-            const int vi = lean_reduce_index<R>(lane);
-            if ((lane & 1) == 0 && vi >= 0) {
-              const int x = ms[vi >> 2];
-              if (x != (int)LT_EMPTY) gsum[(x * NWARP + (tid >> 5)) * 4 + (vi & 3)] += tot;
+          } else {
+            // The chains of one round act on different qubits, so <lambda|P_a|psi> does not care whether the OTHER slots
+            // are already un-applied (their 2x2 commute with P_a and cancel between bra and ket up to the real factor the
+            // resolve kernel tracks): all moments of the round are taken first, from the same registers, and reduced together.
+            bool any = FAST;
+            if constexpr (!FAST) {
+#pragma unroll
+              for (int a = 0; a < R; ++a) any |= ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN;
+#ifdef B200SV_LEAN_DBGX
+              if (A.dbg & 16) any = false;  // bit 16: no moments at all
+#endif
             }
+            if (any) {  // uniform across the CTA
+              double mo[4 * R];
+              static_for_up<0, R>([&](auto ic) {
+                constexpr int a = decltype(ic)::value;
+                double m4[4] = {0.0, 0.0, 0.0, 0.0};
+                if (FAST || (ms[a] != (int)LT_EMPTY && (gt[ms[a]].gr & 0xff) == GR_CHAIN)) RG::template moments<a>(p, l, m4);
+                mo[4 * a] = m4[0]; mo[4 * a + 1] = m4[1]; mo[4 * a + 2] = m4[2]; mo[4 * a + 3] = m4[3];
+              });
+              const int lane = tid & 31;
+              bool reduce = true;
+#ifdef B200SV_LEAN_DBGX
+              if (A.dbg & 32) {  // bit 32: moments without the cross-lane reduction
+                double chk = 0;
+#pragma unroll
+                for (int i = 0; i < 4 * R; ++i) chk += mo[i];
+                if (chk == 123456.789) gsum[0] += chk;
+                reduce = false;
+              }
+#endif
+              if (reduce) {
+                const double tot = lean_reduce_moments<R>(mo, lane);
+                const int vi = lean_reduce_index<R>(lane);
+                if ((lane & 1) == 0 && vi >= 0) {
+                  const int x = ms[vi >> 2];
+                  if (FAST || x != (int)LT_EMPTY) gsum[(x * NWARP + (tid >> 5)) * 4 + (vi & 3)] += tot;
+                }
+              }
+            }
+            static_for_down<R - 1>([&](auto ic) {
+              constexpr int a = decltype(ic)::value;
+              if (FAST || ms[a] != (int)LT_EMPTY) {
+                const LeanGate<real>& g = gt[ms[a]];
+                RG::template nmat<a>(p, g.m);
+                RG::template nmat<a>(l, g.m);
+              }
+            });
           }
-          static_for_down<R - 1>([&](auto ic) {
-            constexpr int a = decltype(ic)::value;
-            if (ms[a] != (int)LT_EMPTY) {
-              const LeanGate<real>& g = gt[ms[a]];
-              RG::template nmat<a>(p, g.m);
-              RG::template nmat<a>(l, g.m);
-            }
-          });
+        };
+        if constexpr (HAS_FAST) {
+          if (full) math(std::true_type{});
+          else math(std::false_type{});
+        } else {
+          math(std::false_type{});
         }
       }
       if (rr == n_rounds - 1 && scale) {  // the sweep's pending scalar, once per amplitude
@@ -580,14 +652,31 @@ lean_sweep_kernel(const __grid_constant__ LeanArgs<real> A, const __grid_constan
           }
         }
       }
+#ifdef B200SV_LEAN_DBGX
+      if (A.dbg & 4) {  // keep the arithmetic alive without the stores
+        real chk = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { chk += p[j].x + p[j].y; if constexpr (ADJ) chk += l[j].x + l[j].y; }
+        if (chk == (real)123456.789) sts_c2(ALIGNED ? sa0 : tile_psi + sa0, p[0]);
+      } else
+#endif
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const unsigned a = sa0 ^ xmask(j, 16);
-        sts_c2(a, p[j]);
-        if constexpr (ADJ) sts_c2(a + TILE_BYTES, l[j]);
+        if constexpr (ALIGNED) {
+          sts_c2(a, p[j]);
+          if constexpr (ADJ) sts_c2(a + TILE_BYTES, l[j]);
+        } else {
+          *reinterpret_cast<c2*>(tile_ptr + a) = p[j];
+          if constexpr (ADJ) *reinterpret_cast<c2*>(tile_ptr + a + TILE_BYTES) = l[j];
+        }
       }
       if (use_tma && rr == n_rounds - 1) fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+#ifdef B200SV_LEAN_DBGX
+      if (!(A.dbg & 8) || rr == n_rounds - 1) __syncthreads();
+#else
       __syncthreads();
+#endif
     }
     if (tracing) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); trow[1] = now; }
 

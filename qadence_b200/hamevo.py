@@ -376,7 +376,7 @@ def evolve_lindblad(op: Op, compiled: Any, rho: Tensor, values: Mapping[str, Ten
 
     g = op.generator
     if op.tsym:
-        terms = _pauli_terms_dense(g, sup)
+        terms = _pauli_terms_dense(compiled.ps, sup)
         steps = max(1, op.steps)
         dt = t / steps
         props = [np.eye(d * d, dtype=np.complex128) for _ in range(B)]
@@ -388,7 +388,7 @@ def evolve_lindblad(op: Op, compiled: Any, rho: Tensor, values: Mapping[str, Ten
     else:
         if isinstance(g, PauliSum):
             coef = compiled.coef(values, cpu).detach().numpy()  # [T, 1 or B]
-            terms = _pauli_terms_dense(g, sup)
+            terms = _pauli_terms_dense(compiled.ps, sup)
             hs = [np.tensordot(coef[:, b], terms, axes=1) for b in range(coef.shape[1])]
         elif isinstance(g, str):
             m = torch.as_tensor(values[g]).detach().to(torch.complex128).cpu()

@@ -57,6 +57,7 @@ LT_STRIDE = 48
 LT_EMPTY = 0xFFFF
 TMA_SWIZZLE_FLAG = 0x100  # b200sv_tma.rank bit 8: the tensor map uses CU_TENSOR_MAP_SWIZZLE_128B
 TMA_SWIZZLE_DEFAULT = "0"
+VPERM_DEFAULT = "1"  # track the folded permutations of a lean sweep instead of applying them round by round (_lean_sweep_tables)
 
 GK_MAT, GK_REAL, GK_RX, GK_RY, GK_RZ, GK_PHASE, GK_DIAG, GK_X, GK_SWAP, GK_SCALE = range(10)
 GF_GRAD = 1
@@ -101,8 +102,14 @@ class TileConfig:
             # forward: 2^10-amplitude tiles with 64-thread CTAs (7 per SM) beat 2^11 / 128 threads (3 per SM, the tile
             # alignment slack costs the fourth) although cfg2 then needs 9 sweeps instead of 8: 9 x 3.17 ms vs 8 x 3.87 ms
             # (profiles/r02_lean_kernel.md)
-            return TileConfig(m=10, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=3, low=2, fold=3, adjoint=True)
-        return TileConfig(m=12, r=4, low=2, fold=4) if not adjoint else TileConfig(m=11, r=3, low=2, fold=4, adjoint=True)
+            # adjoint: r = 4 (16 amplitudes of psi and lambda per thread, 255 registers, 4 CTAs of 64 threads per SM): 48 instead
+            # of 61 rounds for cfg2 — the per-round overhead (tile exchange, moment reduction) outweighs the 8 instead of 16
+            # warps per SM: 85.6 ms per pass (9 sweeps) vs 93.2 ms with r = 3 (8 sweeps)
+            return TileConfig(m=10, r=4, low=2, fold=3) if not adjoint else TileConfig(m=10, r=4, low=2, fold=3, adjoint=True)
+        # complex64: the sweeps are issue bound (FFMA is not the limit), so the per-round overhead decides: more register
+        # bits per round.  cfg2, ms per pass (profiles/r02_lean_kernel.md §7): forward (12,4) 22.9 -> (12,5) 18.1; adjoint
+        # (11,3) 70.8 -> (11,4) 52.1
+        return TileConfig(m=12, r=5, low=2, fold=4) if not adjoint else TileConfig(m=11, r=4, low=2, fold=4, adjoint=True)
 
 
 @dataclass
@@ -694,6 +701,18 @@ def build_plan(ops: Sequence[Op], n: int, slot_of: dict[str, int], cfg: TileConf
                 leaders[fx + int(gates[gi]["xidx"])] = gi
     plan = SweepPlan(n, cfg, sweeps, rounds, gates, pool.array(), len(ops), leaders, order=order)
     finish_lean(plan, n_total)
+    if r > 4 and any(int(sw["io_mode"]) == IO_GENERIC for sw in plan.sweeps):
+        # the generic kernel holds at most 4 register bits: a plan with sweeps the lean kernel cannot take (small registers,
+        # controlled gates, sharded states) is rebuilt with r = 4
+        from dataclasses import replace
+
+        return build_plan(ops, n, slot_of, replace(cfg, r=4), chains, n_total, packer)
+    if cfg.adjoint and cfg.c128 and r == 4 and any(int(sw["io_mode"]) == IO_GENERIC for sw in plan.sweeps):
+        # ... and its complex128 adjoint variant was tuned with r = 3 (r = 4 would be 128 data registers of psi and lambda
+        # next to the interpreter's state): keep that geometry for plans that are not purely lean
+        from dataclasses import replace
+
+        return build_plan(ops, n, slot_of, replace(cfg, r=3), chains, n_total, packer)
     return plan
 
 
@@ -761,13 +780,68 @@ def _swz_b(e: int, c128: bool) -> int:
     return e ^ (((e >> 3) ^ (e >> 6) ^ (e >> 9)) & 7) if c128 else e ^ (((e >> 4) ^ (e >> 8)) & 15)
 
 
-def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_layout: bool, store_plain_layout: bool,
-                      tma_swizzle: bool = False) -> np.ndarray:
-    """One round's B200SV_LT_STRIDE words for one direction (layout documented in include/b200sv.h).  `*_plain_layout`:
-    that side of the round faces the TMA-written / TMA-read tile (box order, hardware-swizzled if `tma_swizzle`)."""
+class _Affine:
+    """x -> XOR_{bits i of x} cols[i] ^ const ^ XOR_{external bit e set in the tile index} ext[e] on GF(2)^m."""
+
+    def __init__(self, cols: list[int], const: int = 0, ext: dict[int, int] | None = None):
+        self.cols, self.const, self.ext = list(cols), int(const), {k: v for k, v in (ext or {}).items() if v}
+
+    @staticmethod
+    def identity(m: int) -> "_Affine":
+        return _Affine([1 << i for i in range(m)])
+
+    @staticmethod
+    def of_round(rd, m: int) -> "_Affine":
+        if not (int(rd["flags"]) & RF_PERM):
+            return _Affine.identity(m)
+        ext = {int(rd["pext"][k]["bit"]): int(rd["pext"][k]["vec"]) for k in range(int(rd["n_pext"]))}
+        return _Affine([int(x) for x in rd["pcol"][:m]], int(rd["pconst"]), ext)
+
+    def lin(self, v: int) -> int:
+        out, i = 0, 0
+        while v:
+            if v & 1:
+                out ^= self.cols[i]
+            v >>= 1
+            i += 1
+        return out
+
+    def after(self, first: "_Affine") -> "_Affine":
+        """self ∘ first."""
+        ext = dict(self.ext)
+        for e, v in first.ext.items():
+            ext[e] = ext.get(e, 0) ^ self.lin(v)
+        return _Affine([self.lin(c) for c in first.cols], self.const ^ self.lin(first.const), ext)
+
+    def inverse(self) -> "_Affine":
+        m = len(self.cols)
+        inv = {self.lin(x): x for x in range(1 << m)}
+        assert len(inv) == 1 << m, "not a permutation"
+        lin_inv = _Affine([inv[1 << i] for i in range(m)])
+        return _Affine(lin_inv.cols, lin_inv.lin(self.const), {e: lin_inv.lin(v) for e, v in self.ext.items()})
+
+    @property
+    def is_identity(self) -> bool:
+        return not self.const and not self.ext and self.cols == [1 << i for i in range(len(self.cols))]
+
+
+def _rank_gf2(vs: list[int]) -> int:
+    basis: list[int] = []
+    for v in vs:
+        for b_ in basis:
+            v = min(v, v ^ b_)
+        if v:
+            basis.append(v)
+    return len(basis)
+
+
+def _lean_table(rd, m: int, r: int, c128: bool, lmap: _Affine, smap: _Affine, load_plain_layout: bool, store_plain_layout: bool,
+                tma_swizzle: bool = False, reorder_threads: bool = False) -> np.ndarray:
+    """One round's B200SV_LT_STRIDE words for one direction (layout documented in include/b200sv.h): the amplitude whose
+    position in the ROUND'S OWN frame is x (thread bits -> `thrpos`, register bits -> `regpos`) is loaded from tile position
+    lmap(x) and stored to smap(x).  `*_plain_layout`: that side of the round faces the TMA-written / TMA-read tile (box order,
+    hardware-swizzled if `tma_swizzle`); otherwise the bank-swizzled layout between rounds."""
     shift = 4 if c128 else 3
-    perm = bool(int(rd["flags"]) & RF_PERM)
-    pcol = [int(x) for x in rd["pcol"][:m]]
     regs = [int(x) for x in rd["regpos"][: min(r, 4)]] + ([int(rd["regpos4"])] if r > 4 else [])
     thr = [int(x) for x in rd["thrpos"][: m - r]]
 
@@ -776,38 +850,103 @@ def _lean_round_table(rd, m: int, r: int, c128: bool, forward: bool, load_plain_
             return (_swz_a(v, c128) if tma_swizzle else v) << shift
         return _swz_b(v, c128) << shift
 
-    def word(plain_v: int, perm_v: int) -> int:
-        lv, sv = (plain_v, perm_v) if forward else (perm_v, plain_v)
+    def word(lv: int, sv: int) -> int:
         lo, hi = lay(lv, load_plain_layout), lay(sv, store_plain_layout)
         assert lo < 65536 and hi < 65536
         return lo | (hi << 16)
 
+    if reorder_threads:
+        # which positions sit on the low lane bits decides the shared-memory bank conflicts: a quarter warp (complex128,
+        # 16-byte accesses; half warp for complex64) is conflict-free iff its lanes' offsets differ in the bank bits, i.e.
+        # iff the bank-bit projections of the low lane bits' address vectors are linearly independent — on both sides
+        nb = 3 if c128 else 4
+        bsh, bmask = (4, 7) if c128 else (3, 15)
+
+        def banks(p: int) -> tuple[int, int]:
+            w = word(lmap.cols[p], smap.cols[p])
+            return ((w & 0xFFFF) >> bsh) & bmask, ((w >> 16) >> bsh) & bmask
+
+        chosen: list[int] = []
+        lo_set: list[int] = []
+        hi_set: list[int] = []
+        for want_both in (True, False):
+            for p_ in thr:
+                if len(chosen) >= nb:
+                    break
+                if p_ in chosen:
+                    continue
+                bl, bh = banks(p_)
+                up_l = _rank_gf2(lo_set + [bl]) > _rank_gf2(lo_set)
+                up_h = _rank_gf2(hi_set + [bh]) > _rank_gf2(hi_set)
+                if (up_l and up_h) or (not want_both and (up_l or up_h)):
+                    chosen.append(p_)
+                    lo_set.append(bl)
+                    hi_set.append(bh)
+        thr = chosen + [p_ for p_ in thr if p_ not in chosen]
+
     T = np.zeros(LT_STRIDE, dtype=np.uint32)
+    cw = word(lmap.const, smap.const)
     for half in range(2):
         for v in range(16):
-            plain = permd = 0
+            lv = sv = 0
             for k in range(4):
                 tb = k + 4 * half
                 if tb < len(thr) and (v >> k) & 1:
-                    plain |= 1 << thr[tb]
-                    permd ^= pcol[thr[tb]] if perm else (1 << thr[tb])
-            if half == 0 and perm:
-                permd ^= int(rd["pconst"])
-            T[16 * half + v] = word(plain, permd)
+                    lv ^= lmap.cols[thr[tb]]
+                    sv ^= smap.cols[thr[tb]]
+            T[16 * half + v] = word(lv, sv) ^ (cw if half == 0 else 0)
     for a, pos in enumerate(regs):
-        T[32 + a] = word(1 << pos, pcol[pos] if perm else (1 << pos))
-    T[37] = 1 if (perm or load_plain_layout != store_plain_layout) else 0
+        T[32 + a] = word(lmap.cols[pos], smap.cols[pos])
     ms = [int(x) for x in rd["mslot"]] + [int(rd["mslot4"])]
     for a in range(5):
         T[38 + a] = ms[a] if (a < r and ms[a] >= 0) else LT_EMPTY
-    npx = int(rd["n_pext"])
-    w = npx
-    for k in range(npx):
-        bit, vec = int(rd["pext"][k]["bit"]), int(rd["pext"][k]["vec"])
+    ext_bits = sorted(set(lmap.ext) | set(smap.ext))
+    if len(ext_bits) > 4:
+        raise _TooManyExternalBits()
+    w = len(ext_bits)
+    for k, bit in enumerate(ext_bits):
         w |= bit << (8 + 6 * k)
-        T[44 + k] = word(0, vec)  # only the permuted half is non-zero
+        T[44 + k] = word(lmap.ext.get(bit, 0), smap.ext.get(bit, 0))
     T[43] = w
+    words = [int(x) for x in T[:37]] + [int(x) for x in T[44:48]]
+    T[37] = 1 if any((x & 0xFFFF) != (x >> 16) for x in words) else 0  # some thread stores where another one loads: barrier
     return T
+
+
+class _TooManyExternalBits(Exception):
+    pass
+
+
+def _lean_sweep_tables(rds, m: int, r: int, c128: bool, plain_io: bool, tma_swizzle: bool, virtual: bool) -> tuple[list, list]:
+    """Tables of all rounds of one lean sweep, forward and backward direction.
+
+    `virtual=False`: every round physically applies its permutation (the X / CNOT / SWAP gates folded after its 2x2 gates) when
+    it stores: load at x, barrier, store at pi_k(x).  `virtual=True`: the permutations are only TRACKED — round k loads the
+    amplitude of position x from S_k(x) and stores it back in place (no barrier between the loads and the stores), with
+    S_0 = identity and S_{k+1} = S_k ∘ pi_k^{-1}; only the last round of the sweep stores to the real positions pi_k(x).
+    Backward (rounds in reverse order, un-permute before un-applying): loads from B_k(pi_k(x)), B_last = identity,
+    B_{k-1} = B_k ∘ pi_k, in place, and the final round (k = 0) stores to x."""
+    nr = len(rds)
+    pis = [_Affine.of_round(rd, m) for rd in rds]
+    ident = _Affine.identity(m)
+    fwd, bwd = [], []
+    if not virtual:
+        for k, rd in enumerate(rds):
+            fwd.append(_lean_table(rd, m, r, c128, ident, pis[k], plain_io and k == 0, plain_io and k == nr - 1, tma_swizzle))
+            bwd.append(_lean_table(rd, m, r, c128, pis[k], ident, plain_io and k == nr - 1, plain_io and k == 0, tma_swizzle))
+        return fwd, bwd
+    S = ident
+    for k, rd in enumerate(rds):
+        last = k == nr - 1
+        fwd.append(_lean_table(rd, m, r, c128, S, pis[k] if last else S, plain_io and k == 0, plain_io and last, tma_swizzle, True))
+        S = S.after(pis[k].inverse())
+    Bm = ident
+    for k in range(nr - 1, -1, -1):
+        G = Bm.after(pis[k])
+        bwd.append(_lean_table(rds[k], m, r, c128, G, ident if k == 0 else G, plain_io and k == nr - 1, plain_io and k == 0, tma_swizzle, True))
+        Bm = G
+    bwd.reverse()
+    return fwd, bwd
 
 
 def finish_lean(plan: "SweepPlan", n_total: int) -> None:
@@ -824,6 +963,7 @@ def finish_lean(plan: "SweepPlan", n_total: int) -> None:
     allow = cfg.lean and os.environ.get("B200SV_LEAN", "1") != "0" and n_total == n
     allow_tma = os.environ.get("B200SV_TMA", "1") != "0"
     tma_swizzle = os.environ.get("B200SV_TMA_SWIZZLE", TMA_SWIZZLE_DEFAULT) != "0"
+    virtual = os.environ.get("B200SV_VPERM", VPERM_DEFAULT) != "0"
     for si in range(ns):
         sw = plan.sweeps[si]
         m, r = int(sw["m"]), int(sw["r"])
@@ -843,11 +983,14 @@ def finish_lean(plan: "SweepPlan", n_total: int) -> None:
             continue
         fr, nr = int(sw["first_round"]), int(sw["n_rounds"])
         plain_io = mode == IO_LEAN_TMA  # TMA writes / reads the tile un-swizzled
+        rds = [plan.rounds[fr + k] for k in range(nr)]
+        try:
+            fwd, bwd = _lean_sweep_tables(rds, m, r, cfg.c128, plain_io, plain_io and tma_swizzle, virtual)
+        except _TooManyExternalBits:  # more than 4 external control bits accumulate over the sweep: permute physically
+            fwd, bwd = _lean_sweep_tables(rds, m, r, cfg.c128, plain_io, plain_io and tma_swizzle, False)
         for k in range(nr):
-            rd = plan.rounds[fr + k]
-            sz = plain_io and tma_swizzle
-            plan.lean_tab_fwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, True, plain_io and k == 0, plain_io and k == nr - 1, sz)
-            plan.lean_tab_bwd[fr + k] = _lean_round_table(rd, m, r, cfg.c128, False, plain_io and k == nr - 1, plain_io and k == 0, sz)
+            plan.lean_tab_fwd[fr + k] = fwd[k]
+            plan.lean_tab_bwd[fr + k] = bwd[k]
 
 
 # ---- Pauli sums -----------------------------------------------------------------------------------

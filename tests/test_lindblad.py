@@ -179,6 +179,35 @@ def test_lindblad_ops_round_trip_through_json() -> None:
     assert again.is_noisy
 
 
+@pytest.mark.parametrize("case", ["constant", "time-dependent"])
+def test_host_side_of_the_product_propagator(monkeypatch, case: str) -> None:
+    """`hamevo.evolve_lindblad` (support-local superoperator, term order of the COMPILED Pauli sum, batch handling) with the
+    one device call it makes, `engine.apply_dense`, replaced by the oracle's dense operator application."""
+    from qadence_b200 import engine as E
+    from qadence_b200.program import OpKind as K
+
+    def apply_dense(psi, matrix, bits):
+        n = int(psi.shape[1]).bit_length() - 1
+        m = torch.as_tensor(matrix).to(torch.complex128)
+        out = oracle.apply_operator(oracle.to_pyq_shape(psi, n), m[:, :, None], [n - 1 - b for b in bits])
+        return oracle.from_pyq_shape(out).contiguous()
+
+    monkeypatch.setattr(E, "apply_dense", apply_dense)
+    prog, values = (lindblad_case(1) if case == "constant" else td_case())[:2]
+    n = prog.n_qubits
+    vprog, needs = density.vectorise(prog)
+    vals = density.extend_values(values, needs)
+    B = max(int(torch.as_tensor(v).numel()) for v in values.values())
+    state = density.vectorise_state(oracle.zero_state(n, B), n)
+    for op in vprog.ops:
+        if op.kind == K.HAMEVO and op.jumps:
+            state = hamevo.evolve_lindblad(op, E.CompiledPauliSum.build(op.generator), state, vals, 2 * n)
+        else:
+            state = oracle.run(Program(2 * n, [op]), vals, state)
+    want = run_vectorised(prog, values).reshape(B, -1)
+    assert (state - want).abs().max() < 1e-12
+
+
 # ------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(3))

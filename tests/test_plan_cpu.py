@@ -78,7 +78,8 @@ def test_hea_fuses_into_few_sweeps() -> None:
     assert len(prog.ops) == 632
     assert plan.n_sweeps <= 9, plan.n_sweeps  # vs 632 state round trips gate by gate (2^10-amplitude tiles; 8 with 2^11)
     assert build_plan(prog.ops, n, slot_of, TileConfig(m=11, r=4, low=2, fold=3)).n_sweeps <= 8
-    assert build_plan(prog.ops, n, slot_of, TileConfig.default(True, True)).n_sweeps <= 8  # adjoint geometry (first fit: 13)
+    assert build_plan(prog.ops, n, slot_of, TileConfig.default(True, True)).n_sweeps <= 9  # adjoint geometry (m = 10, r = 4; first fit: 13)
+    assert build_plan(prog.ops, n, slot_of, TileConfig(m=10, r=3, low=2, fold=3, adjoint=True)).n_sweeps <= 8
     assert build_plan(prog.ops, n, slot_of, TileConfig(m=11, r=4, low=2, fold=3), packer="greedy").n_sweeps == 11
     assert int(plan.rounds["n_exec"].sum()) == 0  # no interpreter entries: merged 2x2 + folded CNOT permutations only
     for sw in plan.sweeps:

@@ -45,15 +45,23 @@ def main() -> None:
     ws_f = fwd.workspace(dtype, a.batch, False).data_ptr()
     ws_a = adj.workspace(dtype, a.batch, True).data_ptr()
     st = _stream_ptr(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     for _ in range(a.steps):
         cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], a.n, a.batch, st), "init")
+        ev[0].record()
         cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
+        ev[1].record()
         e = engine.pauli_expectation(cob.pauli, coef, psi)
         engine.pauli_apply(cob.pauli, coef, psi, out=lam)
         grads.zero_()
+        ev[2].record()
         cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0,
                                            adj.n_sweeps, 0, ws_a, st), "adj")
+        ev[3].record()
     torch.cuda.synchronize(dev)
+    # CUDA-event times of the LAST step (the first one warms up): forward plan, Pauli kernels, adjoint plan
+    print(f"TIMES forward_ms={ev[0].elapsed_time(ev[1]):.3f} ({fwd.n_sweeps} sweeps) pauli_ms={ev[1].elapsed_time(ev[2]):.3f} "
+          f"adjoint_ms={ev[2].elapsed_time(ev[3]):.3f} ({adj.n_sweeps} sweeps) total_ms={ev[0].elapsed_time(ev[3]):.3f}")
     print("E[0:3] =", e[:3].tolist(), " |grad| =", float(grads.abs().sum()), " psi[0,0] =", complex(psi[0, 0]))
 
 

@@ -326,8 +326,12 @@ def main() -> None:
             qnames = sorted({p.name for p in parameters(block) if not p.is_number}, key=lambda s: int(s.split("_")[-1]))
             assert len(qnames) == n_slots
 
+            x_host = {nm: host_params[i].clone().requires_grad_(True) for i, nm in enumerate(qnames)}  # HOST tensors (leaves)
+
             def e2e_step():
-                x = {nm: host_params[i].clone().requires_grad_(True) for i, nm in enumerate(qnames)}  # HOST tensors
+                x = x_host
+                for t_ in x.values():
+                    t_.grad = None
                 out = bk.expectation(conv.circuit, conv.observable, conv.embedding_fn(conv.params, x))  # H2D inside
                 out.sum().backward()  # adjoint sweeps; the gradients land on the host tensors (D2H inside)
                 return out, x

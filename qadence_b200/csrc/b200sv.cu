@@ -689,7 +689,7 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
 }
 
 // out = alpha * (sum_t c_t P_t psi) + beta * acc
-template <typename c2, bool PEER = false>
+template <typename c2, bool PEER = false, bool DIAG = false>
 __global__ void __launch_bounds__(EXP_THREADS)
 pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, long long batch,
                    const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
@@ -719,16 +719,17 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
     const long long gbase = base + (long long)g * (EXP_THREADS * PK_K);
     if (gbase >= N) break;
     c2 av[PK_K], zv[PK_K];  // loads first (memory-level parallelism), see pauli_expect_kernel
-    double2 dv[PK_K];
-    const double2* dg = diag ? reinterpret_cast<const double2*>(diag) + ((diag_ld == 1 ? 0 : b) << n) : nullptr;
+    double2 dv[DIAG ? PK_K : 1];  // (a template parameter: the 16 extra registers cost the plain kernel a third of its speed)
+    const double2* dg = DIAG ? reinterpret_cast<const double2*>(diag) + ((diag_ld == 1 ? 0 : b) << n) : nullptr;
 #pragma unroll
     for (int k = 0; k < PK_K; ++k) {
       const long long i = gbase + (long long)k * EXP_THREADS;
-      av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0; dv[k].x = 0.0; dv[k].y = 0.0;
+      av[k].x = 0; av[k].y = 0; zv[k].x = 0; zv[k].y = 0;
+      if constexpr (DIAG) { dv[k].x = 0.0; dv[k].y = 0.0; }
       if (i < N) {
         av[k] = __ldcs(p + i);
         if (acc != nullptr) zv[k] = acc[(b << n) + i];
-        if (dg != nullptr) dv[k] = dg[i];
+        if constexpr (DIAG) dv[k] = dg[i];
       }
     }
     const double wgr = wtr + dt.gr[g], wgi = wti + dt.gi[g];
@@ -737,7 +738,8 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
       const long long i = gbase + (long long)k * EXP_THREADS;
       if (i >= N) break;
       const c2 a = av[k];
-      double wr = wgr + dt.kr[k] + dv[k].x, wi = wgi + dt.ki[k] + dv[k].y, sr = 0.0, si = 0.0;
+      double wr = wgr + dt.kr[k], wi = wgi + dt.ki[k], sr = 0.0, si = 0.0;
+      if constexpr (DIAG) { wr += dv[k].x; wi += dv[k].y; }
       if (T > 0) {
         const unsigned long long gi = (unsigned long long)i | index_hi;
         for (int t = 0; t < T; ++t) {
@@ -1303,9 +1305,9 @@ int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dty
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (br == 0.0 && bi == 0.0) acc = nullptr;
   if (dtype == B200SV_C128)
-    pauli_apply_kernel<double2><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+    pauli_apply_kernel<double2, false, true><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
   else if (dtype == B200SV_C64)
-    pauli_apply_kernel<float2><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+    pauli_apply_kernel<float2, false, true><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;

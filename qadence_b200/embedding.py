@@ -370,6 +370,59 @@ def _resolve_device(device: torch.device | str | None) -> torch.device:
     return torch.device(device)
 
 
+_STAGING: dict = {}
+
+
+def _staging(rows: int, batch: int) -> tuple[Tensor, "torch.cuda.Event"]:
+    """Pinned host buffer [rows, batch] (float64) reused from call to call, with the event of the last copy out of it."""
+    key = (rows, batch)
+    if key not in _STAGING:
+        if len(_STAGING) > 16:
+            _STAGING.clear()
+        _STAGING[key] = (torch.empty(rows, batch, dtype=torch.float64).pin_memory(), torch.cuda.Event())
+    buf, ev = _STAGING[key]
+    ev.synchronize()  # the previous call's host-to-device copy has read the buffer
+    return buf, ev
+
+
+class _PackRows(torch.autograd.Function):
+    """feat[F, batch] (float64, on the simulation device) from the F separate feature tensors of an `inputs` dict, as ONE
+    autograd node: the rows are stacked on their own device, copied once (host inputs: through a pinned staging buffer), and
+    the backward pass brings all F gradients back with one copy.  `torch.stack(...).to(device)` does the same arithmetic but
+    leaves 2 F autograd nodes behind — 6 ms of host time per backward pass for cfg2's 480 inputs, as much as five sweeps."""
+
+    @staticmethod
+    def forward(ctx, dev, batch, *rows):  # type: ignore[override]
+        ctx.meta = [(r.numel(), r.device, r.dtype) for r in rows]
+        src = rows[0].device
+        ctx.same_device = all(r.device == src for r in rows)
+        det = [r.detach() for r in rows]
+        if ctx.same_device and all(r.dtype == torch.float64 for r in det):
+            if src.type == "cpu" and dev.type == "cuda":
+                buf, ev = _staging(len(det), batch)
+                torch.stack([r.expand(batch) for r in det], out=buf)
+                out = buf.to(dev, non_blocking=True)
+                ev.record(torch.cuda.current_stream(dev))
+                return out
+            return torch.stack([r.expand(batch) for r in det]).to(dev)
+        return torch.stack([r.to(device=src, dtype=torch.float64).expand(batch) for r in det]).to(dev)
+
+    @staticmethod
+    def backward(ctx, g):  # type: ignore[override]
+        meta = ctx.meta
+        gh = g.to(meta[0][1]) if ctx.same_device else g  # ONE device-to-host copy for all rows
+        outs: list = [None, None]
+        for i, (numel, device, dtype) in enumerate(meta):
+            if not ctx.needs_input_grad[2 + i]:
+                outs.append(None)
+                continue
+            r = gh[i]
+            if numel == 1 and r.numel() != 1:
+                r = r.sum().reshape(1)
+            outs.append(r.to(device=device, dtype=dtype))
+        return tuple(outs)
+
+
 def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, stock_fn: Callable[[dict, dict], dict],
                       passthrough: bool, matrix_rows: Sequence[tuple[str, str]] = ()) -> Callable[[dict, dict], dict]:
     """embedding_fn(params, inputs) with the signature of qadence/blocks/embedding.py:118; `stock_fn` (the reference's
@@ -405,7 +458,7 @@ def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, sto
         input_device = src[0].device if src else torch.device("cpu")
         var = torch.cat(var_rows).to(device=dev, dtype=torch.float64) if var_rows else torch.zeros(1, dtype=torch.float64, device=dev)
         if feat_rows:
-            feat = torch.stack([r.expand(batch) for r in feat_rows]).to(device=dev, dtype=torch.float64)
+            feat = _PackRows.apply(dev, batch, *feat_rows)
         else:
             feat = torch.zeros(1, batch, dtype=torch.float64, device=dev)
         table = evaluate(prog, var, feat, batch)

@@ -442,6 +442,33 @@ def main() -> None:
 
         multi = multi_gpu_sections.run(rank, world, dev, steps=max(2, min(args.steps, 3)))
 
+    # complex64, informative: the same step with FP32 arithmetic (half the bytes, a quarter of the FP pipe time; the state lives in
+    # the first half of the complex128 buffers)
+    c64 = None
+    if world == 1:
+        d32 = torch.complex64
+        f32, a32 = cp.device_plan(seg, d32, False, dev), cp.device_plan(seg, d32, True, dev)
+        psi32 = psi.view(d32).reshape(-1)[: BATCH << N_QUBITS].view(BATCH, 1 << N_QUBITS)
+        lam32 = lam.view(d32).reshape(-1)[: BATCH << N_QUBITS].view(BATCH, 1 << N_QUBITS)
+        w32f, w32a = f32.workspace(d32, BATCH, False).data_ptr(), a32.workspace(d32, BATCH, True).data_ptr()
+
+        def c64_step():
+            cabi.check(lib.b200sv_init_zero_state(psi32.data_ptr(), _DT[d32], N_QUBITS, BATCH, st), "init")
+            cabi.check(lib.b200sv_apply_plan(psi32.data_ptr(), _DT[d32], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(f32.struct), 0, f32.n_sweeps, 0, w32f, st), "fwd")
+            e32 = engine.pauli_expectation(cob.pauli, coef, psi32)
+            engine.pauli_apply(cob.pauli, coef, psi32, out=lam32)
+            grads.zero_()
+            cabi.check(lib.b200sv_adjoint_plan(psi32.data_ptr(), lam32.data_ptr(), _DT[d32], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(a32.struct), 0, a32.n_sweeps, 0, w32a, st), "adj")
+            return e32
+
+        e32 = c64_step()
+        err32 = float((e32.reshape(-1).double() - e_dev.reshape(-1)).abs().max())
+        g32_err = None
+        ms32 = timed(c64_step, 3) / 3
+        c64 = {"ms_per_step": ms32, "evals_per_s": BATCH / (ms32 * 1e-3), "speedup_vs_complex128": ms_per_step / ms32,
+               "fwd_sweeps": f32.n_sweeps, "adj_sweeps": a32.n_sweeps, "tiles": {"forward": [f32.plan.cfg.m, f32.plan.cfg.r], "adjoint": [a32.plan.cfg.m, a32.plan.cfg.r]},
+               "max_abs_diff_expectation_vs_complex128": err32}
+
     if rank == 0:
         cpu = None
         if do_cpu:
@@ -493,13 +520,16 @@ def main() -> None:
                                        "merged_2x2_fwd": n_chain_f, "merged_2x2_adj": n_chain_a, "achieved": fp64_tflops, "peak": FP64_PEAK_TFLOPS,
                                        "unit": "TFLOP/s", "frac": fp64_tflops / FP64_PEAK_TFLOPS,
                                        "floor_ms_per_step": 2 * fp64_instr / (FP64_PEAK_TFLOPS * 1e12) * 1e3},
+                         "complex64": c64,
                          "step": {"what": "algorithmic HBM bytes of the whole step (2S per forward sweep, 4S per adjoint sweep, S init, S <O>, 2S lambda = O psi)",
                                   "hbm_bytes_per_step": hbm_bytes_step, "hbm_floor_ms_per_step": hbm_bytes_step / (peak * 1e9) * 1e3,
                                   "frac": hbm_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak,
                                   "rounds_fwd": int(fwd.plan.sweeps["n_rounds"].sum()), "rounds_adj": int(adj.plan.sweeps["n_rounds"].sum())},
-                         "note": ("what the counters say (profiles/r02_*.md): the heavy sweeps sit at neither roof. With ~20 merged 2x2 per tile the FP64 floor of a "
-                                  "sweep is ~2x its HBM floor, and the kernel reaches about half of the FP64 pipe: 4 warps per scheduler (register-limited) leave "
-                                  "dependency and shared-memory latencies exposed (issue slots ~60 % busy; an FP64 instruction takes two of them)")},
+                         "note": ("what the counters say (profiles/r02_lean_kernel.md §8, ncu of this build): the heavy sweeps sit at neither roof. DRAM traffic "
+                                  "equals the algorithmic bytes and a light sweep streams at 97 % of the HBM peak, but with ~20 merged 2x2 per tile the FP64 floor of a "
+                                  "sweep is ~2x its HBM floor, and the kernels reach 56 % (adjoint, 255 registers, 2 warps per scheduler) / 62 % (forward) of the FP64 "
+                                  "pipe: an FP64 instruction occupies the pipe for two cycles, 71 % of the adjoint sweep's instructions are FP64, and the remaining "
+                                  "latencies of a round (shared-memory tile exchange, moment reduction, barrier) are not covered by two warps")},
             "cpu_baseline": cpu,
             "clocks": clocks,
             **multi,

@@ -388,38 +388,42 @@ def _staging(rows: int, batch: int) -> tuple[Tensor, "torch.cuda.Event"]:
 class _PackRows(torch.autograd.Function):
     """feat[F, batch] (float64, on the simulation device) from the F separate feature tensors of an `inputs` dict, as ONE
     autograd node: the rows are stacked on their own device, copied once (host inputs: through a pinned staging buffer), and
-    the backward pass brings all F gradients back with one copy.  `torch.stack(...).to(device)` does the same arithmetic but
-    leaves 2 F autograd nodes behind — 6 ms of host time per backward pass for cfg2's 480 inputs, as much as five sweeps."""
+    the backward pass brings all F gradients back with one copy.  `torch.stack([v.reshape(-1) ...]).to(device)` does the same
+    arithmetic but leaves 3 F autograd nodes behind — 6 ms of host time per backward pass for cfg2's 480 inputs, as much as five
+    sweeps.  The rows are taken as the user passed them (any shape with `numel` in (1, batch))."""
 
     @staticmethod
     def forward(ctx, dev, batch, *rows):  # type: ignore[override]
-        ctx.meta = [(r.numel(), r.device, r.dtype) for r in rows]
+        ctx.meta = [(r.shape, r.device, r.dtype) for r in rows]
         src = rows[0].device
         ctx.same_device = all(r.device == src for r in rows)
-        det = [r.detach() for r in rows]
-        if ctx.same_device and all(r.dtype == torch.float64 for r in det):
+        plain = ctx.same_device and all(r.dtype == torch.float64 and r.dim() == 1 and r.shape[0] == batch for r in rows)
+        if plain:  # the common case: F vectors of length batch
             if src.type == "cpu" and dev.type == "cuda":
-                buf, ev = _staging(len(det), batch)
-                torch.stack([r.expand(batch) for r in det], out=buf)
+                buf, ev = _staging(len(rows), batch)
+                torch.stack(rows, out=buf)
                 out = buf.to(dev, non_blocking=True)
                 ev.record(torch.cuda.current_stream(dev))
                 return out
-            return torch.stack([r.expand(batch) for r in det]).to(dev)
-        return torch.stack([r.to(device=src, dtype=torch.float64).expand(batch) for r in det]).to(dev)
+            return torch.stack(rows).to(dev)
+        return torch.stack([r.reshape(-1).to(device=src, dtype=torch.float64).expand(batch) for r in rows]).to(dev)
 
     @staticmethod
     def backward(ctx, g):  # type: ignore[override]
         meta = ctx.meta
         gh = g.to(meta[0][1]) if ctx.same_device else g  # ONE device-to-host copy for all rows
+        parts = gh.unbind(0)
         outs: list = [None, None]
-        for i, (numel, device, dtype) in enumerate(meta):
+        for i, (shape, device, dtype) in enumerate(meta):
             if not ctx.needs_input_grad[2 + i]:
                 outs.append(None)
                 continue
-            r = gh[i]
-            if numel == 1 and r.numel() != 1:
-                r = r.sum().reshape(1)
-            outs.append(r.to(device=device, dtype=dtype))
+            r = parts[i]
+            if len(shape) != 1 or shape[0] != r.shape[0]:
+                r = (r.sum() if shape.numel() == 1 and r.numel() != 1 else r).reshape(shape)
+            if r.device != device or r.dtype != dtype:
+                r = r.to(device=device, dtype=dtype)
+            outs.append(r)
         return tuple(outs)
 
 
@@ -447,8 +451,8 @@ def make_embedding_fn(prog: EmbedProgram, device: torch.device | str | None, sto
             v = torch.as_tensor(inputs[nm])
             if v.is_complex() or v.dim() > 1 and v.numel() != v.shape[0]:
                 return stock_fn(params, inputs)
-            feat_rows.append(v.reshape(-1))
-            batch = max(batch, feat_rows[-1].numel())
+            feat_rows.append(v)
+            batch = max(batch, v.numel())
         for nm, v in inputs.items():  # inputs that feed no expression may still set the batch size (qadence/backends/utils.py:169-184)
             if isinstance(v, Tensor) and v.dim() == 1:
                 batch = max(batch, v.shape[0])

@@ -219,3 +219,131 @@ def test_production_tables_are_hazard_free(shape: str) -> None:
             assert all(int(s["io_mode"]) != P.IO_GENERIC for s in plan.sweeps)
             total += check_tables_hazard_free(plan, forward=not adjoint)
     assert total > 100
+
+
+# ------------------------------------------------------------------------------------------ tracked permutations
+def test_affine_maps_compose_and_invert() -> None:
+    rng = np.random.default_rng(11)
+    m = 7
+    for _ in range(20):
+        # a random invertible GF(2) matrix as a product of transvections (CNOTs) and swaps, plus constants / external vectors
+        a = P._Affine.identity(m)
+        for _ in range(12):
+            i, j = (int(x) for x in rng.choice(m, size=2, replace=False))
+            step = P._Affine([(1 << k) | ((1 << j) if k == i else 0) for k in range(m)], int(rng.integers(1 << m)), {int(rng.integers(20, 24)): int(rng.integers(1 << m))})
+            a = step.after(a)
+        inv = a.inverse()
+        for ext_mask in (0, 1, 5):
+            def apply(f, x):
+                v = f.lin(x) ^ f.const
+                for k, (e, vec) in enumerate(sorted(f.ext.items())):
+                    if (ext_mask >> (e - 20)) & 1:
+                        v ^= vec
+                return v
+            for x in rng.integers(0, 1 << m, size=16):
+                assert apply(inv, apply(a, int(x))) == int(x)
+                both = inv.after(a)
+                assert apply(both, int(x)) == int(x)
+
+
+@pytest.mark.parametrize("adjoint", [False, True])
+def test_tracked_permutations_equal_physical_ones_and_drop_the_barriers(any_geometry, monkeypatch, adjoint: bool) -> None:
+    """`B200SV_VPERM=1` (default) and `=0` execute the same program on the emulator; with tracking, only the first and the last
+    round of a TMA-staged sweep keep the barrier between their loads and stores."""
+    n, B = 9, 2
+    prog = hea_program(n, 3)
+    rng = np.random.default_rng(2)
+    values = {nm: torch.tensor(rng.uniform(0.1, 3.0, size=B)) for nm in prog.param_names}
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    params = np.stack([values[nm].numpy() for nm in prog.param_names])
+    cfg = TileConfig(m=6, r=3, low=2, fold=3, adjoint=adjoint)
+    plans = {}
+    for v in ("1", "0"):
+        monkeypatch.setenv("B200SV_VPERM", v)
+        plans[v] = build_plan(prog.ops, n, slot_of, cfg)
+    tabs = {v: (p.lean_tab_bwd if adjoint else p.lean_tab_fwd) for v, p in plans.items()}
+    assert not np.array_equal(tabs["1"], tabs["0"])
+    sync = {v: 0 for v in tabs}
+    inner = {v: 0 for v in tabs}
+    for v, plan in plans.items():
+        for sw in plan.sweeps:
+            if int(sw["io_mode"]) == P.IO_GENERIC:
+                continue
+            fr, nr = int(sw["first_round"]), int(sw["n_rounds"])
+            for k in range(nr):
+                s_ = int(tabs[v][fr + k][37]) & 1
+                sync[v] += s_
+                if 0 < k < nr - 1:
+                    inner[v] += s_
+        assert check_tables_hazard_free(plan, not adjoint) > 0
+    assert inner["1"] == 0 and inner["0"] > 0 and sync["1"] < sync["0"]
+    z0 = oracle.zero_state(n, B).numpy()
+    want = oracle.run(prog, values).numpy()
+    if not adjoint:
+        for v, plan in plans.items():
+            psi, _, _ = emulate_lean(plan, z0, params)
+            np.testing.assert_allclose(psi, want, atol=1e-11, err_msg=f"VPERM={v}")
+    else:
+        obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.3, (), ((0, "X"), (4, "Y")))])
+        _, want_g = oracle.adjoint_expectation_and_grads(prog, obs, values)
+        lam = oracle.from_pyq_shape(oracle.paulisum_apply(obs, oracle.to_pyq_shape(torch.tensor(want), n), values)).numpy()
+        for v, plan in plans.items():
+            back_psi, _, grads = emulate_lean(plan, want, params, lam=lam)
+            np.testing.assert_allclose(back_psi, z0, atol=1e-11, err_msg=f"VPERM={v}")
+            for nm, i in slot_of.items():
+                np.testing.assert_allclose(grads[i], want_g[nm].numpy(), atol=1e-10, err_msg=f"VPERM={v} {nm}")
+
+
+def test_low_lanes_stay_bank_conflict_free_under_tracked_permutations(any_geometry) -> None:
+    """Quarter warps (complex128: 8 lanes × 16 bytes) must hit 8 different 16-byte columns on the load AND the store side of
+    every round of cfg2's production tables, although the tracked permutations make the address vectors of the thread bits
+    arbitrary: `_lean_table` re-chooses which positions sit on the low lane bits."""
+    n = 20
+    prog = hea_program(n, 8)
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    for adjoint in (False, True):
+        plan = build_plan(prog.ops, n, slot_of, TileConfig(m=10, r=4, low=2, fold=3, adjoint=adjoint))
+        tab = plan.lean_tab_bwd if adjoint else plan.lean_tab_fwd
+        bad = total = 0
+        for sw in plan.sweeps:
+            if int(sw["io_mode"]) == P.IO_GENERIC:
+                continue
+            for k in range(int(sw["n_rounds"])):
+                T = tab[int(sw["first_round"]) + k]
+                lanes = np.arange(8)
+                w = T[lanes & 15]
+                for half, shift in ((0, 0), (1, 16)):
+                    cols = ((w >> shift) & 0xFFFF) >> 4 & 7
+                    total += 1
+                    bad += len(set(int(c) for c in cols)) != 8
+        assert bad <= total // 8, (adjoint, bad, total)  # 8 of 96 today: rounds that face the un-swizzled TMA layout with low register bits
+
+
+def test_register_bit_fallbacks_for_sweeps_the_lean_kernel_cannot_take() -> None:
+    """A plan that needs the generic kernel (controlled rotations, or a register smaller than the tile) never carries r = 5
+    (the generic kernel holds 4 register bits), and complex128 adjoint plans fall back to the r = 3 geometry it was tuned for."""
+    from qadence_b200 import cabi
+
+    try:
+        cabi.load()
+    except cabi.B200svError:
+        pytest.skip("libb200sv.so not built")
+    n = 14
+    b = ProgramBuilder(n)
+    for q in range(n):
+        b.RX(q, f"a{q}")
+    for q in range(n - 1):
+        b.CRZ(q, q + 1, f"c{q}")
+    prog = b.build()
+    slot_of = {nm: i for i, nm in enumerate(prog.param_names)}
+    p64 = build_plan(prog.ops, n, slot_of, TileConfig.default(False, False))
+    assert TileConfig.default(False, False).r == 5 and all(int(s["r"]) <= 4 for s in p64.sweeps)
+    pad = build_plan(prog.ops, n, slot_of, TileConfig.default(True, True))
+    assert TileConfig.default(True, True).r == 4 and all(int(s["r"]) == 3 for s in pad.sweeps)
+    small = hea_program(5, 1)
+    ps = build_plan(small.ops, 5, {nm: i for i, nm in enumerate(small.param_names)}, TileConfig.default(False, False))
+    assert all(int(s["r"]) <= 4 and int(s["m"]) - int(s["r"]) >= 0 for s in ps.sweeps)
+    # a pure HEA keeps the lean geometry
+    hp = hea_program(n, 2)
+    ph = build_plan(hp.ops, n, {nm: i for i, nm in enumerate(hp.param_names)}, TileConfig.default(True, True))
+    assert all(int(s["r"]) == 4 for s in ph.sweeps)

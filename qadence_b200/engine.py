@@ -213,6 +213,8 @@ class CompiledProgram:
         self.slot_of = {nm: i for i, nm in enumerate(self.names)}
         self.segments: list[Segment] = []
         self._shift_rules: list[int | None] | None = None
+        self._absorb: tuple | None = None  # absorb_trailing_permutation: (CompiledProgram without the closing X / CNOT / SWAP gates, those gates)
+        self._absorb_obs: dict = {}
         run: list[Op] = []
         for op in program.ops:
             if op.kind < OpKind.MATK:
@@ -767,6 +769,43 @@ class _AdjointGradient(torch.autograd.Function):
         return None, None, None, None, None, None, d_theta, d_gout
 
 
+def absorb_trailing_permutation(cp: CompiledProgram, cobs: Sequence["CompiledObservable"]) -> tuple[CompiledProgram, list["CompiledObservable"]]:
+    """(cp', observables') with the same expectation values and gradients: the X / CNOT / SWAP gates that close the circuit are
+    conjugated into the Pauli-sum observables (`clifford.py`) when that saves a state round trip — i.e. when the plan of the
+    circuit without them has fewer sweeps (the closing CNOT ladder of an HEA on a register larger than a tile).  Cached on `cp`.
+    `B200SV_ABSORB_PERM=0` disables it."""
+    from . import clifford
+
+    cobs = list(cobs)
+    if os.environ.get("B200SV_ABSORB_PERM", "1") == "0" or not cobs or any(c.pauli is None for c in cobs):
+        return cp, cobs
+    if cp._absorb is None:
+        cp._absorb = (None, [])
+        seg = cp.segments[-1] if cp.segments else None
+        if seg is not None and seg.gates is not None:
+            body, gates = clifford.split_trailing_permutation(cp.program)
+            if gates and len(gates) < len(seg.gates):
+                tc = TileConfig.default(True, False)
+                full_sweeps = build_plan(seg.gates, cp.n_qubits, cp.slot_of, tc).n_sweeps
+                body_cp = CompiledProgram(body)
+                bseg = body_cp.segments[-1]
+                if body_cp.names == cp.names and bseg.gates is not None and build_plan(bseg.gates, cp.n_qubits, body_cp.slot_of, tc).n_sweeps < full_sweeps:
+                    cp._absorb = (body_cp, gates)
+    body_cp, gates = cp._absorb
+    if body_cp is None:
+        return cp, cobs
+    out = []
+    for c in cobs:
+        hit = cp._absorb_obs.get(id(c))
+        if hit is None or hit[0] is not c:
+            hit = (c, CompiledObservable(clifford.conjugate_observable(c.obs, gates)))
+            if len(cp._absorb_obs) > 64:
+                cp._absorb_obs.clear()
+            cp._absorb_obs[id(c)] = hit
+        out.append(hit[1])
+    return body_cp, out
+
+
 def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], values: Mapping[str, Tensor] | None = None,
                 state: Tensor | None = None, dtype: torch.dtype = torch.complex128,
                 device: torch.device | str | None = None) -> Tensor:
@@ -777,7 +816,7 @@ def expectation(cp: CompiledProgram, observables: Sequence[CompiledObservable], 
     B = infer_batch(values)
     if state is not None:
         B = max(B, state.shape[0])
-    cobs = list(observables)
+    cp, cobs = absorb_trailing_permutation(cp, observables)
     ptable = pack_params(cp.names, values, B, dev)
     real_dt = torch.float64 if dtype == torch.complex128 else torch.float32
     grad_on = torch.is_grad_enabled()

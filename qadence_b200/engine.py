@@ -771,13 +771,17 @@ class _AdjointGradient(torch.autograd.Function):
 
 def absorb_trailing_permutation(cp: CompiledProgram, cobs: Sequence["CompiledObservable"]) -> tuple[CompiledProgram, list["CompiledObservable"]]:
     """(cp', observables') with the same expectation values and gradients: the X / CNOT / SWAP gates that close the circuit are
-    conjugated into the Pauli-sum observables (`clifford.py`) when that saves a state round trip — i.e. when the plan of the
-    circuit without them has fewer sweeps (the closing CNOT ladder of an HEA on a register larger than a tile).  Cached on `cp`.
-    `B200SV_ABSORB_PERM=0` disables it."""
+    conjugated into the Pauli-sum observables (`clifford.py`) when that (1) saves a state round trip — the plan of the circuit
+    without them has fewer sweeps — and (2) does not make the observable more expensive: no observable may end up with more
+    terms outside the single-Z fast path of the Pauli kernels than it had.  (2) excludes the case that motivated this — the
+    closing CNOT ladder of cfg2's HEA turns Z_tot into 20 prefix-parity strings: measured 1.9 ms saved in the sweeps, 10.6 ms
+    lost in <O> and λ = Oψ, profiles/r02_lean_kernel.md §9 — and keeps closing SWAP / X layers and CNOTs whose targets the
+    observable does not touch.  `B200SV_ABSORB_PERM=0` disables it, `=force` skips (2).  Cached on `cp`."""
     from . import clifford
 
     cobs = list(cobs)
-    if os.environ.get("B200SV_ABSORB_PERM", "1") == "0" or not cobs or any(c.pauli is None for c in cobs):
+    mode = os.environ.get("B200SV_ABSORB_PERM", "1")
+    if mode == "0" or not cobs or any(c.pauli is None for c in cobs):
         return cp, cobs
     if cp._absorb is None:
         cp._absorb = (None, [])
@@ -794,14 +798,20 @@ def absorb_trailing_permutation(cp: CompiledProgram, cobs: Sequence["CompiledObs
     body_cp, gates = cp._absorb
     if body_cp is None:
         return cp, cobs
+    def slow_terms(ps: PauliSum) -> int:
+        return sum(1 for t in ps.terms if not (len(t.paulis) == 1 and t.paulis[0][1] == "Z"))
+
     out = []
     for c in cobs:
         hit = cp._absorb_obs.get(id(c))
         if hit is None or hit[0] is not c:
-            hit = (c, CompiledObservable(clifford.conjugate_observable(c.obs, gates)))
+            conj = clifford.conjugate_observable(c.obs, gates)
+            hit = (c, CompiledObservable(conj) if (mode == "force" or slow_terms(conj) <= slow_terms(c.obs)) else None)
             if len(cp._absorb_obs) > 64:
                 cp._absorb_obs.clear()
             cp._absorb_obs[id(c)] = hit
+        if hit[1] is None:
+            return cp, cobs
         out.append(hit[1])
     return body_cp, out
 

@@ -1,0 +1,169 @@
+"""Trailing X / CNOT / SWAP gates absorbed into Pauli-sum observables (`qadence_b200/clifford.py`,
+`engine.absorb_trailing_permutation`): P† O P must be the same operator, and the trimmed circuit with the conjugated
+observable must give the oracle's expectation values and gradients of the full circuit."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import statevec as oracle
+from qadence_b200 import clifford
+from qadence_b200.program import CONST_MATS, Op, OpKind, PauliSum, PauliTerm, Program, ProgramBuilder, hea_program, total_magnetization
+
+PM = {"X": np.array([[0, 1], [1, 0]], dtype=complex), "Y": np.array([[0, -1j], [1j, 0]], dtype=complex), "Z": np.diag([1.0 + 0j, -1])}
+
+
+def dense_pauli_sum(ps: PauliSum) -> np.ndarray:
+    n = ps.n_qubits
+    out = np.zeros((2**n, 2**n), dtype=complex)
+    for t in ps.terms:
+        m = np.ones((1, 1), dtype=complex)
+        d = dict(t.paulis)
+        for q in range(n):
+            m = np.kron(m, PM[d[q]] if q in d else np.eye(2))
+        out += complex(t.const) * m
+    return out
+
+
+def dense_unitary(ops, n: int) -> np.ndarray:
+    cols = oracle.run(Program(n, list(ops)), {}, torch.eye(2**n, dtype=torch.complex128))
+    return cols.numpy().T
+
+
+def random_permutation_gates(rng, n: int, k: int) -> list[Op]:
+    b = ProgramBuilder(n)
+    for _ in range(k):
+        kind = int(rng.integers(3))
+        q = [int(x) for x in rng.permutation(n)]
+        if kind == 0:
+            b.X(q[0])
+        elif kind == 1:
+            b.CNOT(q[0], q[1])
+        else:
+            b.SWAP(q[0], q[1])
+    return b.build().ops
+
+
+def random_pauli_sum(rng, n: int, terms: int) -> PauliSum:
+    out = []
+    for _ in range(terms):
+        qs = sorted(int(x) for x in rng.choice(n, size=int(rng.integers(1, n + 1)), replace=False))
+        out.append(PauliTerm(float(rng.normal()), (), tuple((q, "XYZ"[int(rng.integers(3))]) for q in qs)))
+    return PauliSum(n, out)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_conjugation_is_the_same_operator(seed: int) -> None:
+    rng = np.random.default_rng(seed)
+    n = 4
+    gates = random_permutation_gates(rng, n, 9)
+    obs = random_pauli_sum(rng, n, 6)
+    P = dense_unitary(gates, n)
+    want = P.conj().T @ dense_pauli_sum(obs) @ P
+    got = dense_pauli_sum(clifford.conjugate_observable(obs, gates))
+    assert np.abs(got - want).max() < 1e-13
+    assert len(clifford.conjugate_observable(obs, gates).terms) == len(obs.terms)
+
+
+def test_split_takes_only_closing_permutation_gates() -> None:
+    b = ProgramBuilder(3)
+    b.RX(0, "a").CNOT(0, 1).RZ(2, "b").CNOT(1, 2).SWAP(0, 2).X(1)
+    prog = b.build()
+    body, gates = clifford.split_trailing_permutation(prog)
+    assert len(gates) == 3 and len(body.ops) == 3 and body.ops[-1].kind == OpKind.RZ
+    b2 = ProgramBuilder(3)
+    b2.RX(0, "a").CRZ(0, 1, "c")
+    assert clifford.split_trailing_permutation(b2.build())[1] == []
+    toffoli = Op(OpKind.MAT1, (2,), (0, 1), matrix=CONST_MATS["X"].copy(), label="Toffoli")
+    assert not clifford.is_permutation_gate(toffoli)  # a permutation, but not a Clifford gate: Pauli strings do not stay strings
+
+
+def test_hea_ladder_turns_total_magnetization_into_prefix_parities() -> None:
+    n = 6
+    prog = hea_program(n, 2)
+    body, gates = clifford.split_trailing_permutation(prog)
+    assert len(gates) == n - 1 and all(g.controls for g in gates)
+    conj = clifford.conjugate_observable(total_magnetization(n), gates)
+    assert all(all(p == "Z" for _, p in t.paulis) for t in conj.terms)
+    rng = np.random.default_rng(0)
+    values = {nm: torch.tensor(rng.uniform(0, 2 * np.pi, size=3)) for nm in prog.param_names}
+    full = oracle.expectation(prog, [total_magnetization(n)], values)
+    trimmed = oracle.expectation(body, [conj], values)
+    assert (full - trimmed).abs().max() < 1e-13
+
+
+def test_engine_absorbs_only_when_it_pays(monkeypatch) -> None:
+    from qadence_b200 import cabi, engine
+
+    try:
+        cabi.load()
+    except cabi.B200svError:
+        pytest.skip("libb200sv.so not built")
+    # cfg2: a sweep would be saved, but Z_tot would become 20 prefix-parity strings (slow Pauli kernels): not absorbed ...
+    big = engine.CompiledProgram(hea_program(20, 8))
+    cob = engine.CompiledObservable(total_magnetization(20))
+    same, cobs = engine.absorb_trailing_permutation(big, [cob])
+    assert same is big and cobs[0] is cob
+    # ... unless forced
+    monkeypatch.setenv("B200SV_ABSORB_PERM", "force")
+    big2 = engine.CompiledProgram(hea_program(20, 8))
+    body, cobs = engine.absorb_trailing_permutation(big2, [cob])
+    assert body is not big2 and len(body.program.ops) == len(big2.program.ops) - 19 and body.names == big2.names
+    assert cobs[0] is not cob and len(cobs[0].obs.terms) == 20
+    assert engine.absorb_trailing_permutation(big2, [cob])[1][0] is cobs[0]  # cached
+    monkeypatch.delenv("B200SV_ABSORB_PERM")
+    # a closing layer of long-range SWAPs costs sweeps and leaves Z_tot a sum of single Z: absorbed
+    b = ProgramBuilder(20)
+    for op in hea_program(20, 2).ops:
+        b._add(op)
+    for q in range(20):
+        b.RX(q, f"last{q}")
+    for q in range(10):
+        b.SWAP(q, 19 - q)
+    sw = engine.CompiledProgram(b.build())
+    body, cobs = engine.absorb_trailing_permutation(sw, [cob])
+    assert body is not sw and all(len(t.paulis) == 1 for t in cobs[0].obs.terms)
+    small = engine.CompiledProgram(hea_program(6, 2))  # one sweep either way: nothing to gain
+    c6 = engine.CompiledObservable(total_magnetization(6))
+    same, cobs6 = engine.absorb_trailing_permutation(small, [c6])
+    assert same is small and cobs6[0] is c6
+    # gradients of the trimmed problem equal the full one (oracle, a smaller instance of the same structure)
+    prog = hea_program(5, 2)
+    bodyp, gates = clifford.split_trailing_permutation(prog)
+    obs = PauliSum(5, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(5)] + [PauliTerm(0.4, (), ((0, "X"), (3, "Y")))])
+    rng = np.random.default_rng(1)
+    values = {nm: torch.tensor(rng.uniform(0, 2 * np.pi, size=2)) for nm in prog.param_names}
+    e1, g1 = oracle.adjoint_expectation_and_grads(prog, obs, values)
+    e2, g2 = oracle.adjoint_expectation_and_grads(bodyp, clifford.conjugate_observable(obs, gates), values)
+    assert (e1 - e2).abs().max() < 1e-13 and max((g1[k] - g2[k]).abs().max() for k in g1) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+def test_gpu_expectation_with_and_without_absorption(monkeypatch, dtype) -> None:
+    """hea(13, 2) on the GPU: the closing ladder is absorbed (it saves a sweep at 2^10-amplitude tiles); values and all
+    gradients equal the oracle's for the FULL circuit, and the run with `B200SV_ABSORB_PERM=0`."""
+    from qadence_b200 import engine
+
+    n, B = 13, 3
+    prog = hea_program(n, 2)
+    obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.5, (), ((1, "X"), (9, "Y"))), PauliTerm(-0.3, (), ((12, "Y"),))])
+    rng = np.random.default_rng(4)
+    base = {nm: torch.tensor(rng.uniform(0, 2 * np.pi, size=B)) for nm in prog.param_names}
+    want_e, want_g = oracle.adjoint_expectation_and_grads(prog, obs, base)
+    tol = 1e-10 if dtype == torch.complex128 else 2e-4
+    results = {}
+    for flag in ("force", "0"):
+        monkeypatch.setenv("B200SV_ABSORB_PERM", flag)
+        cp = engine.CompiledProgram(prog)
+        cob = engine.CompiledObservable(obs)
+        body, _ = engine.absorb_trailing_permutation(cp, [cob])
+        assert (body is not cp) == (flag == "force")
+        values = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        e = engine.expectation(cp, [cob], values, dtype=dtype, device="cuda:0")
+        e.sum().backward()
+        assert (e[:, 0].detach().cpu().double() - want_e).abs().max() < tol
+        assert max((values[k].grad.cpu() - want_g[k]).abs().max() for k in values) < tol
+        results[flag] = e.detach().cpu()
+    assert (results["force"] - results["0"]).abs().max() < tol

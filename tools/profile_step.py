@@ -33,6 +33,7 @@ def main() -> None:
     prog = hea_program(a.n, a.depth)
     cp = engine.CompiledProgram(prog)
     cob = engine.CompiledObservable(total_magnetization(a.n))
+    cp, (cob,) = engine.absorb_trailing_permutation(cp, [cob])  # what engine.expectation runs (B200SV_ABSORB_PERM=0: the full circuit)
     seg = cp.segments[0]
     fwd = cp.device_plan(seg, dtype, False, dev)
     adj = cp.device_plan(seg, dtype, True, dev)

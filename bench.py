@@ -248,8 +248,8 @@ def main() -> None:
         st = _stream_ptr(dev)
         cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st), "init")
         cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
-        e = engine.pauli_expectation(cob.pauli, coef, psi)
-        engine.pauli_apply(cob.pauli, coef, psi, out=lam)
+        e = cob.expectation(psi, {})
+        cob.apply(psi, {}, out=lam)
         grads.zero_()
         cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0, adj.n_sweeps, 0, ws_a, st), "adj")
         return e
@@ -376,7 +376,7 @@ def main() -> None:
     device_step()
     cabi.check(lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st), "init")
     cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
-    engine.pauli_apply(cob.pauli, coef, psi, out=lam)
+    cob.apply(psi, {}, out=lam)
     torch.cuda.synchronize(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(adj.n_sweeps + 1)]
     ev[0].record()
@@ -395,8 +395,8 @@ def main() -> None:
     # the other kernels of the step, each alone (init, <O>, λ = Oψ)
     small = {}
     for nm, fn in (("zero_state", lambda: lib.b200sv_init_zero_state(psi.data_ptr(), _DT[dtype], N_QUBITS, BATCH, st)),
-                   ("pauli_expectation", lambda: engine.pauli_expectation(cob.pauli, coef, psi)),
-                   ("pauli_apply", lambda: engine.pauli_apply(cob.pauli, coef, psi, out=lam))):
+                   ("pauli_expectation", lambda: cob.expectation(psi, {})),
+                   ("pauli_apply", lambda: cob.apply(psi, {}, out=lam))):
         fn()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
@@ -459,8 +459,8 @@ def main() -> None:
         def c64_step():
             cabi.check(lib.b200sv_init_zero_state(psi32.data_ptr(), _DT[d32], N_QUBITS, BATCH, st), "init")
             cabi.check(lib.b200sv_apply_plan(psi32.data_ptr(), _DT[d32], N_QUBITS, BATCH, ptable.data_ptr(), C.byref(f32.struct), 0, f32.n_sweeps, 0, w32f, st), "fwd")
-            e32 = engine.pauli_expectation(cob.pauli, coef, psi32)
-            engine.pauli_apply(cob.pauli, coef, psi32, out=lam32)
+            e32 = cob.expectation(psi32, {})
+            cob.apply(psi32, {}, out=lam32)
             grads.zero_()
             cabi.check(lib.b200sv_adjoint_plan(psi32.data_ptr(), lam32.data_ptr(), _DT[d32], N_QUBITS, BATCH, ptable.data_ptr(), grads.data_ptr(), C.byref(a32.struct), 0, a32.n_sweeps, 0, w32a, st), "adj")
             return e32

@@ -249,7 +249,16 @@ int b200sv_pauli_diagonal(const b200sv_pterm* terms, int n_terms, int n_single, 
                           int n_qubits, int64_t rows, double* out, uint64_t index_hi, void* stream);
 int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dtype, int n_qubits, int64_t batch,
                             const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld, const double* diag,
-                            int64_t diag_ld, double alpha_re, double alpha_im, double beta_re, double beta_im, void* stream);
+                            int64_t diag_ld, const double* diag_scale, double alpha_re, double alpha_im, double beta_re,
+                            double beta_im, void* stream);
+/* ... and the expectation value with the same table: out[b] += Re sum_i conj(psi_i) (Re diag[b][i] psi_i + sum_{X/Y terms} ...).
+ * `diag_scale` above (nullable) is a complex factor [batch][2] of the table per batch element.  Observables with constant
+ * multi-qubit Z strings (Ising / zz_hamiltonian observables, constructors/hamiltonians.py) take this path: the table
+ * (2^n complex numbers, L2-resident for n <= 22) is built once per observable.  Replaces obs.native.expectation
+ * (backends/pyqtorch/backend.py:208,249). */
+int b200sv_pauli_expectation_diag(const void* psi, int dtype, int n_qubits, int64_t batch, const b200sv_pterm* terms,
+                                  int n_terms, const double* coef, int64_t coef_ld, const double* diag, int64_t diag_ld,
+                                  double* out, void* stream);
 
 /* psi[b][i] *= exp(-i t[b] d_b(i)), d_b(i) = sum_t coef[row_t][b] (-1)^{popc(i & zmask_t)} evaluated
  * on the fly from the index bits (all terms must have xmask == 0).  The diagonal Rydberg interaction

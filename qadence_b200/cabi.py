@@ -30,6 +30,7 @@ EXPORTS = [
     "b200sv_pauli_apply",
     "b200sv_pauli_diagonal",
     "b200sv_pauli_apply_diag",
+    "b200sv_pauli_expectation_diag",
     "b200sv_diag_evolve",
     "b200sv_dot",
     "b200sv_axpy",
@@ -108,7 +109,8 @@ def load() -> C.CDLL:
         "b200sv_pauli_expectation": [vp, i32, i32, i64, vp, i32, i32, vp, i64, vp, u64, vp],
         "b200sv_pauli_apply": [vp, vp, vp, i32, i32, i64, vp, i32, i32, vp, i64, f64, f64, f64, f64, u64, vp],
         "b200sv_pauli_diagonal": [vp, i32, i32, vp, i64, i32, i64, vp, u64, vp],
-        "b200sv_pauli_apply_diag": [vp, vp, vp, i32, i32, i64, vp, i32, vp, i64, vp, i64, f64, f64, f64, f64, vp],
+        "b200sv_pauli_apply_diag": [vp, vp, vp, i32, i32, i64, vp, i32, vp, i64, vp, i64, vp, f64, f64, f64, f64, vp],
+        "b200sv_pauli_expectation_diag": [vp, i32, i32, i64, vp, i32, vp, i64, vp, i64, vp, vp],
         "b200sv_diag_evolve": [vp, i32, i32, i64, vp, i32, i32, vp, i64, vp, i64, f64, u64, vp],
         "b200sv_dot": [vp, vp, i32, i32, i64, vp, vp],
         "b200sv_axpy": [vp, vp, vp, i32, i32, i64, vp],

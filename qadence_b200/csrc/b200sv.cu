@@ -617,11 +617,15 @@ __device__ __forceinline__ void diag_tables(const SingleZ& sz, DiagTables* dt, l
 // E[b] += Re sum_i conj(psi_i) sum_t c_t (-1)^{popc(i&z_t)} psi[i^x_t]
 // PEER: psi is this rank's shard of a register sharded by its top qubits; the partner amplitude psi[i ^ x] of a term with
 // X / Y factors on global qubits lives in another rank's shard and is read through NVLink peer memory (pt.p[owner]).
-template <typename c2, bool PEER = false>
+template <typename c2, bool PEER = false, bool DIAG = false>
 __global__ void __launch_bounds__(EXP_THREADS)
 pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b200sv_pterm* __restrict__ terms,
                     int T, int n_single, const double* __restrict__ coef, long long coef_ld, double* __restrict__ out,
-                    unsigned long long index_hi, long long blocks_per_state, const PeerTable pt) {
+                    unsigned long long index_hi, long long blocks_per_state, const PeerTable pt,
+                    const double* __restrict__ diag = nullptr, long long diag_ld = 1) {
+  // DIAG: the real parts of `diag` [diag_ld][2^n] (b200sv_pauli_diagonal) are the weights of ALL diagonal terms; the term list
+  // holds the X / Y terms only.  A constant observable with ZZ.. strings reads 16 bytes of an L2-resident table per amplitude
+  // instead of evaluating every string's parity per amplitude (20 strings on 20 qubits: 5.9 ms -> the stream's 0.7 ms)
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
   __shared__ DiagTables dt;
@@ -646,11 +650,17 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
     // all of the group's amplitudes are requested before the first one is used: the kernel is a pure stream (1·S bytes)
     // and needs several independent 16-byte loads in flight per thread to fill the HBM pipe
     c2 av[PK_K];
+    double dw[DIAG ? PK_K : 1];
+    const double2* dg = DIAG ? reinterpret_cast<const double2*>(diag) + ((diag_ld == 1 ? 0 : b) << n) : nullptr;
 #pragma unroll
     for (int k = 0; k < PK_K; ++k) {
       const long long i = gbase + (long long)k * EXP_THREADS;
       av[k].x = 0; av[k].y = 0;
-      if (i < N) av[k] = __ldcs(p + i);
+      if constexpr (DIAG) dw[k] = 0.0;
+      if (i < N) {
+        av[k] = __ldcs(p + i);
+        if constexpr (DIAG) dw[k] = dg[i].x;
+      }
     }
     const double wg = wt + dt.gr[g];
 #pragma unroll
@@ -659,6 +669,7 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
       if (i >= N) break;
       const c2 a = av[k];
       double wr = wg + dt.kr[k];  // diagonal weight of the single-Z terms
+      if constexpr (DIAG) wr += dw[k];
       double sr = 0.0, si = 0.0;  // off-diagonal sum
       if (T > 0) {
         const unsigned long long gi = (unsigned long long)i | index_hi;
@@ -695,7 +706,9 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
                    const b200sv_pterm* __restrict__ terms, int T, int n_single, const double* __restrict__ coef,
                    long long coef_ld, double ar, double ai, double br, double bi,
                    unsigned long long index_hi, long long blocks_per_state, const PeerTable pt,
-                   const double* __restrict__ diag = nullptr, long long diag_ld = 1) {
+                   const double* __restrict__ diag = nullptr, long long diag_ld = 1, const double* __restrict__ diag_scale = nullptr) {
+  // diag_scale (optional): complex factor [batch][2] of the table per batch element (the adjoint pass weights observable o by
+  // the cotangent of E[b, o]; the term coefficients carry the same factor in `coef`)
   // diag (optional): precomputed complex weights [diag_ld][2^n] of ALL diagonal terms of the sum (b200sv_pauli_diagonal); the
   // term list then holds only the X / Y terms — the Krylov matvec of a Rydberg Hamiltonian (66 ZZ + 12 Z + 12 X terms)
   // evaluates 12 terms per amplitude instead of 90
@@ -739,7 +752,15 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
       if (i >= N) break;
       const c2 a = av[k];
       double wr = wgr + dt.kr[k], wi = wgi + dt.ki[k], sr = 0.0, si = 0.0;
-      if constexpr (DIAG) { wr += dv[k].x; wi += dv[k].y; }
+      if constexpr (DIAG) {
+        if (diag_scale != nullptr) {
+          const double sx = diag_scale[2 * b], sy = diag_scale[2 * b + 1];
+          wr += sx * dv[k].x - sy * dv[k].y;
+          wi += sx * dv[k].y + sy * dv[k].x;
+        } else {
+          wr += dv[k].x; wi += dv[k].y;
+        }
+      }
       if (T > 0) {
         const unsigned long long gi = (unsigned long long)i | index_hi;
         for (int t = 0; t < T; ++t) {
@@ -1292,9 +1313,28 @@ int b200sv_pauli_diagonal(const b200sv_pterm* terms, int n_terms, int n_single, 
   return 0;
 }
 
+int b200sv_pauli_expectation_diag(const void* psi, int dtype, int n, int64_t batch, const b200sv_pterm* terms, int n_terms,
+                                  const double* coef, int64_t coef_ld, const double* diag, int64_t diag_ld, double* out, void* stream) {
+  if (!psi || !out || !diag || batch <= 0 || (coef_ld != 1 && coef_ld != batch) || (diag_ld != 1 && diag_ld != batch)) return B200SV_E_ARG;
+  if (n_terms > 0 && (!terms || !coef)) return B200SV_E_ARG;
+  if (int rc = check_terms(n_terms, 0)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long N = 1ll << n;
+  const long long bps = (N + PK_TILE - 1) / PK_TILE;
+  const long long grid = bps * batch;
+  if (grid > 2147483647ll) return B200SV_E_ARG;
+  if (dtype == B200SV_C128)
+    pauli_expect_kernel<double2, false, true><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const double2*)psi, n, batch, terms, n_terms, 0, coef, coef_ld, out, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+  else if (dtype == B200SV_C64)
+    pauli_expect_kernel<float2, false, true><<<(unsigned)grid, EXP_THREADS, 0, st>>>((const float2*)psi, n, batch, terms, n_terms, 0, coef, coef_ld, out, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+  else return B200SV_E_ARG;
+  LAUNCH_CK();
+  return 0;
+}
+
 int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dtype, int n, int64_t batch,
                             const b200sv_pterm* terms, int n_terms, const double* coef, int64_t coef_ld, const double* diag,
-                            int64_t diag_ld, double ar, double ai, double br, double bi, void* stream) {
+                            int64_t diag_ld, const double* diag_scale, double ar, double ai, double br, double bi, void* stream) {
   if (!psi || !out || psi == out || !diag || batch <= 0 || (coef_ld != 1 && coef_ld != batch) || (diag_ld != 1 && diag_ld != batch)) return B200SV_E_ARG;
   if (n_terms > 0 && (!terms || !coef)) return B200SV_E_ARG;
   if (int rc = check_terms(n_terms, 0)) return rc;
@@ -1305,9 +1345,9 @@ int b200sv_pauli_apply_diag(const void* psi, void* out, const void* acc, int dty
   if (grid > 2147483647ll) return B200SV_E_ARG;
   if (br == 0.0 && bi == 0.0) acc = nullptr;
   if (dtype == B200SV_C128)
-    pauli_apply_kernel<double2, false, true><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+    pauli_apply_kernel<double2, false, true><<<(unsigned)grid, 256, 0, st>>>((const double2*)psi, (double2*)out, (const double2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld, diag_scale);
   else if (dtype == B200SV_C64)
-    pauli_apply_kernel<float2, false, true><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld);
+    pauli_apply_kernel<float2, false, true><<<(unsigned)grid, 256, 0, st>>>((const float2*)psi, (float2*)out, (const float2*)acc, n, batch, terms, n_terms, 0, coef, coef_ld, ar, ai, br, bi, 0ull, bps, PeerTable{}, diag, (long long)diag_ld, diag_scale);
   else return B200SV_E_ARG;
   LAUNCH_CK();
   return 0;

@@ -144,6 +144,30 @@ class CompiledPauliSum:
             self._split = (CompiledPauliSum.build(PauliSum(self.ps.n_qubits, dg)), CompiledPauliSum.build(PauliSum(self.ps.n_qubits, off))) if dg and off else None
         return self._split
 
+    TABLE_MAX_QUBITS = 24  # 2^24 complex weights = 256 MiB; up to n = 22 the table stays in the 126 MB L2
+    TABLE_MIN_AMPLITUDES = 1 << 22  # smaller states: the per-amplitude term loop costs microseconds either way
+
+    def table_split(self) -> "tuple[CompiledPauliSum, CompiledPauliSum | None] | None":
+        """(diagonal part to tabulate, X / Y part or None) when the diagonal part holds CONSTANT multi-qubit Z strings — the
+        terms the Pauli kernels would otherwise evaluate by one parity per term and amplitude (single-Z sums have their own fast
+        path) — and the register is small enough for a table; else None.  Cached."""
+        if not hasattr(self, "_table_split"):
+            self._table_split = None
+            n = self.ps.n_qubits
+            dg = [t for t in self.ps.terms if all(p[1] == "Z" for p in t.paulis)]
+            off = [t for t in self.ps.terms if not all(p[1] == "Z" for p in t.paulis)]
+            if n <= self.TABLE_MAX_QUBITS and sum(1 for t in dg if len(t.paulis) > 1) >= 2 and not any(t.names or t.expr for t in dg):
+                self._table_split = (CompiledPauliSum.build(PauliSum(n, dg)), CompiledPauliSum.build(PauliSum(n, off)) if off else None)
+                self._tables: dict = {}
+        return self._table_split
+
+    def diag_table(self, device: torch.device) -> Tensor:
+        """[1, 2^n, 2] float64 weights of the tabulated diagonal part (built once per device)."""
+        dg = self.table_split()[0]
+        if device not in self._tables:
+            self._tables[device] = pauli_diagonal(dg, dg.coef({}, device), device)
+        return self._tables[device]
+
     @property
     def is_parametric(self) -> bool:
         return any(len(nm) > 0 for nm in self.names)
@@ -389,16 +413,38 @@ def pauli_diagonal(cps: CompiledPauliSum, coef: Tensor, device: torch.device) ->
     return out
 
 
-def pauli_apply_diag(off: CompiledPauliSum, coef_off: Tensor, diag: Tensor, psi: Tensor, out: Tensor | None = None) -> Tensor:
-    """out = diag ⊙ ψ + Σ_{X/Y terms} coef_t P_t ψ  (the Krylov matvec with a tabulated diagonal)."""
-    n = off.ps.n_qubits
+def pauli_apply_diag(off: "CompiledPauliSum | None", coef_off: Tensor | None, diag: Tensor, psi: Tensor, out: Tensor | None = None,
+                     acc: Tensor | None = None, alpha: complex = 1.0, beta: complex = 0.0, diag_scale: Tensor | None = None) -> Tensor:
+    """out = alpha·(s_b·diag ⊙ ψ + Σ_{X/Y terms} coef_t P_t ψ) + beta·acc  (the Krylov matvec with a tabulated diagonal; the
+    adjoint pass's λ = Σ_o ḡ·O_o ψ for observables with a tabulated diagonal part: `diag_scale` = s [B] complex128)."""
+    n = int(psi.shape[1]).bit_length() - 1
     B = psi.shape[0]
     dev = psi.device
     out = torch.empty_like(psi) if out is None else out
-    cf = torch.view_as_real(coef_off.detach().to(torch.complex128).contiguous())
-    rc = cabi.load().b200sv_pauli_apply_diag(psi.data_ptr(), out.data_ptr(), 0, _DT[psi.dtype], n, B, off.terms(dev).data_ptr(), off.n_terms, cf.data_ptr(),
-                                             coef_off.shape[1], diag.data_ptr(), diag.shape[0], 1.0, 0.0, 0.0, 0.0, _stream_ptr(dev))
+    nt = 0 if off is None else off.n_terms
+    cf = torch.view_as_real(coef_off.detach().to(torch.complex128).contiguous()) if nt else None
+    ds = torch.view_as_real(diag_scale.detach().to(torch.complex128).contiguous()) if diag_scale is not None else None
+    a, b_ = complex(alpha), complex(beta)
+    rc = cabi.load().b200sv_pauli_apply_diag(psi.data_ptr(), out.data_ptr(), acc.data_ptr() if acc is not None else 0, _DT[psi.dtype], n, B,
+                                             off.terms(dev).data_ptr() if nt else 0, nt, cf.data_ptr() if nt else 0,
+                                             coef_off.shape[1] if nt else 1, diag.data_ptr(), diag.shape[0], ds.data_ptr() if ds is not None else 0,
+                                             a.real, a.imag, b_.real, b_.imag, _stream_ptr(dev))
     cabi.check(rc, "pauli_apply_diag")
+    return out
+
+
+def pauli_expectation_diag(off: "CompiledPauliSum | None", coef_off: Tensor | None, diag: Tensor, psi: Tensor) -> Tensor:
+    """[B] float64: Re⟨ψ|(diag + Σ_{X/Y terms} coef_t P_t)|ψ⟩ with the diagonal part tabulated (`pauli_diagonal`)."""
+    n = int(psi.shape[1]).bit_length() - 1
+    B = psi.shape[0]
+    dev = psi.device
+    out = torch.zeros(B, dtype=torch.float64, device=dev)
+    nt = 0 if off is None else off.n_terms
+    cf = torch.view_as_real(coef_off.detach().to(torch.complex128).contiguous()) if nt else None
+    rc = cabi.load().b200sv_pauli_expectation_diag(psi.data_ptr(), _DT[psi.dtype], n, B, off.terms(dev).data_ptr() if nt else 0, nt,
+                                                   cf.data_ptr() if nt else 0, coef_off.shape[1] if nt else 1, diag.data_ptr(), diag.shape[0],
+                                                   out.data_ptr(), _stream_ptr(dev))
+    cabi.check(rc, "pauli_expectation_diag")
     return out
 
 
@@ -566,16 +612,27 @@ class CompiledObservable:
     def names(self) -> list[str]:
         return self.pauli.ps.param_names if self.pauli is not None else self.program.names
 
-    def apply(self, psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
-        """λ = O ψ (new tensor)."""
+    def apply(self, psi: Tensor, values: Mapping[str, Tensor], out: Tensor | None = None) -> Tensor:
+        """λ = O ψ (a new tensor, or `out` for Pauli-sum observables)."""
         if self.pauli is not None:
-            return pauli_apply(self.pauli, self.pauli.coef(values, psi.device), psi)
+            if self.uses_table(psi):
+                dg, off = self.pauli.table_split()
+                return pauli_apply_diag(off, off.coef(values, psi.device) if off is not None else None, self.pauli.diag_table(psi.device), psi, out=out)
+            return pauli_apply(self.pauli, self.pauli.coef(values, psi.device), psi, out=out)
         tmp = psi.clone()
         tab = pack_params(self.program.names, values, psi.shape[0], psi.device)
         return _run_segments(self.program, tmp, tab, values)
 
+    def uses_table(self, psi: Tensor) -> bool:
+        """Constant multi-qubit Z strings on a large state: tabulated diagonal (`CompiledPauliSum.table_split`)."""
+        return (self.pauli is not None and psi.numel() >= CompiledPauliSum.TABLE_MIN_AMPLITUDES and os.environ.get("B200SV_DIAG_TABLE", "1") != "0"
+                and self.pauli.table_split() is not None)
+
     def expectation(self, psi: Tensor, values: Mapping[str, Tensor]) -> Tensor:
         if self.pauli is not None:
+            if self.uses_table(psi):
+                dg, off = self.pauli.table_split()
+                return pauli_expectation_diag(off, off.coef(values, psi.device) if off is not None else None, self.pauli.diag_table(psi.device), psi)
             return pauli_expectation(self.pauli, self.pauli.coef(values, psi.device), psi)
         return dot(psi, self.apply(psi, values)).real
 
@@ -636,7 +693,16 @@ def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], v
         go = grad_out.to(torch.float64)
         for o, cob in enumerate(cobs):
             w = go[:, o].to(torch.complex128)
-            if cob.pauli is not None:
+            if cob.pauli is not None and cob.uses_table(psi):
+                dg, off = cob.pauli.table_split()
+                coef = None
+                if off is not None:
+                    coef = off.coef(values, dev)
+                    coef = coef.expand(coef.shape[0], B) * w[None, :]
+                new = torch.empty_like(psi)
+                pauli_apply_diag(off, coef, cob.pauli.diag_table(dev), psi, out=new, acc=lam, alpha=1.0, beta=0.0 if lam is None else 1.0, diag_scale=w)
+                lam = new
+            elif cob.pauli is not None:
                 coef = cob.pauli.coef(values, dev)
                 coef = coef.expand(coef.shape[0], B) * w[None, :]
                 if lam is None:
@@ -773,10 +839,11 @@ def absorb_trailing_permutation(cp: CompiledProgram, cobs: Sequence["CompiledObs
     """(cp', observables') with the same expectation values and gradients: the X / CNOT / SWAP gates that close the circuit are
     conjugated into the Pauli-sum observables (`clifford.py`) when that (1) saves a state round trip — the plan of the circuit
     without them has fewer sweeps — and (2) does not make the observable more expensive: no observable may end up with more
-    terms outside the single-Z fast path of the Pauli kernels than it had.  (2) excludes the case that motivated this — the
-    closing CNOT ladder of cfg2's HEA turns Z_tot into 20 prefix-parity strings: measured 1.9 ms saved in the sweeps, 10.6 ms
-    lost in <O> and λ = Oψ, profiles/r02_lean_kernel.md §9 — and keeps closing SWAP / X layers and CNOTs whose targets the
-    observable does not touch.  `B200SV_ABSORB_PERM=0` disables it, `=force` skips (2).  Cached on `cp`."""
+    terms that the Pauli kernels evaluate one parity at a time (anything but single-Z terms and CONSTANT Z strings, which are
+    tabulated: `CompiledPauliSum.table_split`).  The closing CNOT ladder of cfg2's HEA turns Z_tot into 20 prefix-parity strings
+    Z_0⋯Z_q: absorbed thanks to the table (without it: 1.9 ms saved in the sweeps, 10.6 ms lost in <O> and λ = Oψ,
+    profiles/r02_lean_kernel.md §9); the same ladder under an observable with parametric coefficients is not.
+    `B200SV_ABSORB_PERM=0` disables it, `=force` skips (2).  Cached on `cp`."""
     from . import clifford
 
     cobs = list(cobs)
@@ -798,15 +865,17 @@ def absorb_trailing_permutation(cp: CompiledProgram, cobs: Sequence["CompiledObs
     body_cp, gates = cp._absorb
     if body_cp is None:
         return cp, cobs
-    def slow_terms(ps: PauliSum) -> int:
-        return sum(1 for t in ps.terms if not (len(t.paulis) == 1 and t.paulis[0][1] == "Z"))
+    def slow_terms(co: "CompiledObservable") -> int:
+        if co.pauli.table_split() is not None:  # the whole diagonal part is one table read
+            return sum(1 for t in co.obs.terms if not all(p[1] == "Z" for p in t.paulis))
+        return sum(1 for t in co.obs.terms if not (len(t.paulis) == 1 and t.paulis[0][1] == "Z"))
 
     out = []
     for c in cobs:
         hit = cp._absorb_obs.get(id(c))
         if hit is None or hit[0] is not c:
-            conj = clifford.conjugate_observable(c.obs, gates)
-            hit = (c, CompiledObservable(conj) if (mode == "force" or slow_terms(conj) <= slow_terms(c.obs)) else None)
+            conj = CompiledObservable(clifford.conjugate_observable(c.obs, gates))
+            hit = (c, conj if (mode == "force" or slow_terms(conj) <= slow_terms(c)) else None)
             if len(cp._absorb_obs) > 64:
                 cp._absorb_obs.clear()
             cp._absorb_obs[id(c)] = hit

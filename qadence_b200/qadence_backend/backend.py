@@ -131,8 +131,9 @@ class NativeCircuit:
             """`QuantumModel.to()` moves the model only `if isinstance(native, pyqtorch.QuantumCircuit)` (qadence/model.py:651);
             isinstance falls back to `__class__`, `type(obj)` (used by copy / pickle) is untouched."""
             try:
-                from pyqtorch import QuantumCircuit as PyQCircuit
+                import pyqtorch
 
+                PyQCircuit = pyqtorch.DropoutQuantumCircuit if self.dropout_prob > 0.0 else pyqtorch.QuantumCircuit  # backend.py:127-141
                 return PyQCircuit if isinstance(PyQCircuit, type) else NativeCircuit
             except Exception:
                 return NativeCircuit

@@ -7,7 +7,15 @@ class _Unavailable:
         raise RuntimeError("pyqtorch is not installed; tests/_shims provides names only")
 
 
-QuantumCircuit = DropoutQuantumCircuit = Observable = _Unavailable
+class QuantumCircuit(_Unavailable):
+    pass
+
+
+class DropoutQuantumCircuit(QuantumCircuit):
+    pass
+
+
+Observable = _Unavailable
 Scale = Sequence = Add = Merge = HamiltonianEvolution = _Unavailable
 
 

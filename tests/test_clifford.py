@@ -100,18 +100,22 @@ def test_engine_absorbs_only_when_it_pays(monkeypatch) -> None:
         cabi.load()
     except cabi.B200svError:
         pytest.skip("libb200sv.so not built")
-    # cfg2: a sweep would be saved, but Z_tot would become 20 prefix-parity strings (slow Pauli kernels): not absorbed ...
+    # cfg2: a sweep is saved and Z_tot becomes 20 CONSTANT prefix-parity strings, which the Pauli kernels read from a table
     big = engine.CompiledProgram(hea_program(20, 8))
     cob = engine.CompiledObservable(total_magnetization(20))
-    same, cobs = engine.absorb_trailing_permutation(big, [cob])
-    assert same is big and cobs[0] is cob
+    body, cobs = engine.absorb_trailing_permutation(big, [cob])
+    assert body is not big and len(body.program.ops) == len(big.program.ops) - 19 and body.names == big.names
+    assert cobs[0] is not cob and len(cobs[0].obs.terms) == 20 and cobs[0].pauli.table_split() is not None
+    assert engine.absorb_trailing_permutation(big, [cob])[1][0] is cobs[0]  # cached
+    # the same ladder under an observable with PARAMETRIC coefficients would put 19 strings on the slow path: not absorbed ...
+    pobs = engine.CompiledObservable(PauliSum(20, [PauliTerm(1.0, (f"w{q}",), ((q, "Z"),)) for q in range(20)]))
+    same, pc = engine.absorb_trailing_permutation(big, [pobs])
+    assert same is big and pc[0] is pobs
     # ... unless forced
     monkeypatch.setenv("B200SV_ABSORB_PERM", "force")
     big2 = engine.CompiledProgram(hea_program(20, 8))
-    body, cobs = engine.absorb_trailing_permutation(big2, [cob])
-    assert body is not big2 and len(body.program.ops) == len(big2.program.ops) - 19 and body.names == big2.names
-    assert cobs[0] is not cob and len(cobs[0].obs.terms) == 20
-    assert engine.absorb_trailing_permutation(big2, [cob])[1][0] is cobs[0]  # cached
+    body2, pc2 = engine.absorb_trailing_permutation(big2, [pobs])
+    assert body2 is not big2 and pc2[0] is not pobs
     monkeypatch.delenv("B200SV_ABSORB_PERM")
     # a closing layer of long-range SWAPs costs sweeps and leaves Z_tot a sum of single Z: absorbed
     b = ProgramBuilder(20)
@@ -142,12 +146,12 @@ def test_engine_absorbs_only_when_it_pays(monkeypatch) -> None:
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
 def test_gpu_expectation_with_and_without_absorption(monkeypatch, dtype) -> None:
-    """hea(13, 2) on the GPU: the closing ladder is absorbed (it saves a sweep at 2^10-amplitude tiles); values and all
+    """hea(17, 3) on the GPU: the closing ladder is absorbed (it saves a sweep at 2^10-amplitude tiles: 4 -> 3); values and all
     gradients equal the oracle's for the FULL circuit, and the run with `B200SV_ABSORB_PERM=0`."""
     from qadence_b200 import engine
 
-    n, B = 13, 3
-    prog = hea_program(n, 2)
+    n, B = 17, 2
+    prog = hea_program(n, 3)
     obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.5, (), ((1, "X"), (9, "Y"))), PauliTerm(-0.3, (), ((12, "Y"),))])
     rng = np.random.default_rng(4)
     base = {nm: torch.tensor(rng.uniform(0, 2 * np.pi, size=B)) for nm in prog.param_names}
@@ -167,3 +171,47 @@ def test_gpu_expectation_with_and_without_absorption(monkeypatch, dtype) -> None
         assert max((values[k].grad.cpu() - want_g[k]).abs().max() for k in values) < tol
         results[flag] = e.detach().cpu()
     assert (results["force"] - results["0"]).abs().max() < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
+def test_gpu_tabulated_diagonal_observables(monkeypatch, dtype) -> None:
+    """Observables with constant ZZ.. strings on a state of >= 2^22 amplitudes take the tabulated-diagonal kernels
+    (`b200sv_pauli_expectation_diag`, `b200sv_pauli_apply_diag` with a per-batch scale): expectation values and gradients of TWO
+    observables with different cotangents equal the oracle's and the term-by-term kernels' (`B200SV_DIAG_TABLE=0`)."""
+    from qadence_b200 import engine
+
+    n, B = 11, 2048  # 2^22 amplitudes
+    prog = hea_program(n, 1)
+    ising = PauliSum(n, [PauliTerm(0.7 + 0.1 * q, (), ((q, "Z"), (q + 1, "Z"))) for q in range(n - 1)] + [PauliTerm(0.3, (), ((q, "Z"),)) for q in range(n)]
+                     + [PauliTerm(0.25, (), ((0, "X"), (5, "X"))), PauliTerm(-0.4, (), ((2, "Y"),))])
+    parity = PauliSum(n, [PauliTerm(1.0, (), tuple((q, "Z") for q in range(k + 1))) for k in range(n)])
+    rng = np.random.default_rng(8)
+    base = {nm: torch.tensor(rng.uniform(0, 2 * np.pi, size=B)) for nm in prog.param_names}
+    wts = torch.tensor(rng.normal(size=(B, 2)))
+    tol = 1e-10 if dtype == torch.complex128 else 3e-4
+    cols = [0, 1, B - 1]
+    sub = {k: v[cols] for k, v in base.items()}
+    want = oracle.expectation(prog, [ising, parity], sub)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("B200SV_DIAG_TABLE", flag)
+        cp = engine.CompiledProgram(prog)
+        cobs = [engine.CompiledObservable(ising), engine.CompiledObservable(parity)]
+        values = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        e = engine.expectation(cp, cobs, values, dtype=dtype, device="cuda:0")
+        psi_probe = torch.empty(B, 1 << n, dtype=dtype, device="cuda:0")
+        assert cobs[0].uses_table(psi_probe) == (flag == "1")
+        (e.cpu().double() * wts).sum().backward()
+        assert (e[cols].detach().cpu().double() - want).abs().max() < tol
+        out[flag] = (e.detach().cpu().double(), torch.stack([values[k].grad for k in values]))
+    assert (out["1"][0] - out["0"][0]).abs().max() < tol
+    assert (out["1"][1] - out["0"][1]).abs().max() < 10 * tol
+    # gradients against the oracle for the sampled batch elements
+    g_want = {k: 0 for k in base}
+    for o, obs in enumerate((ising, parity)):
+        _, g = oracle.adjoint_expectation_and_grads(prog, obs, sub)
+        for k in g:
+            g_want[k] = g_want[k] + g[k] * wts[cols, o]
+    got = {k: out["1"][1][i][cols] for i, k in enumerate(base)}
+    assert max((got[k] - g_want[k]).abs().max() for k in base) < 10 * tol

@@ -52,8 +52,8 @@ def main() -> None:
         ev[0].record()
         cabi.check(lib.b200sv_apply_plan(psi.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), C.byref(fwd.struct), 0, fwd.n_sweeps, 0, ws_f, st), "fwd")
         ev[1].record()
-        e = engine.pauli_expectation(cob.pauli, coef, psi)
-        engine.pauli_apply(cob.pauli, coef, psi, out=lam)
+        e = cob.expectation(psi, {})
+        cob.apply(psi, {}, out=lam)
         grads.zero_()
         ev[2].record()
         cabi.check(lib.b200sv_adjoint_plan(psi.data_ptr(), lam.data_ptr(), _DT[dtype], a.n, a.batch, ptable.data_ptr(), grads.data_ptr(), C.byref(adj.struct), 0,

@@ -630,8 +630,11 @@ pauli_expect_kernel(const c2* __restrict__ psi, int n, long long batch, const b2
   __shared__ SingleZ sz;
   __shared__ DiagTables dt;
   __shared__ double red[32];
-  const long long b = blockIdx.x / blocks_per_state;
-  const long long blk = blockIdx.x % blocks_per_state;
+  // DIAG with one table for the whole batch: consecutive CTAs take the SAME index range of consecutive batch elements, so a
+  // table slice is read from DRAM once and served from L2 for the rest of the batch
+  const bool b_inner = DIAG && diag_ld == 1;
+  const long long b = b_inner ? blockIdx.x % batch : blockIdx.x / blocks_per_state;
+  const long long blk = b_inner ? blockIdx.x / batch : blockIdx.x % blocks_per_state;
   resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
   T -= n_single;
@@ -715,8 +718,9 @@ pauli_apply_kernel(const c2* __restrict__ psi, c2* out, const c2* acc, int n, lo
   __shared__ TermS sh[MAX_TERMS_SMEM];
   __shared__ SingleZ sz;
   __shared__ DiagTables dt;
-  const long long b = blockIdx.x / blocks_per_state;
-  const long long blk = blockIdx.x % blocks_per_state;
+  const bool b_inner = DIAG && diag_ld == 1;  // see pauli_expect_kernel
+  const long long b = b_inner ? blockIdx.x % batch : blockIdx.x / blocks_per_state;
+  const long long blk = b_inner ? blockIdx.x / batch : blockIdx.x % blocks_per_state;
   resolve_terms(sh, terms, T, coef, coef_ld, b, &sz, n_single);
   __syncthreads();
   T -= n_single;

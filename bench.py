@@ -467,7 +467,6 @@ def main() -> None:
 
         e32 = c64_step()
         err32 = float((e32.reshape(-1).double() - e_dev.reshape(-1)).abs().max())
-        g32_err = None
         ms32 = timed(c64_step, 3) / 3
         c64 = {"ms_per_step": ms32, "evals_per_s": BATCH / (ms32 * 1e-3), "speedup_vs_complex128": ms_per_step / ms32,
                "fwd_sweeps": f32.n_sweeps, "adj_sweeps": a32.n_sweeps, "tiles": {"forward": [f32.plan.cfg.m, f32.plan.cfg.r], "adjoint": [a32.plan.cfg.m, a32.plan.cfg.r]},

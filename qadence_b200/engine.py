@@ -673,14 +673,22 @@ class _AdjointExpectation(torch.autograd.Function):
             # create_graph=True: hand out a gradient that can itself be differentiated (DQC-style losses)
             grads = _AdjointGradient.apply(ctx.cp, ctx.cobs, ctx.values, ctx.state, ctx.dtype, ctx.batch, ptable, grad_out)
         else:
-            grads = _adjoint_gradient(ctx.cp, ctx.cobs, ctx.values, ctx.batch, ptable, grad_out, ctx.psi, ctx.grad_names)
+            # the adjoint walk un-applies the circuit IN PLACE on the saved wavefunction (no 2^n·B copy per step); a second
+            # backward pass over a retained graph finds it consumed and recomputes it
+            psi, ctx.psi = ctx.psi, None
+            if psi is None:
+                with torch.no_grad():
+                    st = prepare_state(ctx.cp.n_qubits, ctx.batch, ctx.state, ctx.dtype, ptable.device)
+                    psi = _run_segments(ctx.cp, st, ptable.detach(), ctx.values)
+            grads = _adjoint_gradient(ctx.cp, ctx.cobs, ctx.values, ctx.batch, ptable, grad_out, psi, ctx.grad_names)
         return None, None, None, None, None, None, None, grads
 
 
 def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], values: Mapping[str, Any], B: int, ptable: Tensor,
                       grad_out: Tensor, psi: Tensor, grad_names: set | None = None) -> Tensor:
     """`[n_slots, B]` vector-Jacobian product Σ_o ḡ[b,o]·∂E[b,o]/∂θ[slot,b] by the adjoint method: λ = Σ_o ḡ·O_o ψ, then
-    one backward walk (`_adjoint_walk`) that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps."""
+    one backward walk (`_adjoint_walk`) that un-applies the circuit on ψ and λ and reduces every gate's gradient in the same sweeps.
+    CONSUMES `psi` (un-applied in place)."""
     dev = psi.device
     with torch.no_grad():
         if not cp.invertible:
@@ -715,7 +723,6 @@ def _adjoint_gradient(cp: CompiledProgram, cobs: Sequence[CompiledObservable], v
                 t = cob.apply(psi, values)
                 scal(w, t)
                 lam = t if lam is None else lam + t
-        psi = psi.clone()  # keep ctx.psi intact for double calls of backward(retain_graph=True)
     return _adjoint_walk(cp, values, B, ptable, psi, lam, grad_names)[0]
 
 

@@ -95,6 +95,23 @@ def test_hea_expectation_and_adjoint(n: int, depth: int, batch: int, dtype: torc
         assert (values[k].grad.cpu() - want).abs().max().item() <= tol * 10, k
 
 
+def test_second_backward_over_a_retained_graph() -> None:
+    """The first backward pass consumes the saved wavefunction (the adjoint walk un-applies the circuit in place); a second
+    pass over a retained graph recomputes it and must give the same gradients again."""
+    n, batch = 9, 3
+    prog = hea_program(n, 2)
+    g = torch.Generator().manual_seed(5)
+    values = {nm: (2 * torch.pi * torch.rand(batch, generator=g, dtype=torch.float64)).requires_grad_(True) for nm in prog.param_names}
+    out = engine.expectation(engine.CompiledProgram(prog), [engine.CompiledObservable(total_magnetization(n))], values, device="cuda:0")
+    out.sum().backward(retain_graph=True)
+    first = {k: v.grad.clone() for k, v in values.items()}
+    out.sum().backward()
+    _, want = oracle.adjoint_expectation_and_grads(prog, total_magnetization(n), {k: v.detach() for k, v in values.items()})
+    for k in values:
+        assert (first[k].cpu() - want[k]).abs().max().item() <= 1e-10, k
+        assert (values[k].grad.cpu() - 2 * want[k]).abs().max().item() <= 2e-10, k
+
+
 def test_shared_and_scalar_parameters() -> None:
     """`[1]`-shaped (shared) parameters: autograd sum-reduces the per-batch gradients."""
     n, batch = 5, 6

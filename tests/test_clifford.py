@@ -100,20 +100,25 @@ def test_engine_absorbs_only_when_it_pays(monkeypatch) -> None:
         cabi.load()
     except cabi.B200svError:
         pytest.skip("libb200sv.so not built")
-    # cfg2: a sweep is saved and Z_tot becomes 20 CONSTANT prefix-parity strings, which the Pauli kernels read from a table
-    big = engine.CompiledProgram(hea_program(20, 8))
+    # hea(20, 3): the closing ladder costs a sweep of its own (4 -> 3) and Z_tot becomes 20 CONSTANT prefix-parity strings, which the
+    # Pauli kernels read from a table: absorbed
+    big = engine.CompiledProgram(hea_program(20, 3))
     cob = engine.CompiledObservable(total_magnetization(20))
     body, cobs = engine.absorb_trailing_permutation(big, [cob])
     assert body is not big and len(body.program.ops) == len(big.program.ops) - 19 and body.names == big.names
     assert cobs[0] is not cob and len(cobs[0].obs.terms) == 20 and cobs[0].pauli.table_split() is not None
     assert engine.absorb_trailing_permutation(big, [cob])[1][0] is cobs[0]  # cached
+    # cfg2 (depth 8): the planner folds the ladder into the other sweeps (8 sweeps either way): nothing to gain, Z_tot stays single-Z
+    cfg2 = engine.CompiledProgram(hea_program(20, 8))
+    same, c2 = engine.absorb_trailing_permutation(cfg2, [cob])
+    assert same is cfg2 and c2[0] is cob
     # the same ladder under an observable with PARAMETRIC coefficients would put 19 strings on the slow path: not absorbed ...
     pobs = engine.CompiledObservable(PauliSum(20, [PauliTerm(1.0, (f"w{q}",), ((q, "Z"),)) for q in range(20)]))
     same, pc = engine.absorb_trailing_permutation(big, [pobs])
     assert same is big and pc[0] is pobs
     # ... unless forced
     monkeypatch.setenv("B200SV_ABSORB_PERM", "force")
-    big2 = engine.CompiledProgram(hea_program(20, 8))
+    big2 = engine.CompiledProgram(hea_program(20, 3))
     body2, pc2 = engine.absorb_trailing_permutation(big2, [pobs])
     assert body2 is not big2 and pc2[0] is not pobs
     monkeypatch.delenv("B200SV_ABSORB_PERM")
@@ -146,11 +151,11 @@ def test_engine_absorbs_only_when_it_pays(monkeypatch) -> None:
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.complex128, torch.complex64])
 def test_gpu_expectation_with_and_without_absorption(monkeypatch, dtype) -> None:
-    """hea(17, 3) on the GPU: the closing ladder is absorbed (it saves a sweep at 2^10-amplitude tiles: 4 -> 3); values and all
+    """hea(18, 3) on the GPU: the closing ladder is absorbed (it saves a sweep at 2^10-amplitude tiles: 4 -> 3); values and all
     gradients equal the oracle's for the FULL circuit, and the run with `B200SV_ABSORB_PERM=0`."""
     from qadence_b200 import engine
 
-    n, B = 17, 2
+    n, B = 18, 1
     prog = hea_program(n, 3)
     obs = PauliSum(n, [PauliTerm(1.0, (), ((q, "Z"),)) for q in range(n)] + [PauliTerm(0.5, (), ((1, "X"), (9, "Y"))), PauliTerm(-0.3, (), ((12, "Y"),))])
     rng = np.random.default_rng(4)

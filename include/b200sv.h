@@ -149,12 +149,16 @@ typedef struct b200sv_tma {  /* 24 bytes */
 
 /* Lean index tables: B200SV_LT_STRIDE uint32 words per round and direction (built by qadence_b200/plan.py).
  *   [0,16)  XOR contribution of thread-index bits 0..3 (entry v = XOR over the set bits of v), [16,32) of bits 4..7:
- *           low 16 bits = byte offset on the LOAD side of the round, high 16 bits = on the STORE side
- *           (forward: load = plain index, store = permuted index; backward: the other way round);
- *   [32,37) contribution of register bit a;   [37] bit 0: barrier needed between the round's loads and stores;
+ *           low 16 bits = byte offset on the LOAD side of the round, high 16 bits = on the STORE side.  The kernel only
+ *           follows these offsets; the planner decides what they mean: either every round applies its folded X / CNOT / SWAP
+ *           permutation physically (forward: load = plain index, store = permuted index; backward: the other way round),
+ *           or the permutations are tracked — a round loads the amplitude of position x from S_k(x) and stores it in place,
+ *           S_{k+1} = S_k o pi_k^-1, and only the last round of the sweep stores to the true positions (default);
+ *   [32,37) contribution of register bit a;   [37] bit 0: some thread stores where another one loads, i.e. a barrier is
+ *           needed between the round's loads and stores;
  *   [38,43) resolved-entry index (relative to the sweep) of register bit a's merged 2x2, or 0xffff;
- *   [43]    n_pext | bit_k << (8 + 6k): external control bits of the permutation;  [44,48) their XOR vectors, already
- *           placed in the half (load / store) the permuted side occupies. */
+ *   [43]    n_ext | bit_k << (8 + 6k): index bits outside the tile (controls of folded CNOTs) whose value shifts the
+ *           offsets of this round;  [44,48) their XOR vectors (load half and store half like the entries above). */
 #define B200SV_LT_STRIDE 48
 
 /* Device-resident plan: the three arrays above plus the constant pool, uploaded once at convert

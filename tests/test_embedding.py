@@ -140,3 +140,35 @@ def test_gpu_param_table_feeds_the_engine() -> None:
     assert (xs.grad - xh.grad).abs().max() < 1e-10
     want = oracle.expectation(prog, [total_magnetization(n)], {k: t.detach().cpu() for k, t in vals.items()})
     assert (e.detach().cpu() - want).abs().max() < 1e-10
+
+
+def test_packed_feature_rows_are_one_autograd_node_with_the_gradients_of_a_stack() -> None:
+    """`embedding._PackRows` (host side of the plugin's input path): same values and gradients as `torch.stack(...)` for rows of
+    every accepted shape — [batch], [1], 0-dim, [batch, 1], float32 — including rows that do not ask for a gradient."""
+    from qadence_b200.embedding import _PackRows
+
+    B = 5
+    g = torch.Generator().manual_seed(3)
+    rows = [torch.rand(B, generator=g, dtype=torch.float64).requires_grad_(True), torch.rand(1, generator=g, dtype=torch.float64).requires_grad_(True),
+            torch.tensor(0.7, dtype=torch.float64, requires_grad=True), torch.rand(B, 1, generator=g, dtype=torch.float64).requires_grad_(True),
+            torch.rand(B, generator=g, dtype=torch.float32).requires_grad_(True), torch.rand(B, generator=g, dtype=torch.float64)]
+    w = torch.rand(len(rows), B, generator=g, dtype=torch.float64)
+    out = _PackRows.apply(torch.device("cpu"), B, *rows)
+    assert out.shape == (len(rows), B) and out.dtype == torch.float64 and out.grad_fn is not None
+    (out * w).sum().backward()
+    got = [None if r.grad is None else r.grad.clone() for r in rows]
+    for r in rows:
+        r.grad = None
+    ref = torch.stack([r.reshape(-1).to(torch.float64).expand(B) for r in rows])
+    assert torch.equal(ref.detach(), out.detach())
+    (ref * w).sum().backward()
+    for a, r in zip(got, rows):
+        assert (a is None) == (r.grad is None)
+        if a is not None:
+            assert a.shape == r.shape and a.dtype == r.dtype and torch.allclose(a, r.grad, atol=1e-6 if r.dtype == torch.float32 else 1e-14)
+    # the common case (all rows [batch] float64) takes the single-copy path and keeps ONE node for all inputs
+    plain = [torch.rand(B, generator=g, dtype=torch.float64).requires_grad_(True) for _ in range(4)]
+    o2 = _PackRows.apply(torch.device("cpu"), B, *plain)
+    assert type(o2.grad_fn).__name__ == "_PackRowsBackward" and len(o2.grad_fn.next_functions) == len(plain)  # straight to the leaves
+    o2.sum().backward()
+    assert all(torch.equal(p.grad, torch.ones(B, dtype=torch.float64)) for p in plain)
